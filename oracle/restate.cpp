@@ -849,8 +849,9 @@ V3 PathTrace(const Ctx& cx, Ray ray, uint32_t pixel, uint32_t sample, int row, i
     for (uint32_t node = 1; (int)node <= max_depth + 1; node++) {
         Hit h = FindIntersection(cx, ray);
         if (!h.full) {
-            if (node == 1) L = L + cmul(beta, Background(cx, row, col, ray));
-            else if (s->env_light_index != -1 && (count_emission || !cx.opts.pt_nee)) L = L + cmul(beta, Background(cx, row, col, ray));
+            // background lookup convention of the renderer: transposed pixel-uv at 1 spp, as the kernels do
+            int br = cx.spp <= 1 ? col : row, bc = cx.spp <= 1 ? row : col;
+            if (node == 1 || (s->env_light_index != -1 && (count_emission || !cx.opts.pt_nee))) L = L + cmul(beta, Background(cx, br, bc, ray));
             break;
         }
         const RtMaterial& mat = s->materials[h.matIndex - 1];

@@ -1,0 +1,162 @@
+#include "bvh_build.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+namespace rt795 {
+namespace {
+
+constexpr int kBins = 16;
+constexpr float kTraversalCost = 1.0f, kIntersectCost = 1.0f;
+constexpr int kMaxDepth = 36;   // deeper subtrees fall back to median splits (depth <= 36 + log2 n); core.cu checks TLAS+BLAS depth against the traversal stack
+
+struct Tmp {
+    Aabb box;
+    int left = -1, right = -1;    // Tmp indices, or -1
+    int first = 0, count = 0;     // leaf range in `order`
+    bool leaf = false;
+};
+
+struct Builder {
+    const Aabb* pb;
+    std::vector<int32_t>& order;
+    std::vector<float> cen;       // centroids, 3 per primitive
+    std::vector<Tmp> tmp;
+    int max_leaf;
+    int max_depth = 0;
+
+    Builder(const Aabb* b, int n, int ml, std::vector<int32_t>& ord) : pb(b), order(ord), max_leaf(ml) {
+        cen.resize((size_t)n * 3);
+        for (int i = 0; i < n; i++)
+            for (int k = 0; k < 3; k++) cen[(size_t)i * 3 + k] = 0.5f * (b[i].lo[k] + b[i].hi[k]);
+    }
+
+    int Build(int first, int count, int depth) {
+        max_depth = std::max(max_depth, depth);
+        int me = (int)tmp.size();
+        tmp.emplace_back();
+        Aabb box, cbox;
+        box.Reset(); cbox.Reset();
+        for (int i = first; i < first + count; i++) { box.Grow(pb[order[i]]); cbox.Grow(&cen[(size_t)order[i] * 3]); }
+        tmp[me].box = box;
+        auto make_leaf = [&]() { tmp[me].leaf = true; tmp[me].first = first; tmp[me].count = count; return me; };
+        if (count <= 1) return make_leaf();
+
+        int mid = -1;
+        if (depth < kMaxDepth) {
+            // binned SAH over the three axes
+            float best_cost = std::numeric_limits<float>::max();
+            int best_axis = -1, best_split = -1;
+            for (int axis = 0; axis < 3; axis++) {
+                float lo = cbox.lo[axis], ext = cbox.hi[axis] - lo;
+                if (!(ext > 0)) continue;
+                float scale = kBins / ext;
+                Aabb bb[kBins];
+                int bc[kBins];
+                for (int b = 0; b < kBins; b++) { bb[b].Reset(); bc[b] = 0; }
+                for (int i = first; i < first + count; i++) {
+                    int p = order[i];
+                    int b = std::min(kBins - 1, std::max(0, (int)((cen[(size_t)p * 3 + axis] - lo) * scale)));
+                    bb[b].Grow(pb[p]); bc[b]++;
+                }
+                float ra[kBins]; int rc[kBins];
+                Aabb acc; acc.Reset(); int c = 0;
+                for (int b = kBins - 1; b >= 1; b--) { acc.Grow(bb[b]); c += bc[b]; ra[b] = acc.HalfArea(); rc[b] = c; }
+                acc.Reset(); c = 0;
+                for (int b = 0; b < kBins - 1; b++) {
+                    acc.Grow(bb[b]); c += bc[b];
+                    if (c == 0 || rc[b + 1] == 0) continue;
+                    float cost = acc.HalfArea() * c + ra[b + 1] * rc[b + 1];
+                    if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = b; }
+                }
+            }
+            float area = box.HalfArea();
+            float leaf_cost = kIntersectCost * count;
+            float split_cost = best_axis >= 0 && area > 0 ? kTraversalCost + kIntersectCost * best_cost / area : std::numeric_limits<float>::max();
+            if (count <= max_leaf && leaf_cost <= split_cost) return make_leaf();
+            if (best_axis >= 0) {
+                float lo = cbox.lo[best_axis], scale = kBins / (cbox.hi[best_axis] - lo);
+                auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](int32_t p) {
+                    int b = std::min(kBins - 1, std::max(0, (int)((cen[(size_t)p * 3 + best_axis] - lo) * scale)));
+                    return b <= best_split;
+                });
+                mid = (int)(it - order.begin());
+                if (mid == first || mid == first + count) mid = -1;
+            }
+        }
+        if (mid < 0) {
+            if (count <= max_leaf) return make_leaf();
+            // centroids coincide (or depth cap reached): median split along the widest box axis
+            int axis = 0;
+            float e0 = box.hi[0] - box.lo[0], e1 = box.hi[1] - box.lo[1], e2 = box.hi[2] - box.lo[2];
+            if (e1 > e0 && e1 >= e2) axis = 1; else if (e2 > e0 && e2 > e1) axis = 2;
+            mid = first + count / 2;
+            std::nth_element(order.begin() + first, order.begin() + mid, order.begin() + first + count,
+                             [&](int32_t a, int32_t b) { return cen[(size_t)a * 3 + axis] < cen[(size_t)b * 3 + axis]; });
+        }
+        int l = Build(first, mid - first, depth + 1);
+        int r = Build(mid, first + count - mid, depth + 1);
+        tmp[me].left = l; tmp[me].right = r;
+        return me;
+    }
+};
+
+void PutChild(BvhNode64& n, int slot, const Aabb* box, int32_t child) {
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    if (box) { memcpy(lo, box->lo, 12); memcpy(hi, box->hi, 12); }
+    float* q = n.q;
+    q[slot * 4 + 0] = lo[0]; q[slot * 4 + 1] = hi[0]; q[slot * 4 + 2] = lo[1]; q[slot * 4 + 3] = hi[1];
+    q[8 + slot * 2 + 0] = lo[2]; q[8 + slot * 2 + 1] = hi[2];
+    memcpy(&q[12 + slot], &child, 4);
+}
+
+}  // namespace
+
+void BuildSahBvh(const Aabb* prim_bounds, int n, int max_leaf, BuiltBvh* out) {
+    out->nodes.clear();
+    out->order.resize(n);
+    for (int i = 0; i < n; i++) out->order[i] = i;
+    out->bounds.Reset();
+    if (n == 0) {
+        BvhNode64 root; memset(&root, 0, sizeof root);
+        PutChild(root, 0, nullptr, kNoChild); PutChild(root, 1, nullptr, kNoChild);
+        out->nodes.push_back(root);
+        return;
+    }
+    Builder b(prim_bounds, n, std::min(8, std::max(1, max_leaf)), out->order);
+    b.tmp.reserve((size_t)n);
+    int root = b.Build(0, n, 0);
+    out->bounds = b.tmp[root].box;
+    out->max_depth = b.max_depth;
+
+    // flatten: inner Tmp nodes get consecutive indices in DFS order (children after parents, near each other)
+    std::vector<int> idx(b.tmp.size(), -1);
+    int inner = 0;
+    if (b.tmp[root].leaf) inner = 1;   // synthetic root
+    {
+        std::vector<int> st{root};
+        while (!st.empty()) {
+            int t = st.back(); st.pop_back();
+            if (b.tmp[t].leaf) continue;
+            idx[t] = inner++;
+            st.push_back(b.tmp[t].right); st.push_back(b.tmp[t].left);
+        }
+    }
+    out->nodes.assign(inner, BvhNode64());
+    for (auto& nd : out->nodes) memset(&nd, 0, sizeof nd);
+    auto child_ref = [&](int t) -> int32_t { return b.tmp[t].leaf ? EncodeLeaf(b.tmp[t].first, b.tmp[t].count) : idx[t]; };
+    if (b.tmp[root].leaf) {
+        PutChild(out->nodes[0], 0, &b.tmp[root].box, child_ref(root));
+        PutChild(out->nodes[0], 1, nullptr, kNoChild);
+    }
+    for (size_t t = 0; t < b.tmp.size(); t++) {
+        if (b.tmp[t].leaf) continue;
+        BvhNode64& nd = out->nodes[idx[t]];
+        PutChild(nd, 0, &b.tmp[b.tmp[t].left].box, child_ref(b.tmp[t].left));
+        PutChild(nd, 1, &b.tmp[b.tmp[t].right].box, child_ref(b.tmp[t].right));
+    }
+}
+
+}  // namespace rt795

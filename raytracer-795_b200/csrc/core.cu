@@ -1,0 +1,649 @@
+// Core of librt795: scene flatten/upload and the wavefront render driver behind the C ABI (include/rt795.h).
+//
+// rt_scene_create  replaces BVH construction (src/Scene.cpp:321-323, src/BVH.cpp:53-110) with the host SAH builder
+//                  (bvh_build.cpp) and uploads the flattened scene to HBM.
+// rt_render*       replaces the 8-thread pixel loop (src/Scene.cpp:269-292, 336-356) with
+//                  generate -> [extend -> shade -> shadow]* -> resolve over ray queues in HBM.
+// There is no CPU rendering path in this library.
+#include "../../include/rt795.h"
+#include "bvh_build.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace rt795 {
+void SetLastError(const std::string& msg);
+}
+using namespace rt795;
+
+namespace {
+
+struct CudaFail { cudaError_t e; const char* what; int line; };
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) throw CudaFail{e_, #call, __LINE__}; } while (0)
+struct Invalid { std::string msg; };
+
+inline float BitsToFloat(int v) { float f; memcpy(&f, &v, 4); return f; }
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    void Alloc(size_t count) {
+        if (count <= n && p) return;
+        Free();
+        if (count == 0) count = 1;
+        CK(cudaMalloc((void**)&p, count * sizeof(T)));
+        n = count;
+    }
+    void Upload(const T* h, size_t count, cudaStream_t st) {
+        Alloc(count);
+        if (count) CK(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+    void Free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { Free(); }
+};
+
+struct QueueBufs {
+    DevBuf<float4> o_time, d_tmax, w_pixel, hit;
+    DevBuf<int4> meta;
+    DevBuf<int32_t> hit_obj;
+    void Alloc(size_t cap) { o_time.Alloc(cap); d_tmax.Alloc(cap); w_pixel.Alloc(cap); hit.Alloc(cap); meta.Alloc(cap); hit_obj.Alloc(cap); }
+    DRayQueue View() { return DRayQueue{o_time.p, d_tmax.p, w_pixel.p, meta.p, hit.p, hit_obj.p}; }
+};
+
+}  // namespace
+
+struct RtScene {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DScene d{};
+    // geometry + shading buffers
+    DevBuf<float4> nodes, tris, spheres;
+    DevBuf<DObjectXf> obj_xf;
+    DevBuf<DObjectSh> obj_sh;
+    DevBuf<int32_t> tri_idx;
+    DevBuf<float> vertices, normals, texcoords;
+    DevBuf<RtMaterial> materials;
+    DevBuf<RtTexture> textures;
+    DevBuf<DImage> images;
+    std::vector<DevBuf<unsigned char>> image_px;
+    DevBuf<RtLight> lights;
+    bool has_dielectric = false;
+    int bvh_depth = 0;
+    // render state
+    std::vector<QueueBufs> levels;
+    size_t queue_cap = 0, shadow_cap = 0;
+    DevBuf<float4> sq_o, sq_d, sq_c;
+    DevBuf<float> accum, out_dev;
+    DevBuf<DCounters> counters;
+    DCounters* h_counters = nullptr;   // pinned
+    DevBuf<RtHit> hits_dev;
+    // tone map scratch
+    DevBuf<double> tm_sum; DevBuf<float> tm_max; DevBuf<unsigned> tm_hist; DevBuf<float> tm_in; DevBuf<uint8_t> tm_out;
+    RtStats stats{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+void CameraSetup(const RtCameraDesc* c, DCamera* o) {     // Camera::Camera, src/Camera.cpp:7-61
+    memset(o, 0, sizeof *o);
+    int n = 1;
+    for (int i = 1; i < 1000; i++) if (i * i >= c->num_samples) { n = i; break; }
+    float3 gaze = v3(c->gaze), up = v3(c->up);
+    float3 g = normalize0(gaze);
+    float3 w = c->left_handed ? normalize0(gaze) : normalize0(-gaze);
+    float3 right = normalize0(cross(up, w));
+    float3 upv = cross(w, right);
+    memcpy(o->pos, c->position, 12);
+    o->gaze[0] = g.x; o->gaze[1] = g.y; o->gaze[2] = g.z;
+    o->up[0] = upv.x; o->up[1] = upv.y; o->up[2] = upv.z;
+    o->right[0] = right.x; o->right[1] = right.y; o->right[2] = right.z;
+    o->l = c->left; o->r = c->right; o->b = c->bottom; o->t = c->top; o->dist = c->distance;
+    o->nx = c->nx; o->ny = c->ny; o->spp = c->num_samples < 1 ? 1 : c->num_samples; o->n = n;
+    o->invnx = 1.0f / c->nx; o->invny = 1.0f / c->ny;
+    o->pw = (o->r - o->l) * o->invnx; o->ph = (o->t - o->b) * o->invny;
+    o->sw = o->pw / n; o->sh = o->ph / n;
+    o->dof = c->is_dof; o->focus = c->focus_distance; o->aperture = c->aperture_size;
+}
+
+void Validate(const RtSceneDesc* s) {
+    auto bad = [](const std::string& m) { throw Invalid{m}; };
+    if (!s) bad("null scene description");
+    if (s->abi_version != RT795_ABI_VERSION) bad("abi_version mismatch");
+    if (s->num_vertices < 0 || s->num_triangles < 0 || s->num_objects < 0) bad("negative count");
+    if (s->num_vertices && !s->vertices) bad("vertices missing");
+    if (s->num_triangles && !s->tri_indices) bad("tri_indices missing");
+    if (s->num_materials < 1 || !s->materials) bad("at least one material is required");
+    for (int i = 0; i < s->num_triangles * 3; i++) if (s->tri_indices[i] < 0 || s->tri_indices[i] >= s->num_vertices) bad("triangle vertex index out of range");
+    for (int m = 0; m < s->num_meshes; m++) {
+        const RtMesh& me = s->meshes[m];
+        if (me.first_tri < 0 || me.tri_count < 1 || me.first_tri + me.tri_count > s->num_triangles) bad("mesh triangle range out of bounds");
+        if (me.smooth && !s->vertex_normals) bad("smooth mesh without vertex_normals");
+    }
+    for (int t = 0; t < s->num_textures; t++) {
+        const RtTexture& tx = s->textures[t];
+        if (tx.type == RT_TEX_IMAGE && (tx.image < 0 || tx.image >= s->num_images)) bad("texture image index out of range");
+    }
+    for (int i = 0; i < s->num_images; i++) if (s->images[i].width < 2 || s->images[i].height < 2 || !s->images[i].pixels) bad("image must be at least 2x2");
+    for (int i = 0; i < s->num_objects; i++) {
+        const RtObject& o = s->objects[i];
+        if (o.kind == RT_OBJ_SPHERE) { if (o.geom < 0 || o.geom >= s->num_spheres) bad("object sphere index out of range"); }
+        else if (o.kind == RT_OBJ_MESH) { if (o.geom < 0 || o.geom >= s->num_meshes) bad("object mesh index out of range"); }
+        else bad("unknown object kind");
+        if (o.mat_index < 1 || o.mat_index > s->num_materials) bad("object material index out of range");
+        for (int k = 0; k < 2; k++) if (o.tex[k] < 0 || o.tex[k] > s->num_textures) bad("object texture id out of range");
+        if (o.kind == RT_OBJ_MESH && (o.tex[0] || o.tex[1])) {
+            const RtMesh& me = s->meshes[o.geom];
+            for (int t = me.first_tri * 3; t < (me.first_tri + me.tri_count) * 3; t++) {
+                int uv = s->tri_indices[t] + o.tex_offset;
+                if (uv < 0 || uv >= s->num_texcoords) bad("textured mesh needs texture coordinates for every vertex");
+            }
+        }
+    }
+    for (int i = 0; i < s->num_lights; i++) {
+        const RtLight& l = s->lights[i];
+        if (l.type < RT_LIGHT_POINT || l.type > RT_LIGHT_ENVIRONMENT) bad("unknown light type");
+        if (l.type == RT_LIGHT_ENVIRONMENT && (l.image < 0 || l.image >= s->num_images)) bad("environment light image index out of range");
+    }
+    if (s->env_light_index < -1 || s->env_light_index >= s->num_lights) bad("env_light_index out of range");
+    if (s->background_texture < -1 || s->background_texture >= s->num_textures) bad("background_texture out of range");
+}
+
+void BuildAndUpload(RtScene* sc, const RtSceneDesc* s) {
+    auto t0 = std::chrono::steady_clock::now();
+    cudaStream_t st = sc->stream;
+    const float eps = s->int_test_eps;
+
+    // ---- BLAS per mesh
+    std::vector<BvhNode64> nodes;
+    std::vector<float4> tris;
+    std::vector<int> mesh_root(s->num_meshes, 0), mesh_depth(s->num_meshes, 0);
+    std::vector<Aabb> mesh_bounds(s->num_meshes);
+    tris.reserve((size_t)s->num_triangles * 3);
+    for (int m = 0; m < s->num_meshes; m++) {
+        const RtMesh& me = s->meshes[m];
+        std::vector<Aabb> pb(me.tri_count);
+        for (int t = 0; t < me.tri_count; t++) {
+            const int* ix = s->tri_indices + 3 * (size_t)(me.first_tri + t);
+            Aabb b; b.Reset();
+            float ext = 0.f;
+            for (int k = 0; k < 3; k++) b.Grow(s->vertices + 3 * (size_t)ix[k]);
+            for (int k = 0; k < 3; k++) ext = std::max(ext, b.hi[k] - b.lo[k]);
+            // the reference accepts beta, gamma >= -eps: hits up to eps*edge outside the triangle; pad so the box stays conservative
+            for (int k = 0; k < 3; k++) {
+                float mag = std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]));
+                float pad = 2.0f * eps * ext + 4.0e-7f * mag + 1e-30f;
+                b.lo[k] -= pad; b.hi[k] += pad;
+            }
+            pb[t] = b;
+        }
+        BuiltBvh bv;
+        BuildSahBvh(pb.data(), me.tri_count, 4, &bv);
+        int node_base = (int)nodes.size(), tri_base = (int)(tris.size() / 3);
+        mesh_root[m] = node_base;
+        mesh_depth[m] = bv.max_depth;
+        mesh_bounds[m] = bv.bounds;
+        for (BvhNode64 nd : bv.nodes) {
+            for (int c = 0; c < 2; c++) {
+                int32_t ch; memcpy(&ch, &nd.q[12 + c], 4);
+                if (ch == kNoChild) continue;
+                if (ch >= 0) ch += node_base;
+                else { int payload = ~ch; int first = (payload >> 3) + tri_base; ch = ~((first << 3) | (payload & 7)); }
+                memcpy(&nd.q[12 + c], &ch, 4);
+            }
+            nodes.push_back(nd);
+        }
+        for (int k = 0; k < me.tri_count; k++) {
+            int gtri = me.first_tri + bv.order[k];
+            const int* ix = s->tri_indices + 3 * (size_t)gtri;
+            const float *a = s->vertices + 3 * (size_t)ix[0], *b = s->vertices + 3 * (size_t)ix[1], *c = s->vertices + 3 * (size_t)ix[2];
+            tris.push_back(make_float4(a[0], a[1], a[2], BitsToFloat(gtri)));
+            tris.push_back(make_float4(b[0] - a[0], b[1] - a[1], b[2] - a[2], 0.f));
+            tris.push_back(make_float4(c[0] - a[0], c[1] - a[1], c[2] - a[2], 0.f));
+        }
+    }
+
+    // ---- top-level entries + TLAS
+    std::vector<DObjectXf> oxf(s->num_objects);
+    std::vector<DObjectSh> osh(s->num_objects);
+    std::vector<Aabb> obounds(s->num_objects);
+    std::vector<float4> spheres(s->num_spheres);
+    for (int i = 0; i < s->num_spheres; i++) spheres[i] = make_float4(s->spheres[i].center[0], s->spheres[i].center[1], s->spheres[i].center[2], s->spheres[i].radius);
+    int max_blas_depth = 0;
+    for (int i = 0; i < s->num_objects; i++) {
+        const RtObject& o = s->objects[i];
+        DObjectXf& x = oxf[i];
+        x.inv0 = make_float4(o.inv[0], o.inv[1], o.inv[2], o.inv[3]);
+        x.inv1 = make_float4(o.inv[4], o.inv[5], o.inv[6], o.inv[7]);
+        x.inv2 = make_float4(o.inv[8], o.inv[9], o.inv[10], o.inv[11]);
+        Aabb ob;   // object-space bounds
+        int root;
+        if (o.kind == RT_OBJ_SPHERE) {
+            const RtSphere& sp = s->spheres[o.geom];
+            for (int k = 0; k < 3; k++) { ob.lo[k] = sp.center[k] - sp.radius; ob.hi[k] = sp.center[k] + sp.radius; }
+            root = ~o.geom;
+        } else { ob = mesh_bounds[o.geom]; root = mesh_root[o.geom]; max_blas_depth = std::max(max_blas_depth, mesh_depth[o.geom]); }
+        x.blur_root = make_float4(o.blur[0], o.blur[1], o.blur[2], BitsToFloat(root));
+        // forward matrix M = (M^-1)^-1 (affine): invert the 3x3 part in double
+        double A[3][3], t[3];
+        for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) A[r][c] = o.inv[r * 4 + c]; t[r] = o.inv[r * 4 + 3]; }
+        double det = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) + A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+        if (det == 0.0 || det != det) throw Invalid{"object has a singular inverse transformation"};
+        double M[3][3];
+        M[0][0] = (A[1][1] * A[2][2] - A[1][2] * A[2][1]) / det; M[0][1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) / det; M[0][2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) / det;
+        M[1][0] = (A[1][2] * A[2][0] - A[1][0] * A[2][2]) / det; M[1][1] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) / det; M[1][2] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) / det;
+        M[2][0] = (A[1][0] * A[2][1] - A[1][1] * A[2][0]) / det; M[2][1] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) / det; M[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) / det;
+        double T[3];
+        for (int r = 0; r < 3; r++) T[r] = -(M[r][0] * t[0] + M[r][1] * t[1] + M[r][2] * t[2]);
+        Aabb wb; wb.Reset();
+        for (int corner = 0; corner < 8; corner++) {
+            double p[3] = {corner & 1 ? ob.hi[0] : ob.lo[0], corner & 2 ? ob.hi[1] : ob.lo[1], corner & 4 ? ob.hi[2] : ob.lo[2]};
+            float q[3];
+            for (int r = 0; r < 3; r++) q[r] = (float)(M[r][0] * p[0] + M[r][1] * p[1] + M[r][2] * p[2] + T[r]);
+            wb.Grow(q);
+            float qb[3] = {q[0] + o.blur[0], q[1] + o.blur[1], q[2] + o.blur[2]};   // swept by MotionBlur * time, time in [0,1]
+            wb.Grow(qb);
+        }
+        for (int k = 0; k < 3; k++) {
+            float mag = std::max(std::fabs(wb.lo[k]), std::fabs(wb.hi[k]));
+            float pad = 1.0e-5f * mag + 1.0e-5f * (wb.hi[k] - wb.lo[k]) + 1e-30f;
+            wb.lo[k] -= pad; wb.hi[k] += pad;
+        }
+        obounds[i] = wb;
+        DObjectSh& h = osh[i];
+        memcpy(h.nrm, o.inv_t, sizeof h.nrm);
+        h.mat_index = o.mat_index; h.tex[0] = o.tex[0]; h.tex[1] = o.tex[1]; h.tex_offset = o.tex_offset;
+        h.kind = o.kind; h.geom = o.geom;
+        h.smooth = o.kind == RT_OBJ_MESH ? s->meshes[o.geom].smooth : 0;
+        h.first_tri = o.kind == RT_OBJ_MESH ? s->meshes[o.geom].first_tri : 0;
+    }
+    BuiltBvh tl;
+    BuildSahBvh(obounds.data(), s->num_objects, 1, &tl);
+    int tlas_base = (int)nodes.size();
+    for (BvhNode64 nd : tl.nodes) {
+        for (int c = 0; c < 2; c++) {
+            int32_t ch; memcpy(&ch, &nd.q[12 + c], 4);
+            if (ch == kNoChild) continue;
+            if (ch >= 0) ch += tlas_base;
+            else { int payload = ~ch; int obj = tl.order[payload >> 3]; ch = ~(obj << 3); }   // TLAS leaves hold exactly one entry
+            memcpy(&nd.q[12 + c], &ch, 4);
+        }
+        nodes.push_back(nd);
+    }
+    sc->bvh_depth = tl.max_depth + max_blas_depth + 3;
+    if (sc->bvh_depth > kStackSize) throw Invalid{"BVH too deep for the traversal stack (" + std::to_string(sc->bvh_depth) + " > " + std::to_string(kStackSize) + ")"};
+    auto t1 = std::chrono::steady_clock::now();
+
+    // ---- upload
+    static_assert(sizeof(BvhNode64) == 64, "node size");
+    sc->nodes.Upload((const float4*)nodes.data(), nodes.size() * 4, st);
+    sc->tris.Upload(tris.data(), tris.size(), st);
+    sc->spheres.Upload(spheres.data(), spheres.size(), st);
+    sc->obj_xf.Upload(oxf.data(), oxf.size(), st);
+    sc->obj_sh.Upload(osh.data(), osh.size(), st);
+    sc->tri_idx.Upload(s->tri_indices, (size_t)s->num_triangles * 3, st);
+    sc->vertices.Upload(s->vertices, (size_t)s->num_vertices * 3, st);
+    if (s->vertex_normals) sc->normals.Upload(s->vertex_normals, (size_t)s->num_vertices * 3, st); else sc->normals.Alloc(1);
+    if (s->texcoords) sc->texcoords.Upload(s->texcoords, (size_t)s->num_texcoords * 2, st); else sc->texcoords.Alloc(1);
+    sc->materials.Upload(s->materials, s->num_materials, st);
+    sc->textures.Upload(s->textures, s->num_textures, st);
+    std::vector<RtLight> lights(s->lights, s->lights + s->num_lights);
+    sc->lights.Upload(lights.data(), lights.size(), st);
+    std::vector<DImage> dimg(s->num_images);
+    sc->image_px.resize(s->num_images);
+    for (int i = 0; i < s->num_images; i++) {
+        const RtImage& im = s->images[i];
+        size_t bytes = (size_t)im.width * im.height * (im.format == RT_IMG_RGBA8 ? 4 : 16);
+        sc->image_px[i].Upload((const unsigned char*)im.pixels, bytes, st);
+        dimg[i] = DImage{sc->image_px[i].p, im.width, im.height, im.format, 0};
+    }
+    sc->images.Upload(dimg.data(), dimg.size(), st);
+    CK(cudaStreamSynchronize(st));
+    auto t2 = std::chrono::steady_clock::now();
+
+    DScene& d = sc->d;
+    d.nodes = sc->nodes.p; d.tris = sc->tris.p; d.obj_xf = sc->obj_xf.p; d.spheres = sc->spheres.p; d.tlas_root = tlas_base;
+    d.obj_sh = sc->obj_sh.p; d.tri_idx = sc->tri_idx.p; d.vertices = sc->vertices.p; d.normals = sc->normals.p; d.texcoords = sc->texcoords.p;
+    d.materials = sc->materials.p; d.textures = sc->textures.p; d.images = sc->images.p; d.lights = sc->lights.p;
+    d.num_lights = s->num_lights; d.num_objects = s->num_objects; d.max_depth = s->max_recursion_depth;
+    d.shadow_eps = s->shadow_ray_eps; d.int_eps = s->int_test_eps;
+    memcpy(d.background, s->background_color, 12); memcpy(d.ambient, s->ambient_light, 12);
+    d.env_light = s->env_light_index; d.background_texture = s->background_texture;
+    for (int i = 0; i < s->num_materials; i++) if (s->materials[i].type == RT_MAT_DIELECTRIC) sc->has_dielectric = true;
+
+    sc->stats.bvh_nodes = nodes.size(); sc->stats.bvh_bytes = nodes.size() * 64; sc->stats.tri_bytes = tris.size() * 16;
+    sc->stats.ms_bvh_build = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    sc->stats.ms_upload = std::chrono::duration<double, std::milli>(t2 - t1).count();
+}
+
+inline int Blocks(long long n) { return (int)((n + kBlock - 1) / kBlock); }
+
+struct Driver {
+    RtScene* sc;
+    cudaStream_t st;
+    DCamera cam;
+    DTiling tl;
+    RenderConsts rc;
+    bool count;
+    int nlevels;
+    bool branching;
+    float* accum;
+    DShadowQueue sq;
+    uint64_t launches = 0, secondary = 0, shadow = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> unused;
+    double ms_extend = 0, ms_shade = 0, ms_shadow = 0;
+
+    template <typename F>
+    void Timed(double* acc, F&& f) {
+        if (!count) { f(); return; }
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+        CK(cudaEventRecord(a, st));
+        f();
+        CK(cudaEventRecord(b, st));
+        CK(cudaEventSynchronize(b));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, a, b));
+        *acc += ms;
+        cudaEventDestroy(a); cudaEventDestroy(b);
+    }
+
+    // Processes rays [0, n) of level `lv`; recursion depth is bounded by the queue level count.
+    void ProcessLevel(int lv, int n) {
+        QueueBufs& qb = sc->levels[lv % nlevels];
+        QueueBufs& nb = sc->levels[(lv + 1) % nlevels];
+        DRayQueue q = qb.View(), nq = nb.View();
+        int nl = std::max(1, sc->d.num_lights);
+        // chunk so that neither the next level (<= 2 rays per ray when a dielectric can branch) nor the shadow queue can overflow
+        long long by_next = branching ? (long long)rc.queue_cap / 2 : rc.queue_cap;
+        long long by_shadow = (long long)rc.shadow_cap / nl;
+        int chunk = (int)std::max(1LL, std::min(by_next, by_shadow));
+        for (int first = 0; first < n; first += chunk) {
+            int m = std::min(chunk, n - first);
+            CK(cudaMemsetAsync(&sc->counters.p->next_count, 0, 2 * sizeof(int32_t), st));
+            Timed(&ms_extend, [&] {
+                if (count) k_extend<true><<<Blocks(m), kBlock, 0, st>>>(sc->d, q, first, m, sc->counters.p);
+                else k_extend<false><<<Blocks(m), kBlock, 0, st>>>(sc->d, q, first, m, sc->counters.p);
+            });
+            Timed(&ms_shade, [&] {
+                if (rc.integrator == RT_INTEGRATOR_PATH) k_shade<RT_INTEGRATOR_PATH><<<Blocks(m), kBlock, 0, st>>>(sc->d, cam, rc, q, first, m, nq, sq, sc->counters.p, accum);
+                else k_shade<RT_INTEGRATOR_REFERENCE><<<Blocks(m), kBlock, 0, st>>>(sc->d, cam, rc, q, first, m, nq, sq, sc->counters.p, accum);
+            });
+            launches += 2;
+            CK(cudaMemcpyAsync(sc->h_counters, sc->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+            int next_n = sc->h_counters->next_count, shadow_n = sc->h_counters->shadow_count;
+            if (sc->h_counters->overflow) throw Invalid{"ray queue overflow (raise queue_capacity)"};
+            if (shadow_n > 0) {
+                Timed(&ms_shadow, [&] {
+                    if (count) k_shadow<true><<<Blocks(shadow_n), kBlock, 0, st>>>(sc->d, sq, shadow_n, accum, sc->counters.p);
+                    else k_shadow<false><<<Blocks(shadow_n), kBlock, 0, st>>>(sc->d, sq, shadow_n, accum, sc->counters.p);
+                });
+                launches++;
+                shadow += (uint64_t)shadow_n;
+            }
+            if (next_n > 0) {
+                secondary += (uint64_t)next_n;
+                ProcessLevel(lv + 1, next_n);
+            }
+        }
+    }
+};
+
+void EnsureRenderBuffers(RtScene* sc, const RtRenderOpts* opts, int nlevels, size_t npix3) {
+    size_t cap = opts->queue_capacity > 0 ? (size_t)opts->queue_capacity : ((size_t)1 << 22);
+    cap = std::max<size_t>(cap, 64);
+    size_t scap = (size_t)std::min(8, std::max(2, sc->d.num_lights)) * cap;   // a shade pass over `cap` rays emits <= num_lights shadow rays per ray
+    if ((int)sc->levels.size() < nlevels) sc->levels.resize(nlevels);
+    for (int i = 0; i < nlevels; i++) sc->levels[i].Alloc(cap);
+    sc->queue_cap = cap; sc->shadow_cap = scap;
+    sc->sq_o.Alloc(scap); sc->sq_d.Alloc(scap); sc->sq_c.Alloc(scap);
+    sc->accum.Alloc(npix3);
+    sc->counters.Alloc(1);
+    if (!sc->h_counters) CK(cudaMallocHost((void**)&sc->h_counters, sizeof(DCounters)));
+}
+
+DTiling MakeTiling(const RtCameraDesc* cam, const RtRenderOpts* opts) {
+    DTiling t;
+    t.tw = opts->tile_w > 0 ? opts->tile_w : 16;
+    t.th = opts->tile_h > 0 ? opts->tile_h : 16;
+    if (t.tw % 8 || t.th % 4) throw Invalid{"tile_w must be a multiple of 8 and tile_h of 4"};
+    t.tiles_x = (cam->nx + t.tw - 1) / t.tw; t.tiles_y = (cam->ny + t.th - 1) / t.th;
+    t.count = opts->tile_count > 1 ? opts->tile_count : 1;
+    t.rank = opts->tile_count > 1 ? opts->tile_rank : 0;
+    if (t.rank < 0 || t.rank >= t.count) throw Invalid{"tile_rank out of range"};
+    int ntiles = t.tiles_x * t.tiles_y;
+    t.local_tiles = ntiles > t.rank ? (ntiles - t.rank + t.count - 1) / t.count : 0;
+    return t;
+}
+
+void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts_in, float* d_out, cudaStream_t user_stream) {
+    if (!cam || cam->nx < 1 || cam->ny < 1) throw Invalid{"bad camera resolution"};
+    RtRenderOpts opts;
+    if (opts_in) opts = *opts_in; else { memset(&opts, 0, sizeof opts); }
+    CK(cudaSetDevice(sc->device));
+    cudaStream_t st = user_stream ? user_stream : sc->stream;
+    Driver dr;
+    dr.sc = sc; dr.st = st;
+    CameraSetup(cam, &dr.cam);
+    dr.tl = MakeTiling(cam, &opts);
+    dr.count = opts.collect_counters != 0;
+    bool path = opts.integrator == RT_INTEGRATOR_PATH;
+    int max_depth = path ? (opts.pt_max_depth > 0 ? opts.pt_max_depth : sc->d.max_depth) : sc->d.max_depth;
+    if (max_depth < 0) max_depth = 0;
+    if (max_depth > 250) throw Invalid{"recursion depth above 250 is not supported"};
+    dr.branching = !path && sc->has_dielectric && max_depth > 0;
+    // Two ping-pong levels suffice when a level is always processed in ONE chunk (no branching and the shadow queue can take
+    // a full level); otherwise deeper levels must not overwrite a level that still has unprocessed chunks.
+    dr.nlevels = (dr.branching || sc->d.num_lights > 8) ? max_depth + 2 : 2;
+    size_t npix3 = (size_t)cam->nx * cam->ny * 3;
+    EnsureRenderBuffers(sc, &opts, dr.nlevels, npix3);
+    dr.rc.seed = opts.seed; dr.rc.integrator = opts.integrator; dr.rc.pt_max_depth = max_depth; dr.rc.pt_nee = opts.pt_nee; dr.rc.pt_rr = opts.pt_russian_roulette;
+    dr.rc.pt_importance = opts.pt_importance; dr.rc.queue_cap = (int)sc->queue_cap; dr.rc.shadow_cap = (int)sc->shadow_cap;
+    dr.accum = sc->accum.p;
+    dr.sq = DShadowQueue{sc->sq_o.p, sc->sq_d.p, sc->sq_c.p};
+
+    int wave = opts.wave_rays > 0 ? opts.wave_rays : (int)sc->queue_cap;
+    wave = (int)std::min<size_t>((size_t)wave, sc->queue_cap);
+    wave = std::max(32, wave / 32 * 32);
+    unsigned long long total = (unsigned long long)dr.tl.local_tiles * dr.tl.tw * dr.tl.th * (unsigned long long)dr.cam.spp;
+
+    CK(cudaEventRecord(sc->ev0, st));
+    CK(cudaMemsetAsync(sc->accum.p, 0, npix3 * sizeof(float), st));
+    CK(cudaMemsetAsync(sc->counters.p, 0, sizeof(DCounters), st));
+    uint64_t primary = 0, waves = 0;
+    double ms_raygen = 0;
+    for (unsigned long long base = 0; base < total; base += (unsigned long long)wave) {
+        int n = (int)std::min<unsigned long long>((unsigned long long)wave, total - base);
+        CK(cudaMemsetAsync(&sc->counters.p->next_count, 0, sizeof(int32_t), st));
+        dr.Timed(&ms_raygen, [&] {
+            k_raygen<<<Blocks(n), kBlock, 0, st>>>(dr.cam, dr.tl, dr.rc, max_depth, base, n, sc->levels[0].View(), &sc->counters.p->next_count, 0);
+        });
+        dr.launches++;
+        CK(cudaMemcpyAsync(sc->h_counters, sc->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        int n0 = sc->h_counters->next_count;
+        primary += (uint64_t)n0; waves++;
+        if (n0 > 0) dr.ProcessLevel(0, n0);
+    }
+    double ms_resolve = 0;
+    dr.Timed(&ms_resolve, [&] { k_resolve<<<Blocks((long long)npix3), kBlock, 0, st>>>(sc->accum.p, d_out, (int)npix3, 1.0f / (float)dr.cam.spp); });
+    dr.launches++;
+    CK(cudaEventRecord(sc->ev1, st));
+    CK(cudaEventSynchronize(sc->ev1));
+    CK(cudaGetLastError());
+    float ms = 0; CK(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1));
+    RtStats& s = sc->stats;
+    s.rays_primary = primary; s.rays_secondary = dr.secondary; s.rays_shadow = dr.shadow; s.launches = dr.launches; s.waves = waves;
+    s.ms_total = ms; s.ms_extend = dr.ms_extend; s.ms_shade = dr.ms_shade; s.ms_shadow = dr.ms_shadow; s.ms_raygen = ms_raygen; s.ms_resolve = ms_resolve;
+    if (dr.count) {
+        CK(cudaMemcpy(sc->h_counters, sc->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost));
+        s.node_visits = sc->h_counters->node_visits; s.prim_tests = sc->h_counters->prim_tests;
+    } else { s.node_visits = 0; s.prim_tests = 0; }
+}
+
+template <typename F>
+int Guard(const char* fn, F&& f) {
+    try { f(); return RT_OK; }
+    catch (const CudaFail& c) {
+        SetLastError(std::string(fn) + ": CUDA error '" + cudaGetErrorString(c.e) + "' at core.cu:" + std::to_string(c.line) + " in " + c.what);
+        return c.e == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA;
+    } catch (const Invalid& i) {
+        SetLastError(std::string(fn) + ": " + i.msg);
+        return i.msg.find("overflow") != std::string::npos ? RT_ERR_OVERFLOW : RT_ERR_INVALID;
+    } catch (const std::bad_alloc&) {
+        SetLastError(std::string(fn) + ": host allocation failed");
+        return RT_ERR_OOM;
+    } catch (const std::exception& e) {
+        SetLastError(std::string(fn) + ": " + e.what());
+        return RT_ERR_INVALID;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int rt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out) {
+    if (!out) { SetLastError("rt_scene_create: null out"); return RT_ERR_INVALID; }
+    *out = nullptr;
+    RtScene* sc = nullptr;
+    int rcode = Guard("rt_scene_create", [&] {
+        Validate(desc);
+        int n = 0;
+        CK(cudaGetDeviceCount(&n));
+        if (device < 0 || device >= n) throw Invalid{"CUDA device " + std::to_string(device) + " not available (" + std::to_string(n) + " devices); there is no CPU fallback"};
+        CK(cudaSetDevice(device));
+        sc = new RtScene();
+        sc->device = device;
+        CK(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&sc->ev0)); CK(cudaEventCreate(&sc->ev1));
+        BuildAndUpload(sc, desc);
+    });
+    if (rcode != RT_OK) { if (sc) rt_scene_destroy(sc); return rcode; }
+    *out = sc;
+    return RT_OK;
+}
+
+void rt_scene_destroy(RtScene* sc) {
+    if (!sc) return;
+    cudaSetDevice(sc->device);
+    if (sc->stream) cudaStreamSynchronize(sc->stream);
+    if (sc->h_counters) cudaFreeHost(sc->h_counters);
+    if (sc->ev0) cudaEventDestroy(sc->ev0);
+    if (sc->ev1) cudaEventDestroy(sc->ev1);
+    cudaStream_t st = sc->stream;
+    delete sc;
+    if (st) cudaStreamDestroy(st);
+}
+
+int rt_render_device(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts, float* d_out_rgb, void* cuda_stream) {
+    if (!sc || !d_out_rgb) { SetLastError("rt_render_device: null argument"); return RT_ERR_INVALID; }
+    return Guard("rt_render_device", [&] { RenderDevice(sc, cam, opts, d_out_rgb, (cudaStream_t)cuda_stream); });
+}
+
+int rt_render(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts, float* out_rgb) {
+    if (!sc || !cam || !out_rgb) { SetLastError("rt_render: null argument"); return RT_ERR_INVALID; }
+    return Guard("rt_render", [&] {
+        CK(cudaSetDevice(sc->device));
+        size_t n = (size_t)cam->nx * cam->ny * 3;
+        sc->out_dev.Alloc(n);
+        RenderDevice(sc, cam, opts, sc->out_dev.p, nullptr);
+        CK(cudaMemcpyAsync(out_rgb, sc->out_dev.p, n * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
+        CK(cudaStreamSynchronize(sc->stream));
+    });
+}
+
+int rt_trace_primary(RtScene* sc, const RtCameraDesc* cam, RtHit* out_hits) {
+    if (!sc || !cam || !out_hits) { SetLastError("rt_trace_primary: null argument"); return RT_ERR_INVALID; }
+    return Guard("rt_trace_primary", [&] {
+        CK(cudaSetDevice(sc->device));
+        cudaStream_t st = sc->stream;
+        RtRenderOpts opts; memset(&opts, 0, sizeof opts);
+        size_t npix = (size_t)cam->nx * cam->ny;
+        opts.queue_capacity = (int)std::max<size_t>(sc->queue_cap, 1 << 20);
+        EnsureRenderBuffers(sc, &opts, 2, npix * 3);
+        sc->hits_dev.Alloc(npix);
+        CK(cudaMemsetAsync(sc->hits_dev.p, 0, npix * sizeof(RtHit), st));
+        DCamera dc; CameraSetup(cam, &dc);
+        DTiling tl = MakeTiling(cam, &opts);
+        RenderConsts rc; memset(&rc, 0, sizeof rc);
+        int wave = (int)sc->queue_cap / 32 * 32;
+        unsigned long long total = (unsigned long long)tl.local_tiles * tl.tw * tl.th;
+        for (unsigned long long base = 0; base < total; base += (unsigned long long)wave) {
+            int n = (int)std::min<unsigned long long>((unsigned long long)wave, total - base);
+            CK(cudaMemsetAsync(sc->counters.p, 0, sizeof(DCounters), st));
+            k_raygen<<<Blocks(n), kBlock, 0, st>>>(dc, tl, rc, 0, base, n, sc->levels[0].View(), &sc->counters.p->next_count, 1);
+            CK(cudaMemcpyAsync(sc->h_counters, sc->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            int n0 = sc->h_counters->next_count;
+            if (n0 <= 0) continue;
+            k_extend<false><<<Blocks(n0), kBlock, 0, st>>>(sc->d, sc->levels[0].View(), 0, n0, sc->counters.p);
+            k_primary_hits<<<Blocks(n0), kBlock, 0, st>>>(sc->d, sc->levels[0].View(), n0, sc->hits_dev.p);
+        }
+        CK(cudaMemcpyAsync(out_hits, sc->hits_dev.p, npix * sizeof(RtHit), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+    });
+}
+
+int rt_tonemap(RtScene* sc, const float* in_rgb, int nx, int ny, float key, float burn_percent, float saturation, float gamma, uint8_t* out_rgb8) {
+    if (!sc || !in_rgb || !out_rgb8 || nx < 1 || ny < 1) { SetLastError("rt_tonemap: bad argument"); return RT_ERR_INVALID; }
+    return Guard("rt_tonemap", [&] {
+        CK(cudaSetDevice(sc->device));
+        cudaStream_t st = sc->stream;
+        int npix = nx * ny;
+        sc->tm_in.Alloc((size_t)npix * 3); sc->tm_out.Alloc((size_t)npix * 3);
+        sc->tm_sum.Alloc(1); sc->tm_max.Alloc(1); sc->tm_hist.Alloc(kTmBins);
+        CK(cudaMemcpyAsync(sc->tm_in.p, in_rgb, (size_t)npix * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(sc->tm_sum.p, 0, sizeof(double), st));
+        CK(cudaMemsetAsync(sc->tm_max.p, 0, sizeof(float), st));
+        CK(cudaMemsetAsync(sc->tm_hist.p, 0, kTmBins * sizeof(unsigned), st));
+        int grid = std::min(Blocks(npix), 148 * 8);
+        k_tonemap_logsum<<<grid, kBlock, 0, st>>>(sc->tm_in.p, npix, sc->tm_sum.p, sc->tm_max.p);
+        double sum = 0; float mx = 0;
+        CK(cudaMemcpyAsync(&sum, sc->tm_sum.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&mx, sc->tm_max.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        float lavg = (float)std::exp(sum / npix);
+        float scale = key / std::max(lavg, 1e-20f);
+        float max_scaled = std::max(mx * scale, 1e-20f);
+        float lwhite = max_scaled;
+        if (burn_percent > 0.f) {
+            k_tonemap_hist<<<grid, kBlock, 0, st>>>(sc->tm_in.p, npix, scale, max_scaled, sc->tm_hist.p);
+            std::vector<unsigned> hist(kTmBins);
+            CK(cudaMemcpyAsync(hist.data(), sc->tm_hist.p, kTmBins * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            // luminance at the (100 - burn)% percentile becomes white
+            unsigned long long target = (unsigned long long)((double)npix * (100.0 - burn_percent) / 100.0), acc = 0;
+            int b = 0;
+            for (; b < kTmBins; b++) { acc += hist[b]; if (acc >= target) break; }
+            lwhite = std::max(1e-20f, (b + 0.5f) / (kTmBins - 1) * max_scaled);
+        }
+        k_tonemap_map<<<Blocks(npix), kBlock, 0, st>>>(sc->tm_in.p, npix, scale, lwhite, saturation, 1.0f / std::max(gamma, 1e-6f), sc->tm_out.p);
+        CK(cudaMemcpyAsync(out_rgb8, sc->tm_out.p, (size_t)npix * 3, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+    });
+}
+
+int rt_get_stats(RtScene* sc, RtStats* out) {
+    if (!sc || !out) { SetLastError("rt_get_stats: null argument"); return RT_ERR_INVALID; }
+    *out = sc->stats;
+    return RT_OK;
+}
+
+}  // extern "C"

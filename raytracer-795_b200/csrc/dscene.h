@@ -1,0 +1,88 @@
+// Device-side scene layout (HBM) shared by core.cu (host upload code) and the kernels.
+// Everything the traversal touches is 16-byte aligned and read as float4 (ld.global.nc.v4).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rt795 {
+
+constexpr int kStackSize = 64;          // traversal stack entries per thread (node, t_entry)
+constexpr int kMaxLights = 1 << 16;
+
+// Traversal record of a top-level entry: 64 bytes = the "64-B instance record" of SURVEY §8d.
+struct DObjectXf {
+    float4 inv0, inv1, inv2;            // rows of M^-1 (3x4): o' = inv*(o - blur*time, 1), d' = inv*(d, 0)  (src/Helper.cpp:110-133)
+    float4 blur_root;                   // blur.xyz ; w = bits(int): BLAS root node index, or ~sphere index for spheres
+};
+// Shading record of a top-level entry.
+struct DObjectSh {
+    float nrm[9];                       // upper 3x3 of (M^-1)^T  (src/Helper.cpp:100-108)
+    int32_t mat_index;                  // 1-based
+    int32_t tex[2];                     // 1-based, 0 = none
+    int32_t tex_offset;
+    int32_t smooth;                     // mesh smooth flag
+    int32_t first_tri;                  // mesh first triangle (global numbering), for primitive ids
+    int32_t kind;                       // RT_OBJ_*
+    int32_t geom;
+};
+struct DImage { const void* pixels; int32_t width, height, format, pad; };
+
+struct DScene {
+    // geometry for traversal
+    const float4* nodes;                // BvhNode64 as 4 x float4
+    const float4* tris;                 // 3 x float4 per triangle in leaf order: (v0, bits prim), (e1, 0), (e2, 0)
+    const DObjectXf* obj_xf;
+    const float4* spheres;              // center.xyz, R
+    int32_t tlas_root;
+    // shading data
+    const DObjectSh* obj_sh;
+    const int32_t* tri_idx;             // 3 ints per triangle (original order)
+    const float* vertices;              // 3 per vertex
+    const float* normals;               // 3 per vertex
+    const float* texcoords;             // 2 per entry
+    const struct RtMaterial* materials;
+    const struct RtTexture* textures;
+    const DImage* images;
+    const struct RtLight* lights;
+    int32_t num_lights, num_objects;
+    int32_t max_depth;
+    float shadow_eps, int_eps;
+    float background[3], ambient[3];
+    int32_t env_light, background_texture;
+};
+
+struct DCamera {                        // Camera::Camera, src/Camera.cpp:7-61
+    float pos[3], gaze[3], up[3], right[3];
+    float l, r, b, t, dist;
+    int32_t nx, ny, spp, n;             // n = stratification grid edge
+    float invnx, invny, pw, ph, sw, sh;
+    int32_t dof; float focus, aperture;
+};
+
+struct DTiling {                        // interleaved tile partition across ranks
+    int32_t tw, th, tiles_x, tiles_y, rank, count, local_tiles;
+};
+
+// One level of the ray queue, SoA of 16-byte records (coalesced float4 loads/stores).
+struct DRayQueue {
+    float4* o_time;                     // origin.xyz, time
+    float4* d_tmax;                     // direction.xyz, tmax
+    float4* w_pixel;                    // throughput weight rgb, bits(pixel index)
+    int4* meta;                         // x sample, y depth|flags<<8|beer_mat<<16, z path node, w bits(beer_s)
+    float4* hit;                        // t, beta, gamma, bits(prim)   (prim < 0: miss; sphere: prim = 0)
+    int32_t* hit_obj;                   // top-level entry index
+};
+struct DShadowQueue {
+    float4* o_time;
+    float4* d_tmax;
+    float4* c_pixel;                    // contribution rgb (added if unoccluded), bits(pixel)
+};
+
+enum : uint32_t { RAY_PRIMARY = 1u, RAY_BEER_SELF = 2u, RAY_BEER_SIBLING = 4u, RAY_SPECULAR = 8u };
+
+struct DCounters {
+    int32_t next_count, shadow_count, overflow, pad;
+    unsigned long long node_visits, prim_tests;
+};
+
+}  // namespace rt795

@@ -1,0 +1,452 @@
+// The wavefront kernels K1..K8 for sm_100a.
+//   K1 k_raygen   Camera::getPrimaryRay / PixelLBCorner / getSampleRay / AddDepthOfField (src/Camera.cpp:63-139)
+//   K2 k_extend   closest hit for a ray queue (traverse.cuh)
+//   K3 k_shade    surface evaluation + direct-light shadow-ray emission + continuation rays (shade.cuh)
+//   K4 k_shadow   occlusion query + accumulate
+//   K5            compaction is fused into K3: warp-ballot slot reservation + one atomicAdd per warp per queue
+//   K6 k_shade<RT_INTEGRATOR_PATH>   path-tracing bounce (NEE + Russian roulette)
+//   K7 k_tonemap_*  photographic tone map (log-average reduction, histogram white point, per-pixel map)
+//   K8 k_resolve  box-filter mean (src/Scene.cpp:409) into Image::_data layout (src/Image.cpp:17-24)
+#pragma once
+#include "shade.cuh"
+
+namespace rt795 {
+
+constexpr int kBlock = 128;
+
+// ---- warp-aggregated queue slot reservation (K5).  Must be called by all 32 lanes of the warp.
+RT_D int warp_reserve(int32_t* counter, int want /*0,1,2*/, int& total_out) {
+    const unsigned full = 0xffffffffu;
+    unsigned lane = threadIdx.x & 31u;
+    unsigned b1 = __ballot_sync(full, want >= 1), b2 = __ballot_sync(full, want >= 2);
+    unsigned lt = (1u << lane) - 1u;
+    int total = __popc(b1) + __popc(b2);
+    int base = 0;
+    if (lane == 0 && total) base = atomicAdd(counter, total);
+    base = __shfl_sync(full, base, 0);
+    total_out = total;
+    return base + __popc(b1 & lt) + __popc(b2 & lt);
+}
+
+RT_D int meta_pack(int depth, uint32_t flags, int beer_mat) { return (depth & 0xff) | (int)((flags & 0xffu) << 8) | (beer_mat << 16); }
+
+// ---- K1
+__global__ void __launch_bounds__(kBlock) k_raygen(DCamera cam, DTiling tl, RenderConsts rc, int max_depth, unsigned long long work_base, int count,
+                                                   DRayQueue q, int32_t* q_count, int center_only) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = i < count;
+    float3 o = v3(0.f, 0.f, 0.f), d = o;
+    float time = 0.f;
+    uint32_t pixel = 0, sample = 0;
+    if (active) {
+        unsigned long long w = work_base + (unsigned long long)i;
+        int spp = center_only ? 1 : cam.spp;
+        sample = (uint32_t)(w % (unsigned long long)spp);
+        unsigned long long rest = w / (unsigned long long)spp;
+        int tile_px = tl.tw * tl.th;
+        int pit = (int)(rest % (unsigned long long)tile_px);
+        int lt = (int)(rest / (unsigned long long)tile_px);
+        int k = lt * tl.count + tl.rank;
+        int tx = k % tl.tiles_x, ty = k / tl.tiles_x;
+        int sb = pit >> 5, ln = pit & 31, sbx = tl.tw >> 3;        // 8x4 sub-blocks: one warp = one compact pixel block
+        int x = tx * tl.tw + (sb % sbx) * 8 + (ln & 7), y = ty * tl.th + (sb / sbx) * 4 + (ln >> 3);
+        active = x < cam.nx && y < cam.ny;
+        if (active) {
+            pixel = (uint32_t)(y * cam.nx + x);
+            float3 pos = v3(cam.pos), gaze = v3(cam.gaze), up = v3(cam.up), right = v3(cam.right);
+            if (spp <= 1) {                                          // getPrimaryRay
+                float u = cam.l + (cam.r - cam.l) * (x + 0.5f) * cam.invnx;
+                float v = cam.t - (cam.t - cam.b) * (y + 0.5f) * cam.invny;
+                float3 m = pos + gaze * cam.dist;
+                m = m + u * right;
+                m = m + v * up;
+                o = pos; d = (m - pos) / length(m - pos); time = 0.f;
+            } else {                                                 // PixelLBCorner + getSampleRay (+ AddDepthOfField)
+                float u = cam.l + x * cam.pw;
+                float v = cam.t - (y + 1) * cam.ph;
+                float3 m = pos + gaze * cam.dist;
+                m = m + u * right;
+                m = m + v * up;
+                int si = (int)sample % cam.n, sj = (int)sample / cam.n;
+                float4 r = philox_uniform4(rc.seed, pixel, sample, 0u, DIM_CAMERA);
+                m = m + (si + r.x) * cam.sw * right;
+                m = m + (sj + r.y) * cam.sh * up;
+                o = pos; d = (m - pos) / length(m - pos);
+                if (cam.dof) {
+                    float3 q = pos;
+                    q = q + cam.aperture * (r.z - 0.5f) * right;
+                    q = q + cam.aperture * (r.w - 0.5f) * up;
+                    float3 dir = normalize0(m - pos);
+                    float t_fd = cam.focus / dot(dir, gaze);
+                    float3 p = o + d * t_fd;
+                    o = q; d = normalize0(p - q); time = 0.f;
+                } else time = r.z;
+            }
+        }
+    }
+    int total;
+    int slot = warp_reserve(q_count, active ? 1 : 0, total);
+    if (active) {
+        q.o_time[slot] = make_float4(o.x, o.y, o.z, time);
+        q.d_tmax[slot] = make_float4(d.x, d.y, d.z, 3.0e38f);
+        q.w_pixel[slot] = make_float4(1.f, 1.f, 1.f, __int_as_float((int)pixel));
+        q.meta[slot] = make_int4((int)sample, meta_pack(max_depth, RAY_PRIMARY | RAY_SPECULAR, 0), 1, 0);
+    }
+}
+
+// ---- K2
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_extend(DScene sc, DRayQueue q, int first, int count, DCounters* ctr) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    i += first;
+    float4 ot = q.o_time[i], dt = q.d_tmax[i];
+    HitRec h;
+    float3 o = v3(ot), d = v3(dt);
+    if (any_nan(o) || any_nan(d)) { h.prim = -1; h.obj = -1; h.t = 0.f; h.beta = h.gamma = 0.f; }   // src/Helper.cpp:28-30
+    else {
+        unsigned cn = 0, cp = 0;
+        trace<false, COUNT>(sc, o, d, ot.w, dt.w, h, cn, cp);
+        if (COUNT) { atomicAdd(&ctr->node_visits, (unsigned long long)cn); atomicAdd(&ctr->prim_tests, (unsigned long long)cp); }
+    }
+    q.hit[i] = make_float4(h.t, h.beta, h.gamma, __int_as_float(h.prim));
+    q.hit_obj[i] = h.obj;
+}
+
+// ---- K4
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_shadow(DScene sc, DShadowQueue sq, int count, float* accum, DCounters* ctr) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float4 ot = sq.o_time[i], dt = sq.d_tmax[i];
+    HitRec h;
+    float3 o = v3(ot), d = v3(dt);
+    bool occluded = false;
+    if (!(any_nan(o) || any_nan(d))) {
+        unsigned cn = 0, cp = 0;
+        occluded = trace<true, COUNT>(sc, o, d, ot.w, dt.w, h, cn, cp);
+        if (COUNT) { atomicAdd(&ctr->node_visits, (unsigned long long)cn); atomicAdd(&ctr->prim_tests, (unsigned long long)cp); }
+    }
+    if (!occluded) {
+        float4 c = sq.c_pixel[i];
+        accum_add(accum, (uint32_t)__float_as_int(c.w), v3(c));
+    }
+}
+
+// ---- K3 / K6
+struct RayOut { float3 o, d, w; float time; int sample, meta, node; float beer_s; };
+
+RT_D void write_ray(const DRayQueue& q, int slot, uint32_t pixel, const RayOut& r) {
+    q.o_time[slot] = make_float4(r.o.x, r.o.y, r.o.z, r.time);
+    q.d_tmax[slot] = make_float4(r.d.x, r.d.y, r.d.z, 3.0e38f);
+    q.w_pixel[slot] = make_float4(r.w.x, r.w.y, r.w.z, __int_as_float((int)pixel));
+    q.meta[slot] = make_int4(r.sample, r.meta, r.node, __float_as_int(r.beer_s));
+}
+
+template <int INTEGRATOR>
+__global__ void __launch_bounds__(kBlock) k_shade(DScene sc, DCamera cam, RenderConsts rc, DRayQueue in, int first, int count, DRayQueue out, DShadowQueue sq,
+                                                  DCounters* ctr, float* accum) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = i < count;
+    i += first;
+
+    // per-lane state that survives to the (warp-convergent) queue pushes
+    int n_out = 0;
+    RayOut r0, r1;
+    bool lit = false;                 // evaluate lights at this hit
+    Surface s;
+    RtMaterial mat;
+    float3 W = v3(0.f, 0.f, 0.f), rd = W;
+    float rtime = 0.f;
+    uint32_t pixel = 0, sample = 0, node = 0;
+
+    if (active) {
+        float4 ot = in.o_time[i], dt = in.d_tmax[i], wp = in.w_pixel[i], hr = in.hit[i];
+        int4 me = in.meta[i];
+        float3 ro = v3(ot);
+        rd = v3(dt); rtime = ot.w;
+        W = v3(wp);
+        pixel = (uint32_t)__float_as_int(wp.w);
+        sample = (uint32_t)me.x; node = (uint32_t)me.z;
+        int depth = me.y & 0xff;
+        uint32_t flags = ((uint32_t)me.y >> 8) & 0xffu;
+        int beer_mat = (int)((uint32_t)me.y >> 16);
+        HitRec h;
+        h.t = hr.x; h.beta = hr.y; h.gamma = hr.z; h.prim = __float_as_int(hr.w); h.obj = in.hit_obj[i];
+
+        if (INTEGRATOR == RT_INTEGRATOR_REFERENCE) {
+            // ---- Beer factors whose distance is only known after this ray's (or its sibling's) extend step (src/Scene.cpp:110-115)
+            if (flags & (RAY_BEER_SELF | RAY_BEER_SIBLING)) {
+                float t_b = h.t; bool hit_b = h.prim >= 0;
+                float s_b = __int_as_float(me.w);
+                if (flags & RAY_BEER_SIBLING) { float4 sh = in.hit[i - 1]; t_b = sh.x; hit_b = __float_as_int(sh.w) >= 0; }
+                if (hit_b) {
+                    float e = sc.shadow_eps;
+                    float dist = sqrtf(fmaxf(0.f, e * e + 2.f * t_b * e * s_b + t_b * t_b));   // |hit - p| with origin p -/+ eps*n
+                    const RtMaterial bm = sc.materials[beer_mat - 1];
+                    W = W * v3(expf(-bm.absorption_coeff[0] * dist), expf(-bm.absorption_coeff[1] * dist), expf(-bm.absorption_coeff[2] * dist));
+                }   // miss / TIR: indeterminate in the reference; defined as distance 0 here and in the oracle
+            }
+            if (h.prim < 0) {
+                if (flags & RAY_PRIMARY) accum_add(accum, pixel, W * background(sc, cam, pixel, rd));   // secondary miss = black (src/Scene.cpp:150-153)
+            } else {
+                s = eval_surface(sc, ro, rd, rtime, h);
+                mat = sc.materials[s.mat_index - 1];
+                if ((flags & RAY_PRIMARY) && s.dm == RT_DM_REPLACE_ALL) {                              // Scene::Shading, src/Scene.cpp:232-234
+                    accum_add(accum, pixel, W * s.tex_color);
+                } else {
+                    const float eps = sc.shadow_eps;
+                    auto reflect_ray = [&](float3 weight, uint32_t fl, int bmat, float bs) {            // MirrorReflectance, src/Scene.cpp:32-55
+                        float3 wo = -rd;
+                        float3 wr = -wo + s.N * 2.f * dot(s.N, wo);
+                        wr = wr / length(wr);
+                        if (mat.is_rough) {
+                            float3 u = orthonormal_u(wr), v = cross(wr, u);
+                            float4 r = philox_uniform4(rc.seed, pixel, sample, node, DIM_GLOSSY);
+                            wr = normalize0(wr + ((u * (r.x - 0.5f) + v * (r.y - 0.5f)) * mat.roughness));
+                        }
+                        RayOut r;
+                        r.o = s.P + s.N * eps; r.d = wr; r.w = weight; r.time = rtime; r.sample = (int)sample;
+                        r.meta = meta_pack(depth - 1, fl, bmat); r.node = (int)(node * 2u); r.beer_s = bs;
+                        return r;
+                    };
+                    if (mat.type == RT_MAT_NORMAL || depth <= 0) lit = true;
+                    else if (mat.type == RT_MAT_MIRROR) {
+                        lit = true;
+                        float3 w = W * v3(mat.mirror);
+                        if (!is_zero(w) && !any_nan(w)) { r0 = reflect_ray(w, 0u, 0, 0.f); n_out = 1; }
+                    } else if (mat.type == RT_MAT_CONDUCTOR) {
+                        lit = true;
+                        float f = conductor_fresnel(mat.refraction_index, mat.absorption_index, rd, s.N);
+                        float3 w = (W * f) * v3(mat.mirror);
+                        if (!is_zero(w) && !any_nan(w)) { r0 = reflect_ray(w, 0u, 0, 0.f); n_out = 1; }
+                    } else {   // dielectric: DielectricRefraction, src/Scene.cpp:57-118 + RecursiveShading :166-209
+                        float dp = dot(rd, s.N);
+                        float nt = mat.refraction_index, snell, n_t, n_i;
+                        float3 nn;
+                        bool entering = dp < 0.f;
+                        if (entering) { snell = 1.0f / nt; nn = s.N; n_t = nt; n_i = 1.f; }
+                        else { snell = nt; nn = -s.N; n_t = 1.f; n_i = nt; }
+                        float cosT = -dot(rd, nn);
+                        float3 left = (rd + nn * cosT) * snell;
+                        float sq = 1.f - (snell * snell) * (1.f - cosT * cosT);
+                        bool tir = sq < 0.f;
+                        float3 tdir = normalize0(left - nn * sqrtf(sq));
+                        float cos_t = -dot(tdir, nn), cos_i = cosT;
+                        float rpar = (n_t * cos_i - n_i * cos_t) / (n_t * cos_i + n_i * cos_t);
+                        float rper = (n_i * cos_i - n_t * cos_t) / (n_i * cos_i + n_t * cos_t);
+                        float F = 0.5f * (rpar * rpar + rper * rper);
+                        RayOut tr;
+                        tr.o = s.P - eps * nn; tr.d = tdir; tr.time = rtime; tr.sample = (int)sample; tr.node = (int)(node * 2u + 1u);
+                        // offset.dir for the Beer distance: origin - p = -eps*nn
+                        tr.beer_s = -dot(nn, tdir);
+                        if (entering) {
+                            lit = true;
+                            float3 wt = W * (1.f - F), wr = W * F;
+                            tr.w = wt; tr.meta = meta_pack(depth - 1, RAY_BEER_SELF, s.mat_index);
+                            bool okt = !is_zero(wt) && !any_nan(wt), okr = !is_zero(wr) && !any_nan(wr);
+                            if (okt) { r0 = tr; n_out = 1; }
+                            if (okr) { RayOut rr = reflect_ray(wr, 0u, 0, 0.f); if (n_out) r1 = rr; else r0 = rr; n_out++; }
+                        } else if (tir) {
+                            // beer * Rec(reflected) with the Beer distance of a NaN ray: defined as 0 -> weight unchanged
+                            if (!is_zero(W) && !any_nan(W)) { r0 = reflect_ray(W, 0u, 0, 0.f); n_out = 1; }
+                        } else {
+                            // outside = (1-F) Rec(refracted); reflected = F * beer(|hit(refracted) - p|) * Rec(reflected): the
+                            // reflected sibling reads the refracted ray's hit distance from slot-1 in the next shade pass
+                            float3 wt = W * (1.f - F), wr = W * F;
+                            tr.w = wt; tr.meta = meta_pack(depth - 1, 0u, 0);
+                            bool okr = !is_zero(wr) && !any_nan(wr);
+                            bool okt = (!is_zero(wt) && !any_nan(wt)) || okr;     // keep the refracted ray alive if its sibling needs its distance
+                            if (any_nan(wt)) tr.w = v3(0.f, 0.f, 0.f);
+                            if (okt) { r0 = tr; n_out = 1; }
+                            if (okr) { r1 = reflect_ray(wr, RAY_BEER_SIBLING, s.mat_index, tr.beer_s); n_out = 2; }
+                        }
+                    }
+                    if (lit) accum_add(accum, pixel, W * (v3(sc.ambient) * v3(mat.ambient)));          // Scene::ambient, src/Scene.cpp:22-30
+                }
+            }
+        } else {
+            // ---- K6 path-tracing bounce (no reference code; DESIGN.md §Path tracer; oracle/restate.cpp PathTrace is the twin)
+            bool count_emission = (flags & RAY_SPECULAR) != 0;
+            int max_depth = rc.pt_max_depth;
+            if (h.prim < 0) {
+                if (node == 1u || (sc.env_light != -1 && (count_emission || !rc.pt_nee))) accum_add(accum, pixel, W * background(sc, cam, pixel, rd));
+            } else {
+                s = eval_surface(sc, ro, rd, rtime, h);
+                mat = sc.materials[s.mat_index - 1];
+                float3 Le = v3(mat.emission);
+                if ((Le.x > 0.f || Le.y > 0.f || Le.z > 0.f) && (count_emission || !rc.pt_nee) && dot(s.N, rd) < 0.f) accum_add(accum, pixel, W * Le);
+                if ((int)node < max_depth + 1) {
+                    const float eps = sc.shadow_eps;
+                    float3 n = s.N;
+                    RayOut r;
+                    r.time = rtime; r.sample = (int)sample; r.node = (int)(node + 1u); r.beer_s = 0.f;
+                    if (mat.type == RT_MAT_MIRROR || mat.type == RT_MAT_CONDUCTOR) {
+                        float3 wo = -rd;
+                        float3 wr = normalize0(-wo + n * 2.f * dot(n, wo));
+                        float f = mat.type == RT_MAT_CONDUCTOR ? conductor_fresnel(mat.refraction_index, mat.absorption_index, rd, n) : 1.0f;
+                        r.w = (W * v3(mat.mirror)) * f;
+                        r.o = s.P + n * eps; r.d = wr; r.meta = meta_pack(0, RAY_SPECULAR, 0);
+                        if (!is_zero(r.w) && !any_nan(r.w)) { r0 = r; n_out = 1; }
+                    } else if (mat.type == RT_MAT_DIELECTRIC) {
+                        float dp = dot(rd, n), nt = mat.refraction_index;
+                        float snell = dp < 0.f ? 1.0f / nt : nt, n_t = dp < 0.f ? nt : 1.0f, n_i = dp < 0.f ? 1.0f : nt;
+                        float3 nn = dp < 0.f ? n : -n;
+                        float ci = -dot(rd, nn);
+                        float sq = 1.f - snell * snell * (1.f - ci * ci);
+                        float4 u4 = philox_uniform4(rc.seed, pixel, sample, node, DIM_PT_BSDF);
+                        float F = 1.0f;
+                        float3 tdir = v3(0.f, 0.f, 0.f);
+                        if (sq >= 0.f) {
+                            tdir = normalize0((rd + nn * ci) * snell - nn * sqrtf(sq));
+                            float ct = -dot(tdir, nn);
+                            float rpar = (n_t * ci - n_i * ct) / (n_t * ci + n_i * ct), rper = (n_i * ci - n_t * ct) / (n_i * ci + n_t * ct);
+                            F = 0.5f * (rpar * rpar + rper * rper);
+                        }
+                        r.w = W;
+                        if (u4.x < F) { r.o = s.P + nn * eps; r.d = normalize0(rd + nn * 2.f * ci); }
+                        else {
+                            if (dp >= 0.f) r.w = W * v3(expf(-mat.absorption_coeff[0] * h.t), expf(-mat.absorption_coeff[1] * h.t), expf(-mat.absorption_coeff[2] * h.t));
+                            r.o = s.P - nn * eps; r.d = tdir;
+                        }
+                        r.meta = meta_pack(0, RAY_SPECULAR, 0);
+                        if (!is_zero(r.w) && !any_nan(r.w)) { r0 = r; n_out = 1; }
+                    } else {
+                        if (dot(n, rd) > 0.f) n = -n;
+                        s.N = n;
+                        lit = rc.pt_nee != 0;
+                        float4 u4 = philox_uniform4(rc.seed, pixel, sample, node, DIM_PT_BSDF);
+                        const float pi = 3.14159265358979323846f;
+                        float3 u = orthonormal_u(n), w = cross(n, u);
+                        float3 wi; float pdf;
+                        if (rc.pt_importance) {
+                            float rr = sqrtf(u4.x), ph = 2.0f * pi * u4.y;
+                            wi = normalize0(u * (rr * cosf(ph)) + n * sqrtf(fmaxf(0.f, 1.f - u4.x)) + w * (rr * sinf(ph)));
+                            pdf = fmaxf(1e-8f, dot(wi, n)) / pi;
+                        } else {
+                            float y = u4.x, rr = sqrtf(fmaxf(0.f, 1.f - y * y)), ph = 2.0f * pi * u4.y;
+                            wi = normalize0(u * (rr * cosf(ph)) + n * y + w * (rr * sinf(ph)));
+                            pdf = 1.0f / (2.0f * pi);
+                        }
+                        float cosi = fmaxf(0.f, dot(wi, n));
+                        float3 f = mat.brdf != RT_BRDF_NONE ? term_brdf(mat, wi, -rd, n) : v3(mat.diffuse) / pi;
+                        float3 beta = (W * f) * (cosi / pdf);
+                        bool alive = !any_nan(beta);
+                        if (alive && rc.pt_rr && node >= 2u) {
+                            float q = fminf(0.95f, fmaxf(0.05f, fmaxf(beta.x, fmaxf(beta.y, beta.z))));
+                            float4 rr4 = philox_uniform4(rc.seed, pixel, sample, node, DIM_PT_RR);
+                            if (rr4.x >= q) alive = false; else beta = beta / q;
+                        }
+                        if (alive && !is_zero(beta)) {
+                            r.w = beta; r.o = s.P + n * eps; r.d = wi; r.meta = meta_pack(0, 0u, 0);
+                            r0 = r; n_out = 1;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- continuation rays -> next queue (pairs stay adjacent: slot, slot+1)
+    {
+        int total;
+        int slot = warp_reserve(&ctr->next_count, n_out, total);
+        if (n_out) {
+            if (slot + n_out > rc.queue_cap) atomicExch(&ctr->overflow, 1);
+            else { write_ray(out, slot, pixel, r0); if (n_out == 2) write_ray(out, slot + 1, pixel, r1); }
+        }
+    }
+    // ---- direct lighting: one shadow ray per light with a non-zero unoccluded contribution (Scene::BasicShading loop, src/Scene.cpp:252-264)
+    unsigned any_lit = __ballot_sync(0xffffffffu, lit);
+    if (any_lit) {
+        for (int li = 0; li < sc.num_lights; li++) {
+            LightSample ls;
+            bool emit = false;
+            float3 c = v3(0.f, 0.f, 0.f);
+            if (lit && light_eval(sc, li, mat, s, rd, rc.seed, pixel, sample, node, ls)) {
+                c = W * ls.radiance;
+                emit = !is_zero(c) && !any_nan(c);
+            }
+            int total;
+            int slot = warp_reserve(&ctr->shadow_count, emit ? 1 : 0, total);
+            if (emit) {
+                if (slot >= rc.shadow_cap) atomicExch(&ctr->overflow, 1);
+                else {
+                    float3 so = s.P + s.N * sc.shadow_eps;
+                    sq.o_time[slot] = make_float4(so.x, so.y, so.z, rtime);
+                    sq.d_tmax[slot] = make_float4(ls.wi.x, ls.wi.y, ls.wi.z, ls.tmax);
+                    sq.c_pixel[slot] = make_float4(c.x, c.y, c.z, __int_as_float((int)pixel));
+                }
+            }
+        }
+    }
+}
+
+// ---- K8
+__global__ void k_resolve(const float* __restrict__ accum, float* __restrict__ out, int n3, float inv_spp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n3) out[i] = accum[i] * inv_spp;
+}
+
+// ---- primary-hit dump for rt_trace_primary (parity harness)
+__global__ void k_primary_hits(DScene sc, DRayQueue q, int count, RtHit* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float4 ot = q.o_time[i], dt = q.d_tmax[i], hr = q.hit[i];
+    uint32_t pixel = (uint32_t)__float_as_int(q.w_pixel[i].w);
+    RtHit r;
+    r.full = 0; r.object = 0; r.primitive = 0; r.t = 0.f;
+    r.point[0] = r.point[1] = r.point[2] = 0.f; r.normal[0] = r.normal[1] = r.normal[2] = 0.f;
+    HitRec h;
+    h.t = hr.x; h.beta = hr.y; h.gamma = hr.z; h.prim = __float_as_int(hr.w); h.obj = q.hit_obj[i];
+    if (h.prim >= 0) {
+        Surface s = eval_surface(sc, v3(ot), v3(dt), ot.w, h);
+        r.full = 1; r.object = h.obj; r.primitive = s.prim_in_mesh; r.t = h.t;
+        r.point[0] = s.P.x; r.point[1] = s.P.y; r.point[2] = s.P.z;
+        r.normal[0] = s.N.x; r.normal[1] = s.N.y; r.normal[2] = s.N.z;
+    }
+    out[pixel] = r;
+}
+
+// ---- K7 photographic tone map (Reinhard et al. 2002 global operator; DESIGN.md §Tone map)
+RT_D float luminance(float r, float g, float b) { return 0.2126f * r + 0.7152f * g + 0.0722f * b; }
+
+__global__ void k_tonemap_logsum(const float* __restrict__ rgb, int npix, double* sum_log, float* max_lum) {
+    float acc = 0.f, mx = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        float L = luminance(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+        if (!(L >= 0.f)) L = 0.f;
+        acc += logf(1e-5f + L);
+        mx = fmaxf(mx, L);
+    }
+    for (int o = 16; o; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(sum_log, (double)acc); atomicMax((int*)max_lum, __float_as_int(mx)); }
+}
+constexpr int kTmBins = 4096;
+__global__ void k_tonemap_hist(const float* __restrict__ rgb, int npix, float scale, float max_scaled, unsigned* hist) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        float L = luminance(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+        if (!(L >= 0.f)) L = 0.f;
+        float Ls = L * scale;
+        int b = (int)(Ls / max_scaled * (kTmBins - 1));
+        b = b < 0 ? 0 : (b >= kTmBins ? kTmBins - 1 : b);
+        atomicAdd(&hist[b], 1u);
+    }
+}
+__global__ void k_tonemap_map(const float* __restrict__ rgb, int npix, float scale, float lwhite, float saturation, float inv_gamma, uint8_t* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    float r = rgb[3 * i], g = rgb[3 * i + 1], b = rgb[3 * i + 2];
+    float L = luminance(r, g, b);
+    if (!(L > 0.f)) { out[3 * i] = out[3 * i + 1] = out[3 * i + 2] = 0; return; }
+    float Ls = L * scale;
+    float Ld = Ls * (1.f + Ls / (lwhite * lwhite)) / (1.f + Ls);
+    float c[3] = {r, g, b};
+    for (int k = 0; k < 3; k++) {
+        float v = powf(fmaxf(c[k], 0.f) / L, saturation) * Ld;
+        v = fminf(1.f, fmaxf(0.f, v));
+        out[3 * i + k] = (uint8_t)(255.f * powf(v, inv_gamma) + 0.5f);
+    }
+}
+
+}  // namespace rt795

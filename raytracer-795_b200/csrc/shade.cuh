@@ -1,0 +1,197 @@
+// K3 device code: direct lighting, BRDFs, Whitted continuation rays, path-tracing bounce.
+//
+// Follows Scene::Shading / RecursiveShading / BasicShading (src/Scene.cpp:148-267), MirrorReflectance (:32-55),
+// DielectricRefraction (:57-118), FresnelReflectance / BeerLaw / ConductorFresnel (:120-146), the five light classes
+// (src/Light.cpp:168-660) and Light::BRDF / TermBRDF (:62-162).  The reference's recursion becomes weighted rays:
+// a ray carries the product of the factors the reference multiplies its subtree by (mirrorRef, Fresnel, 1-Fresnel,
+// Beer); leaves add weight * radiance into the pixel accumulator.
+#pragma once
+#include "surface.cuh"
+
+namespace rt795 {
+
+struct RenderConsts {
+    uint64_t seed;
+    int integrator;
+    int pt_max_depth, pt_nee, pt_rr, pt_importance;
+    int queue_cap, shadow_cap;
+};
+
+RT_D float3 orthonormal_u(float3 v) {                         // GeometryHelpers::GetOrthonormalUVector, src/Helper.cpp:322-343
+    float a = fabsf(v.x), b = fabsf(v.y), c = fabsf(v.z);
+    float3 nl = v;
+    if (a <= b && a <= c) nl.x = 1.f; else if (b <= a && b <= c) nl.y = 1.f; else nl.z = 1.f;
+    return normalize0(cross(v, nl));
+}
+
+RT_D float conductor_fresnel(float n_t, float k_t, float3 d, float3 normal) {   // src/Scene.cpp:135-146, src/Light.cpp:18-28
+    float cos_t = -dot(d, normal);
+    float two = 2.f * n_t * cos_t, c2 = cos_t * cos_t, nk = n_t * n_t + k_t * k_t;
+    float rs = (nk - two + c2) / (nk + two + c2);
+    float rp = (nk * c2 - two + 1.f) / (nk * c2 + two + 1.f);
+    return 0.5f * (rs + rp);
+}
+
+RT_D float ipow(float x, int p) { return powf(x, (float)p); }   // pow(float, int) of the reference (promoted to double there)
+
+RT_D float3 term_brdf(const RtMaterial& m, float3 wi, float3 wo, float3 n) {     // Light::TermBRDF, src/Light.cpp:62-155
+    const float pi = 3.14159265358979323846f, eps = 0.001f;
+    float3 kd = v3(m.diffuse), ks = v3(m.specular);
+    int p = m.phong_exp;
+    switch (m.brdf) {
+        case RT_BRDF_MP: case RT_BRDF_OP: case RT_BRDF_MPN: {
+            float3 wr = -wi + n * 2.f * dot(n, wi);
+            wr = wr / length(wr);
+            float ca = fmaxf(0.f, dot(wr, wo));
+            if (m.brdf == RT_BRDF_MP) return kd + ks * ipow(ca, p);
+            if (m.brdf == RT_BRDF_OP) {
+                float ci = fmaxf(0.f, dot(wi, n));
+                if (ci < eps) return v3(0.f, 0.f, 0.f);
+                return kd + (ks * ipow(ca, p)) / ci;
+            }
+            return kd / pi + ks * ((p + 2) / (2.f * pi)) * ipow(ca, p);
+        }
+        case RT_BRDF_MBP: case RT_BRDF_OBP: case RT_BRDF_MBPN: {
+            float3 h = normalize0(wo + wi);
+            float ca = fmaxf(0.f, dot(n, h));
+            if (m.brdf == RT_BRDF_MBP) return kd + ks * ipow(ca, p);
+            if (m.brdf == RT_BRDF_OBP) {
+                float ci = fmaxf(0.f, dot(wi, n));
+                if (ci < eps) return v3(0.f, 0.f, 0.f);
+                return kd + (ks * ipow(ca, p)) / ci;
+            }
+            return kd / pi + ks * ((p + 8) / (8.f * pi)) * ipow(ca, p);
+        }
+        case RT_BRDF_TS: case RT_BRDF_TSF: {
+            float3 wh = normalize0(wo + wi);
+            float3 dpart = kd / pi;
+            float f = 1.f;
+            if (m.brdf == RT_BRDF_TSF) { f = conductor_fresnel(m.refraction_index, m.absorption_index, -wo, n); dpart = dpart * (1.f - f); }
+            float cosA = dot(wh, n), cosT = dot(wi, n), cosP = dot(wo, n);
+            float left = 2.f * dot(n, wh) * dot(n, wo) / dot(wo, wh);
+            float right = 2.f * dot(n, wh) * dot(n, wi) / dot(wi, wh);
+            float g = fminf(1.f, fminf(left, right));
+            float dd = ((p + 2.f) / (2.f * pi)) * ipow(cosA, p);
+            float3 sp = (ks * g * dd) / (4.f * cosP * cosT);
+            if (m.brdf == RT_BRDF_TSF) sp = sp * f;
+            return dpart + sp;
+        }
+        default: return v3(0.f, 0.f, 0.f);
+    }
+}
+
+// Light::BRDF (src/Light.cpp:157-162) or *Light::Diffuse + Specular (e.g. :206-236): outgoing radiance for irradiance E from wi.
+RT_D float3 surface_response(const RtMaterial& m, const Surface& s, float3 ray_d, float3 wi, float3 E) {
+    if (m.brdf != RT_BRDF_NONE) return (E * term_brdf(m, wi, -ray_d, s.N)) * fmaxf(0.f, dot(wi, s.N));
+    float alpha = fmaxf(0.f, dot(s.N, wi));
+    float3 kd;
+    if (s.dm == RT_DM_REPLACE_KD) kd = s.tex_color / s.tex_normalizer;
+    else if (s.dm == RT_DM_BLEND_KD) kd = (v3(m.diffuse) + (s.tex_color / s.tex_normalizer)) * 0.5f;
+    else kd = v3(m.diffuse);
+    float3 diffuse = E * (kd * alpha);
+    float3 wo = -ray_d;
+    float3 h = (wo + wi) / length(wo + wi);
+    float a2 = fmaxf(0.f, dot(s.N, h));
+    float3 specular = E * (v3(m.specular) * ipow(a2, m.phong_exp));
+    return diffuse + specular;
+}
+
+struct LightSample { float3 wi; float3 radiance; float tmax; };   // radiance = reflected radiance if unoccluded (before path weight)
+
+// *Light::BasicShading (src/Light.cpp:238-250, 306-321, 405-436, 522-545, 628-660) minus the shadow query, which is
+// emitted as a shadow ray (direction wi from P + N*eps, occluding interval (0, tmax)) - SURVEY A.5.
+RT_D bool light_eval(const DScene& sc, int li, const RtMaterial& m, const Surface& s, float3 ray_d, uint64_t seed, uint32_t pixel, uint32_t sample,
+                     uint32_t node, LightSample& out) {
+    const float pi = 3.14159265358979323846f;
+    const RtLight L = sc.lights[li];
+    const float eps = sc.shadow_eps;
+    float3 P = s.P, N = s.N;
+    float3 target;
+    bool finite = true;
+    float falloff = 1.f;
+    float3 E;
+    switch (L.type) {
+        case RT_LIGHT_POINT: {
+            target = v3(L.position);
+            float dist = length(P - target);
+            E = v3(L.intensity) / (dist * dist);
+        } break;
+        case RT_LIGHT_DIRECTIONAL: {
+            out.wi = -normalize0(v3(L.direction));
+            E = v3(L.intensity);
+            finite = false;
+        } break;
+        case RT_LIGHT_SPOT: {
+            target = v3(L.position);
+            float3 dir = normalize0(v3(L.direction));
+            float coverage = (L.coverage_deg * 0.5f) * (pi / 180.0f), fall = (L.falloff_deg * 0.5f) * (pi / 180.0f);
+            float angle = acosf(dot(normalize0(P - target), dir));
+            if (angle < fall) falloff = 1.f;
+            else if (angle < coverage) { float cf = cosf(fall), cc = cosf(coverage); float q = (cosf(angle) - cc) / (cf - cc); falloff = (q * q) * (q * q); }
+            else return false;
+            float dist = length(P - target);
+            E = v3(L.intensity) / (dist * dist);
+        } break;
+        case RT_LIGHT_AREA: {
+            float3 ln = normalize0(v3(L.direction));
+            float3 u = orthonormal_u(ln), v = cross(ln, u);
+            float4 r = philox_uniform4(seed, pixel, sample, node, DIM_LIGHT0 + li * DIM_LIGHT_STRIDE);
+            target = v3(L.position) + (u * L.size * (r.x - 0.5f)) + (v * L.size * (r.y - 0.5f));
+            float3 dtp = normalize0(P - target);
+            float cosT = fabsf(dot(dtp, ln));
+            float dsq = length(P - target); dsq = dsq * dsq;
+            E = v3(L.intensity) * ((L.size * L.size) * (cosT / dsq));
+        } break;
+        default: {   // RT_LIGHT_ENVIRONMENT
+            float3 u = orthonormal_u(N), w = cross(N, u);
+            float3 dir = N;
+            for (int it = 0; it < 64; it++) {
+                float4 r = philox_uniform4(seed, pixel, sample, node, DIM_LIGHT0 + li * DIM_LIGHT_STRIDE + it);
+                float x = r.x * 2.f - 1.0f, y = r.y * 2.f - 1.0f, z = r.z * 2.f - 1.0f;
+                float3 dd = (P + u * x + N * y + w * z) - P;
+                if (dot(dd, N) > 0.f && length(dd) <= 1.f) { dir = normalize0(dd); break; }
+            }
+            out.wi = dir;
+            E = env_lookup(sc, L.image, dir) * 2.0f * pi;
+            finite = false;
+        } break;
+    }
+    if (finite) {
+        float3 dv = target - P;
+        float D = length(dv);
+        out.wi = dv / D;
+        float sdot = dot(N, out.wi);
+        // occluded iff the closest hit h satisfies |P-h| < |P-target| with h = P + N*eps + t*wi  
+        out.tmax = -eps * sdot + sqrtf(fmaxf(0.f, eps * eps * sdot * sdot - eps * eps + D * D));
+    } else out.tmax = 3.0e38f;
+    // the reference normalises (target - P) again for wi (e.g. src/Light.cpp:243); same vector
+    out.radiance = surface_response(m, s, ray_d, out.wi, E) * falloff;
+    return true;
+}
+
+// Scene::GetBackgroundColor, src/Scene.cpp:413-435.  At 1 spp the reference's pixel-uv lookup is transposed.
+RT_D float3 background(const DScene& sc, const DCamera& cam, uint32_t pixel, float3 d) {
+    if (sc.env_light != -1) {
+        const RtLight L = sc.lights[sc.env_light];
+        if (L.type != RT_LIGHT_ENVIRONMENT) return v3(sc.background);
+        return env_lookup(sc, L.image, d);
+    }
+    if (sc.background_texture == -1) return v3(sc.background);
+    const RtTexture tx = sc.textures[sc.background_texture];
+    if (tx.type != RT_TEX_IMAGE) return v3(sc.background);
+    int x = (int)(pixel % (uint32_t)cam.nx), y = (int)(pixel / (uint32_t)cam.nx);
+    float u, v;
+    if (cam.spp <= 1) { u = ((float)y) / cam.nx; v = ((float)x) / cam.ny; }
+    else { u = ((float)x) / cam.nx; v = ((float)y) / cam.ny; }
+    return image_lookup(sc.images[tx.image], tx.interpolation, u, v);
+}
+
+RT_D void accum_add(float* accum, uint32_t pixel, float3 c) {
+    if (any_nan(c)) return;                      // NanCheck (src/Scene.cpp:221-228) applied per contribution
+    float* p = accum + (size_t)pixel * 3;
+    if (c.x != 0.f) atomicAdd(p, c.x);
+    if (c.y != 0.f) atomicAdd(p + 1, c.y);
+    if (c.z != 0.f) atomicAdd(p + 2, c.z);
+}
+
+}  // namespace rt795
