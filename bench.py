@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py - Mrays/s and ms/frame of the rendering hot path on N B200s, with roofline + CPU baseline.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` (N>1 under torchrun, one rank per
+GPU) prints ONE JSON line on rank 0.  A "step" is one frame of the workload: generate -> extend -> shade -> shadow
+-> resolve for every pixel sample of the camera, image tiles interleaved over the N ranks, framebuffer reduced to
+rank 0 over NCCL at frame end.  The workload at every N is BASELINE.json's headline configuration C4 (~870k-triangle
+mesh x 16 instances, 1920x1080, 64 spp), so N>1 is STRONG scaling of one frame.
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/ref_raytracer = the UNMODIFIED reference
+compiled against stand-in headers; else the oracle port) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+# ALGORITHMIC bytes per ray, SURVEY.md §8d:  B_ray = 48 + 32*(ceil(log2 N_top) + ceil(log2(N_tri/4))) + 48*4 + 64*[instanced]
+B_RAY = {"c1": 224, "c2": 400, "c3": 784, "c4": 1040, "c5": 416}
+
+WORKLOADS = {
+    # name: (generator kwargs for the full configuration, kwargs for the bounded CPU sample)
+    "c4": (dict(res=(1920, 1080), spp=64, n=660), dict(res=(480, 270), spp=4, n=660)),
+    "c3": (dict(res=(1920, 1080), spp=16, n=187), dict(res=(480, 270), spp=4, n=187)),
+    "c2": (dict(res=1024, spp=100), dict(res=128, spp=16)),
+    "c1": (dict(res=800), dict(res=800)),
+    "c5": (dict(res=(3840, 2160), spp=1024), dict(res=(240, 135), spp=4)),
+}
+
+
+def scene_cache_dir() -> str:
+    d = os.environ.get("RT795_SCENE_CACHE", os.path.join(tempfile.gettempdir(), "rt795_scenes"))
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def make_scene(rt, config: str, kw: dict, tag: str) -> str:
+    d = os.path.join(scene_cache_dir(), f"{config}_{tag}")
+    xml = os.path.join(d, f"{config}.xml")
+    if not os.path.exists(xml):
+        rt.scenes.CONFIGS[config]["gen"](d, **kw)
+    return xml
+
+
+class ClockSampler:
+    """nvidia-smi clocks line of /opt/skills/guides/B200_PROFILING.md, sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(config: str):
+    """dram bytes per k_extend launch from the committed ncu --set full summary, if one exists for this workload."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(config, {}).get("k_extend_dram_bytes_per_launch")
+    return None
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def ref_binary() -> str | None:
+    p = os.path.join(ROOT, "oracle", "_ref", "ref_raytracer")
+    return p if os.path.exists(p) else None
+
+
+def count_reference_rays(rt, xml: str) -> int:
+    """Closest-hit queries the reference algorithm issues for this scene (counted by the instrumented oracle port;
+    the reference itself cannot count).  CPU only."""
+    hs = rt.HostScene(xml)
+    lib = rt.load_oracle()
+    lib.oracle_ray_queries(1)
+    rt.oracle_render(hs.desc, hs.camera(0), threads=os.cpu_count() or 1)
+    n = int(lib.oracle_ray_queries(1))
+    hs.close()
+    return n
+
+
+def time_reference_once(rt, xml: str) -> tuple[float, str, int]:
+    """Render-only seconds of one frame on the host cores.  Returns (seconds, kind, cores)."""
+    exe = ref_binary()
+    if exe:
+        with tempfile.TemporaryDirectory() as td:
+            r = subprocess.run([exe, xml], cwd=td, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, check=True)
+        m = re.search(r"RT795_RENDER_SECONDS ([0-9.eE+-]+)", r.stderr)
+        return float(m.group(1)), "reference", 8          # 8 hard-coded std::threads, src/Scene.cpp:272, 340-347
+    hs = rt.HostScene(xml)
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    rt.oracle_render(hs.desc, hs.camera(0), threads=cores)
+    dt = time.perf_counter() - t0
+    hs.close()
+    return dt, "port", cores
+
+
+def run_reference_arm(args, rt):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    full_kw, sample_kw = WORKLOADS[args.config]
+    xml = make_scene(rt, args.config, sample_kw, "sample")
+    rays = count_reference_rays(rt, xml)
+    for _ in range(args.warmup):
+        time_reference_once(rt, xml)
+    secs, kind, cores = [], "reference", 8
+    for _ in range(args.steps):
+        s, kind, cores = time_reference_once(rt, xml)
+        secs.append(s)
+    ms = 1e3 * float(np.mean(secs))
+    val = rays / (ms * 1e-3) / 1e6
+    sample = f"{args.config} scene at {sample_kw} (full: {full_kw}); rays = closest-hit queries counted by the oracle port"
+    line = {"impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": rt.scenes.CONFIGS[args.config]["label"], "sample": sample, "rays_per_step": rays},
+            "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args, rt):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the rendering core has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    full_kw, sample_kw = WORKLOADS[args.config]
+    if args.small:
+        full_kw = sample_kw
+    if rank == 0:
+        xml = make_scene(rt, args.config, full_kw, "small" if args.small else "full")
+    barrier()
+    xml = make_scene(rt, args.config, full_kw, "small" if args.small else "full")
+    hs = rt.HostScene(xml)
+    cam = hs.camera(0)
+    sc = rt.Scene(hs.desc, local)
+    integrator = rt.RT_INTEGRATOR_PATH if args.config == "c5" else rt.RT_INTEGRATOR_REFERENCE
+    opts = rt.default_opts(integrator=integrator, tile_rank=rank, tile_count=world)
+    npix = cam.nx * cam.ny
+    frame = torch.zeros(npix * 3, dtype=torch.float32, device=dev)
+    host_frame = torch.empty(npix * 3, dtype=torch.float32).pin_memory()
+    cam_host = torch.frombuffer(bytearray(bytes(cam)) + bytearray(bytes(opts)), dtype=torch.uint8).pin_memory()
+    cam_dev = torch.empty_like(cam_host, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def render_step(o):
+        sc.render_device(cam, o, frame.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.reduce(frame, dst=0, op=dist.ReduceOp.SUM)   # tiles are disjoint: x + 0 = x, exact gather over NVLink
+
+    def e2e_step(o):
+        cam_dev.copy_(cam_host, non_blocking=True)            # this step's inputs (camera + options) from pinned host memory
+        render_step(o)
+        if rank == 0:
+            host_frame.copy_(frame, non_blocking=True)        # the step's result: the gathered framebuffer
+        torch.cuda.synchronize()
+
+    launches = 0
+    traced = [0, 0, 0]
+
+    def timed(step_fn, steps):
+        nonlocal launches, traced
+        total = 0.0
+        for _ in range(steps):
+            flush.fill_(1)                                    # L2 flush between timed iterations
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step_fn(opts)
+            e1.record(stream)
+            barrier()
+            total += e0.elapsed_time(e1)
+            st = sc.stats()
+            launches += int(st.launches)
+            traced = [int(st.rays_primary), int(st.rays_secondary), int(st.rays_shadow)]
+        t = torch.tensor([total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        render_step(opts)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches = 0
+    ms_total = timed(render_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    timed_launches = launches
+    ms_e2e = timed(e2e_step, args.steps)
+
+    rays_local = torch.tensor(traced, dtype=torch.float64, device=dev)
+    lt = torch.tensor([timed_launches], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(rays_local)
+        dist.all_reduce(lt)
+    rays = [int(x) for x in rays_local.tolist()]
+    rays_frame = sum(rays)
+    ms_step = ms_total / args.steps
+    value = rays_frame / (ms_step * 1e-3) / 1e6
+    e2e_value = rays_frame / (ms_e2e / args.steps * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (k_extend): one extra frame with per-stage CUDA events (serialises stages)
+    so = rt.default_opts(integrator=integrator, tile_rank=rank, tile_count=world, collect_counters=1)
+    render_step(so)
+    torch.cuda.synchronize()
+    st = sc.stats()
+    ext_rays = int(st.rays_primary + st.rays_secondary)
+    peak, peak_src = measured_peaks()
+    b_ray = B_RAY[args.config]
+    achieved = ext_rays * b_ray / (st.ms_extend * 1e-3) / 1e9 if st.ms_extend > 0 else 0.0
+    stage = {"ms_extend": st.ms_extend, "ms_shade": st.ms_shade, "ms_shadow": st.ms_shadow, "ms_raygen": st.ms_raygen, "ms_resolve": st.ms_resolve,
+             "launches_extend": int(st.launches_extend), "launches_shadow": int(st.launches_shadow)}
+    roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.config),
+                "peak_source": peak_src, "algorithmic_bytes_per_ray": b_ray, "rays_per_launch": ext_rays / max(1, int(st.launches_extend)),
+                "avg_launch_ms": st.ms_extend / max(1, int(st.launches_extend)), "stage_ms": stage,
+                "note": "scene (tris+BVH) fits the 126 MB L2, so the HBM roofline is a reference line, not the binding limit; see DESIGN.md"}
+    sstats = sc.stats()
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sxml = make_scene(rt, args.config, sample_kw, "sample")
+        secs, kind, cores = time_reference_once(rt, sxml)
+        rrays = count_reference_rays(rt, sxml)
+        cpu_baseline = {"value": rrays / secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind, "seconds": secs,
+                        "sample": f"{args.config} scene at {sample_kw}: {rrays} closest-hit queries (counted by the oracle port) in {secs:.2f} s render-only"}
+
+    if rank == 0:
+        line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": rt.scenes.CONFIGS[args.config]["label"] + (" [--small sample]" if args.small else ""),
+                           "resolution": [cam.nx, cam.ny], "spp": cam.num_samples, "rays_per_frame": {"primary": rays[0], "secondary": rays[1], "shadow": rays[2]},
+                           "integrator": "path" if integrator else "reference", "parallelism": f"tiles16x16-interleaved-x{world}", "l2": "flushed between steps (256 MB write)",
+                           "scene_bytes": {"bvh": int(sstats.bvh_bytes), "triangles": int(sstats.tri_bytes)}, "bvh_build_ms": sstats.ms_bvh_build},
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(cam_host.numel()), "d2h_bytes_per_step": int(npix * 12)},
+                "gpu_launches": int(lt.item()), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line), flush=True)
+    sc.close()
+    hs.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--small", action="store_true", help="use the bounded sample configuration (smoke runs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rt = ge.load_package()
+    if args.impl == "reference":
+        run_reference_arm(args, rt)
+    else:
+        run_ours(args, rt)
+
+
+if __name__ == "__main__":
+    main()

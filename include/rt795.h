@@ -202,7 +202,8 @@ typedef struct RtRenderOpts {
     /* engine knobs (0 -> defaults) */
     int32_t wave_rays;        /* primary rays generated per wave                    */
     int32_t queue_capacity;   /* entries per ray-queue level                        */
-    int32_t collect_counters; /* 1: per-ray node / primitive-test counters into RtStats (slower build of the kernels) */
+    int32_t collect_counters; /* bit 0: per-stage CUDA-event timing into RtStats.ms_* (serialises stages);
+                                 bit 1: per-ray node-visit / primitive-test counters into RtStats (slower kernels) */
 } RtRenderOpts;
 
 /* Primary-hit record for parity/debug (rt_trace_primary); mirrors what the oracle hit harness dumps. */
@@ -221,7 +222,8 @@ typedef struct RtStats {
     uint64_t waves;
     uint64_t node_visits, prim_tests;                     /* only with collect_counters */
     double ms_total;          /* first launch -> framebuffer ready (CUDA events) */
-    double ms_extend, ms_shade, ms_shadow, ms_raygen, ms_resolve;  /* per-stage sums, CUDA events (only with collect_counters) */
+    double ms_extend, ms_shade, ms_shadow, ms_raygen, ms_resolve;  /* per-stage sums, CUDA events (only with collect_counters bit 0) */
+    uint64_t launches_extend, launches_shade, launches_shadow;     /* launches per stage in the last render */
     uint64_t bvh_nodes, bvh_bytes, tri_bytes;             /* scene footprint in HBM */
     double ms_bvh_build, ms_upload;                       /* rt_scene_create host build / upload */
 } RtStats;

@@ -21,6 +21,7 @@
 #include "../include/rt795.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -430,8 +431,11 @@ float Gett(const Ray& r, V3 p) {
 }
 
 // BVHMethods::FindIntersection, src/Helper.cpp:18-80 (+ TransformRay :110-133, TransformNormal :100-108)
+std::atomic<unsigned long long> g_ray_queries{0};   // every closest-hit query the algorithm issues (bench.py: rays of the reference arm)
 Hit FindIntersection(const Ctx& cx, const Ray& ray) {
     const RtSceneDesc* s = cx.s;
+    thread_local unsigned local = 0;
+    if (++local == 1024) { g_ray_queries.fetch_add(1024, std::memory_order_relaxed); local = 0; }
     Hit nearest;
     float nearestDistance = std::numeric_limits<float>::max();
     if (isnan3(ray.o) || isnan3(ray.d)) return nearest;
@@ -1002,6 +1006,10 @@ int oracle_trace_primary(const RtSceneDesc* s, const RtCameraDesc* cam, int thre
     for (auto& t : pool) t.join();
     return 0;
 }
+
+// Number of closest-hit queries issued since the last reset, to within 1024 per thread (used to express the
+// reference arm's throughput in rays/s: the reference itself cannot count).
+unsigned long long oracle_ray_queries(int reset) { unsigned long long v = g_ray_queries.load(); if (reset) g_ray_queries.store(0); return v; }
 
 // Known-answer hooks for unit tests (closed forms listed in SURVEY.md §4).
 float oracle_perlin(float x, float y, float z, float scale, int nc) { return ComputePerlin(V3(x, y, z), scale, nc); }

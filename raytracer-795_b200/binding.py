@@ -101,6 +101,7 @@ class RtStats(C.Structure):
                 ("launches", C.c_uint64), ("waves", C.c_uint64), ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64),
                 ("ms_total", C.c_double), ("ms_extend", C.c_double), ("ms_shade", C.c_double), ("ms_shadow", C.c_double),
                 ("ms_raygen", C.c_double), ("ms_resolve", C.c_double),
+                ("launches_extend", C.c_uint64), ("launches_shade", C.c_uint64), ("launches_shadow", C.c_uint64),
                 ("bvh_nodes", C.c_uint64), ("bvh_bytes", C.c_uint64), ("tri_bytes", C.c_uint64),
                 ("ms_bvh_build", C.c_double), ("ms_upload", C.c_double)]
 
@@ -169,6 +170,8 @@ def load_oracle() -> C.CDLL:
         P = C.POINTER
         lib.oracle_render.argtypes = [P(RtSceneDesc), P(RtCameraDesc), P(RtRenderOpts), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.oracle_trace_primary.argtypes = [P(RtSceneDesc), P(RtCameraDesc), C.c_int, C.c_void_p]
+        lib.oracle_ray_queries.argtypes = [C.c_int]
+        lib.oracle_ray_queries.restype = C.c_uint64
         lib.oracle_perlin.argtypes = [C.c_float] * 4 + [C.c_int]
         lib.oracle_perlin.restype = C.c_float
         lib.oracle_philox.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]

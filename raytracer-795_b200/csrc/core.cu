@@ -331,18 +331,19 @@ struct Driver {
     DCamera cam;
     DTiling tl;
     RenderConsts rc;
-    bool count;
+    bool count;        // node / primitive-test counters (collect_counters & 2)
+    bool stage_time;   // per-stage CUDA-event timing (collect_counters & 1)
     int nlevels;
     bool branching;
     float* accum;
     DShadowQueue sq;
-    uint64_t launches = 0, secondary = 0, shadow = 0;
+    uint64_t launches = 0, secondary = 0, shadow = 0, n_extend = 0, n_shade = 0, n_shadow = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> unused;
     double ms_extend = 0, ms_shade = 0, ms_shadow = 0;
 
     template <typename F>
     void Timed(double* acc, F&& f) {
-        if (!count) { f(); return; }
+        if (!stage_time) { f(); return; }
         cudaEvent_t a, b;
         CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
         CK(cudaEventRecord(a, st));
@@ -375,7 +376,7 @@ struct Driver {
                 if (rc.integrator == RT_INTEGRATOR_PATH) k_shade<RT_INTEGRATOR_PATH><<<Blocks(m), kBlock, 0, st>>>(sc->d, cam, rc, q, first, m, nq, sq, sc->counters.p, accum);
                 else k_shade<RT_INTEGRATOR_REFERENCE><<<Blocks(m), kBlock, 0, st>>>(sc->d, cam, rc, q, first, m, nq, sq, sc->counters.p, accum);
             });
-            launches += 2;
+            launches += 2; n_extend++; n_shade++;
             CK(cudaMemcpyAsync(sc->h_counters, sc->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             CK(cudaGetLastError());
@@ -386,7 +387,7 @@ struct Driver {
                     if (count) k_shadow<true><<<Blocks(shadow_n), kBlock, 0, st>>>(sc->d, sq, shadow_n, accum, sc->counters.p);
                     else k_shadow<false><<<Blocks(shadow_n), kBlock, 0, st>>>(sc->d, sq, shadow_n, accum, sc->counters.p);
                 });
-                launches++;
+                launches++; n_shadow++;
                 shadow += (uint64_t)shadow_n;
             }
             if (next_n > 0) {
@@ -434,7 +435,8 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
     dr.sc = sc; dr.st = st;
     CameraSetup(cam, &dr.cam);
     dr.tl = MakeTiling(cam, &opts);
-    dr.count = opts.collect_counters != 0;
+    dr.count = (opts.collect_counters & 2) != 0;
+    dr.stage_time = (opts.collect_counters & 1) != 0;
     bool path = opts.integrator == RT_INTEGRATOR_PATH;
     int max_depth = path ? (opts.pt_max_depth > 0 ? opts.pt_max_depth : sc->d.max_depth) : sc->d.max_depth;
     if (max_depth < 0) max_depth = 0;
@@ -483,6 +485,7 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
     RtStats& s = sc->stats;
     s.rays_primary = primary; s.rays_secondary = dr.secondary; s.rays_shadow = dr.shadow; s.launches = dr.launches; s.waves = waves;
     s.ms_total = ms; s.ms_extend = dr.ms_extend; s.ms_shade = dr.ms_shade; s.ms_shadow = dr.ms_shadow; s.ms_raygen = ms_raygen; s.ms_resolve = ms_resolve;
+    s.launches_extend = dr.n_extend; s.launches_shade = dr.n_shade; s.launches_shadow = dr.n_shadow;
     if (dr.count) {
         CK(cudaMemcpy(sc->h_counters, sc->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost));
         s.node_visits = sc->h_counters->node_visits; s.prim_tests = sc->h_counters->prim_tests;

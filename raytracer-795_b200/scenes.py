@@ -235,3 +235,437 @@ def scene_c1(outdir: str, res: int = 800, name: str = "c1") -> str:
     with open(path, "w") as f:
         f.write(xml)
     return path
+
+
+# ------------------------------------------------------------------------------------------ shared XML helpers
+def _material(mid, ka, kd, ks, phong=1, mtype=None, mirror=None, extra="", brdf=None):
+    attr = f' id="{mid}"' + (f' type="{mtype}"' if mtype else "") + (f' BRDF="{brdf}"' if brdf else "")
+    s = f"    <Material{attr}>\n"
+    s += f"      <AmbientReflectance>{_fmt(ka)}</AmbientReflectance>\n"
+    s += f"      <DiffuseReflectance>{_fmt(kd)}</DiffuseReflectance>\n"
+    s += f"      <SpecularReflectance>{_fmt(ks)}</SpecularReflectance>\n"
+    s += f"      <PhongExponent>{int(phong)}</PhongExponent>\n"
+    if mirror is not None:
+        s += f"      <MirrorReflectance>{_fmt(mirror)}</MirrorReflectance>\n"
+    s += extra
+    s += "    </Material>\n"
+    return s
+
+
+def _quad_faces(verts, quad, want):
+    """Two triangles for quad (4 zero-based vertex ids) wound so the reference normal (c-b)x(a-b) points along `want`."""
+    a, b, c, d = quad
+    tris = [(a, b, c), (a, c, d)]
+    out = []
+    for (i, j, k) in tris:
+        A, B, C = (np.array(verts[i]), np.array(verts[j]), np.array(verts[k]))
+        n = np.cross(C - B, A - B)
+        out.append((i, j, k) if float(np.dot(n, want)) > 0 else (i, k, j))
+    return out
+
+
+def _faces_text(tris):
+    return "\n".join("        " + " ".join(str(i + 1) for i in t) for t in tris)
+
+
+def scene_c2(outdir: str, res: int = 1024, spp: int = 100, name: str = "c2", depth: int = 6) -> str:
+    """C2: closed Cornell box (3 meshes, 12 triangles) + dielectric sphere + rough conductor sphere, one area light,
+    distributed ray tracing.  The box is CLOSED (front wall behind the camera) so refracted rays always hit (A.7)."""
+    os.makedirs(outdir, exist_ok=True)
+    X, Y, Z0, Z1 = 10.0, 20.0, -10.0, 30.0
+    verts = [(-X, 0, Z1), (X, 0, Z1), (X, 0, Z0), (-X, 0, Z0),      # floor 0-3
+             (-X, Y, Z1), (X, Y, Z1), (X, Y, Z0), (-X, Y, Z0),      # ceiling 4-7
+             (-4.0, 4.0, 6.0), (4.6, 3.5, 0.5)]                     # sphere centres 8, 9
+    white = (_quad_faces(verts, (0, 1, 2, 3), (0, 1, 0)) + _quad_faces(verts, (4, 5, 6, 7), (0, -1, 0)) +
+             _quad_faces(verts, (3, 2, 6, 7), (0, 0, 1)) + _quad_faces(verts, (0, 1, 5, 4), (0, 0, -1)))
+    red = _quad_faces(verts, (0, 3, 7, 4), (1, 0, 0))
+    green = _quad_faces(verts, (1, 2, 6, 5), (-1, 0, 0))
+    mats = (_material(1, (1, 1, 1), (0.78, 0.78, 0.78), (0, 0, 0)) + _material(2, (1, 1, 1), (0.8, 0.12, 0.1), (0, 0, 0)) +
+            _material(3, (1, 1, 1), (0.12, 0.7, 0.15), (0, 0, 0)) +
+            _material(4, (0, 0, 0), (0, 0, 0), (0, 0, 0), 1, "dielectric", None,
+                      "      <RefractionIndex>1.5</RefractionIndex>\n      <AbsorptionCoefficient>0.01 0.01 0.01</AbsorptionCoefficient>\n") +
+            _material(5, (0, 0, 0), (0.05, 0.05, 0.05), (0.3, 0.3, 0.3), 50, "conductor", (0.9, 0.8, 0.65),
+                      "      <RefractionIndex>0.37</RefractionIndex>\n      <AbsorptionIndex>2.82</AbsorptionIndex>\n      <Roughness>0.15</Roughness>\n"))
+    xml = f"""<Scene>
+  <MaxRecursionDepth>{depth}</MaxRecursionDepth>
+  <BackgroundColor>0 0 0</BackgroundColor>
+  <ShadowRayEpsilon>1e-3</ShadowRayEpsilon>
+  <IntersectionTestEpsilon>1e-6</IntersectionTestEpsilon>
+  <Cameras>
+    <Camera id="1">
+      <Position>0.37 10.3 28.7</Position>
+      <Gaze>-0.013 -0.031 -1</Gaze>
+      <Up>0 1 0</Up>
+      <NearPlane>-1 1 -1 1</NearPlane>
+      <NearDistance>1.9</NearDistance>
+      <ImageResolution>{res} {res}</ImageResolution>
+      <NumSamples>{spp}</NumSamples>
+      <ImageName>{name}.ppm</ImageName>
+    </Camera>
+  </Cameras>
+  <Lights>
+    <AmbientLight>8 8 8</AmbientLight>
+    <AreaLight id="1">
+      <Position>0 18.6 8</Position>
+      <Normal>0 -1 0</Normal>
+      <Size>4</Size>
+      <Radiance>2000 1900 1700</Radiance>
+    </AreaLight>
+  </Lights>
+  <Materials>
+{mats}  </Materials>
+  <VertexData>
+{chr(10).join("    " + _fmt(v) for v in verts)}
+  </VertexData>
+  <Objects>
+    <Sphere id="1"><Material>4</Material><Center>9</Center><Radius>4.0</Radius></Sphere>
+    <Sphere id="2"><Material>5</Material><Center>10</Center><Radius>3.5</Radius></Sphere>
+    <Mesh id="3">
+      <Material>1</Material>
+      <Faces>
+{_faces_text(white)}
+      </Faces>
+    </Mesh>
+    <Mesh id="4">
+      <Material>2</Material>
+      <Faces>
+{_faces_text(red)}
+      </Faces>
+    </Mesh>
+    <Mesh id="5">
+      <Material>3</Material>
+      <Faces>
+{_faces_text(green)}
+      </Faces>
+    </Mesh>
+  </Objects>
+</Scene>
+"""
+    path = os.path.join(outdir, f"{name}.xml")
+    with open(path, "w") as f:
+        f.write(xml)
+    return path
+
+
+def scene_c3(outdir: str, res=(1920, 1080), spp: int = 16, n: int = 187, name: str = "c3") -> str:
+    """C3: bunny-scale (~69k triangle) smooth PLY mesh + floor, point + area light, 16 spp."""
+    os.makedirs(outdir, exist_ok=True)
+    v, f, uv = displaced_sphere(n)
+    write_ply(os.path.join(outdir, f"{name}_mesh.ply"), v, f, uv)
+    verts = [(-9.0, -1.35, 9.0), (9.0, -1.35, 9.0), (9.0, -1.35, -9.0), (-9.0, -1.35, -9.0)]
+    floor = _quad_faces(verts, (0, 1, 2, 3), (0, 1, 0))
+    mats = (_material(1, (1, 1, 1), (0.75, 0.55, 0.3), (0.5, 0.5, 0.5), 60) + _material(2, (1, 1, 1), (0.6, 0.6, 0.65), (0.05, 0.05, 0.05), 4))
+    xml = f"""<Scene>
+  <MaxRecursionDepth>2</MaxRecursionDepth>
+  <BackgroundColor>20 24 36</BackgroundColor>
+  <ShadowRayEpsilon>1e-3</ShadowRayEpsilon>
+  <IntersectionTestEpsilon>1e-6</IntersectionTestEpsilon>
+  <Cameras>
+    <Camera id="1">
+      <Position>0.31 1.17 4.6</Position>
+      <GazePoint>0.02 -0.11 0.01</GazePoint>
+      <Up>0 1 0</Up>
+      <FovY>38</FovY>
+      <NearDistance>1</NearDistance>
+      <ImageResolution>{res[0]} {res[1]}</ImageResolution>
+      <NumSamples>{spp}</NumSamples>
+      <ImageName>{name}.ppm</ImageName>
+    </Camera>
+  </Cameras>
+  <Lights>
+    <AmbientLight>18 18 18</AmbientLight>
+    <PointLight id="1">
+      <Position>4 6 5</Position>
+      <Intensity>9000 8600 8000</Intensity>
+    </PointLight>
+    <AreaLight id="1">
+      <Position>-4 5 2</Position>
+      <Normal>0.6 -0.75 -0.28</Normal>
+      <Size>2</Size>
+      <Radiance>900 950 1100</Radiance>
+    </AreaLight>
+  </Lights>
+  <Materials>
+{mats}  </Materials>
+  <VertexData>
+{chr(10).join("    " + _fmt(p) for p in verts)}
+  </VertexData>
+  <Objects>
+    <Mesh id="1">
+      <Material>2</Material>
+      <Faces>
+{_faces_text(floor)}
+      </Faces>
+    </Mesh>
+    <Mesh id="2" shadingMode="smooth">
+      <Material>1</Material>
+      <Faces plyFile="{name}_mesh.ply" />
+    </Mesh>
+  </Objects>
+</Scene>
+"""
+    path = os.path.join(outdir, f"{name}.xml")
+    with open(path, "w") as fh:
+        fh.write(xml)
+    return path
+
+
+def checker_exr(path: str, w: int = 256, h: int = 256, seed: int = 795) -> None:
+    """Generated image texture (float RGBA EXR): soft coloured checker + seeded noise, values in 0..255."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    chk = ((xx // 16 + yy // 16) % 2).astype(np.float32)
+    img = np.empty((h, w, 4), dtype=np.float32)
+    img[..., 0] = 60 + 160 * chk + 20 * np.sin(xx * 0.11)
+    img[..., 1] = 70 + 120 * (1 - chk) + 25 * np.cos(yy * 0.07)
+    img[..., 2] = 90 + 60 * chk + rng.uniform(0, 30, size=(h, w))
+    img[..., 3] = 1.0
+    write_exr(path, img)
+
+
+def scene_c4(outdir: str, res=(1920, 1080), spp: int = 64, n: int = 660, name: str = "c4", grid: int = 4) -> str:
+    """C4: dragon-scale (~870k triangle) smooth mesh, 1 base + grid*grid-1 instances (TLAS/BLAS), transformations,
+    motion blur on every 5th entry, Perlin bump on the mesh, Perlin kd + image texture on the ground."""
+    os.makedirs(outdir, exist_ok=True)
+    v, f, uv = displaced_sphere(n, third_harmonic=True)
+    write_ply(os.path.join(outdir, f"{name}_mesh.ply"), v, f, uv)
+    checker_exr(os.path.join(outdir, f"{name}_floor.exr"))
+    S = 3.2 * grid
+    verts = [(-S, -1.4, S), (S, -1.4, S), (S, -1.4, -S), (-S, -1.4, -S),        # ground 0-3
+             (-S, -1.4, -S), (S, -1.4, -S), (S, 9.0, -S), (-S, 9.0, -S)]        # back wall 4-7
+    uvs = [(0, 0), (4, 0), (4, 4), (0, 4), (0, 0), (1, 0), (1, 1), (0, 1)]
+    ground = _quad_faces(verts, (0, 1, 2, 3), (0, 1, 0))
+    wall = _quad_faces(verts, (4, 5, 6, 7), (0, 0, 1))
+    mats = (_material(1, (1, 1, 1), (0.7, 0.45, 0.25), (0.6, 0.6, 0.6), 80) + _material(2, (1, 1, 1), (0.5, 0.5, 0.5), (0.05, 0.05, 0.05), 4) +
+            _material(3, (1, 1, 1), (0.25, 0.4, 0.75), (0.7, 0.7, 0.7), 120) + _material(4, (1, 1, 1), (0.3, 0.7, 0.35), (0.4, 0.4, 0.4), 30) +
+            _material(5, (1, 1, 1), (0.8, 0.8, 0.8), (0, 0, 0), 1))
+    trans, objs = [], []
+    tid = 0
+    sid = [0]
+    scal, rots = [], []
+    inst_xml = []
+    for k in range(grid * grid):
+        gx, gz = k % grid, k // grid
+        px, pz = (gx - (grid - 1) / 2) * 3.1, (gz - (grid - 1) / 2) * 3.1
+        tid += 1
+        trans.append(f'    <Translation id="{tid}">{_fmt((px, 0.0, pz))}</Translation>')
+        tl = f"t{tid}"
+        if k % 3 == 1:
+            scal.append(f'    <Scaling id="{len(scal) + 1}">{_fmt((0.8 + 0.05 * (k % 4), 1.0 + 0.04 * (k % 5), 0.85))}</Scaling>')
+            tl = f"s{len(scal)} " + tl
+        if k % 4 == 2:
+            rots.append(f'    <Rotation id="{len(rots) + 1}">{_fmt((17.0 * k, 0.2, 1.0, 0.1))}</Rotation>')
+            tl = f"r{len(rots)} " + tl
+        blur = f"<MotionBlur>{_fmt((0.0, 0.25, 0.12))}</MotionBlur>" if k % 5 == 4 else ""
+        mat = 1 + (k % 2) * 2 if k % 7 else 4
+        if k == 0:
+            base = (f'    <Mesh id="1" shadingMode="smooth">\n      <Material>{mat}</Material>\n      <Textures>1</Textures>\n'
+                    f'      <Transformations>{tl}</Transformations>\n      <Faces plyFile="{name}_mesh.ply" />\n    </Mesh>')
+        else:
+            inst_xml.append(f'    <MeshInstance id="{100 + k}" baseMeshId="1" resetTransform="true">\n      <Material>{mat}</Material>\n'
+                            f'      <Transformations>{tl}</Transformations>\n      {blur}\n    </MeshInstance>')
+    xml = f"""<Scene>
+  <MaxRecursionDepth>2</MaxRecursionDepth>
+  <BackgroundColor>14 18 28</BackgroundColor>
+  <ShadowRayEpsilon>1e-3</ShadowRayEpsilon>
+  <IntersectionTestEpsilon>1e-6</IntersectionTestEpsilon>
+  <Cameras>
+    <Camera id="1">
+      <Position>0.7 7.3 13.9</Position>
+      <GazePoint>0.05 -0.4 0.1</GazePoint>
+      <Up>0 1 0</Up>
+      <FovY>42</FovY>
+      <NearDistance>1</NearDistance>
+      <ImageResolution>{res[0]} {res[1]}</ImageResolution>
+      <NumSamples>{spp}</NumSamples>
+      <ImageName>{name}.ppm</ImageName>
+    </Camera>
+  </Cameras>
+  <Lights>
+    <AmbientLight>16 16 16</AmbientLight>
+    <PointLight id="1">
+      <Position>6 14 9</Position>
+      <Intensity>52000 50000 47000</Intensity>
+    </PointLight>
+    <AreaLight id="1">
+      <Position>-7 12 3</Position>
+      <Normal>0.5 -0.8 -0.2</Normal>
+      <Size>3</Size>
+      <Radiance>2600 2700 3000</Radiance>
+    </AreaLight>
+  </Lights>
+  <Materials>
+{mats}  </Materials>
+  <Textures>
+    <Images>
+      <Image id="1">{name}_floor.exr</Image>
+    </Images>
+    <TextureMap id="1" type="perlin">
+      <DecalMode>bump_normal</DecalMode>
+      <NoiseConversion>absval</NoiseConversion>
+      <NoiseScale>6</NoiseScale>
+      <BumpFactor>0.3</BumpFactor>
+    </TextureMap>
+    <TextureMap id="2" type="image">
+      <ImageId>1</ImageId>
+      <DecalMode>blend_kd</DecalMode>
+      <Interpolation>bilinear</Interpolation>
+      <Normalizer>255</Normalizer>
+    </TextureMap>
+    <TextureMap id="3" type="perlin">
+      <DecalMode>replace_kd</DecalMode>
+      <NoiseConversion>linear</NoiseConversion>
+      <NoiseScale>0.9</NoiseScale>
+    </TextureMap>
+  </Textures>
+  <Transformations>
+{chr(10).join(trans)}
+{chr(10).join(scal)}
+{chr(10).join(rots)}
+  </Transformations>
+  <VertexData>
+{chr(10).join("    " + _fmt(p) for p in verts)}
+  </VertexData>
+  <TexCoordData>
+{chr(10).join("    " + _fmt(p) for p in uvs)}
+  </TexCoordData>
+  <Objects>
+    <Mesh id="50">
+      <Material>2</Material>
+      <Textures>2</Textures>
+      <Faces>
+{_faces_text(ground)}
+      </Faces>
+    </Mesh>
+    <Mesh id="51">
+      <Material>5</Material>
+      <Textures>3</Textures>
+      <Faces>
+{_faces_text(wall)}
+      </Faces>
+    </Mesh>
+{base}
+{chr(10).join(inst_xml)}
+  </Objects>
+</Scene>
+"""
+    path = os.path.join(outdir, f"{name}.xml")
+    with open(path, "w") as fh:
+        fh.write(xml)
+    return path
+
+
+def sky_exr(path: str, w: int = 1024, h: int = 512) -> None:
+    """Procedural lat-long HDR environment: sky gradient + ground + sun disc (float RGBA EXR)."""
+    v = (np.arange(h) + 0.5) / h
+    u = (np.arange(w) + 0.5) / w
+    theta = v[:, None] * math.pi                  # 0 = +y
+    phi = math.pi - u[None, :] * 2 * math.pi      # inverse of u = (pi - phi) / 2pi
+    dy = np.cos(theta) * np.ones_like(phi)
+    dx = np.sin(theta) * np.cos(phi)
+    dz = np.sin(theta) * np.sin(phi)
+    up = np.clip(dy, 0, 1)
+    img = np.empty((h, w, 4), dtype=np.float32)
+    sky = np.stack([40 + 60 * (1 - up), 70 + 70 * (1 - up), 140 + 60 * up], axis=-1)
+    ground = np.array([38.0, 34.0, 30.0])
+    img[..., :3] = np.where((dy > 0)[..., None], sky, ground)
+    sun = np.array([0.45, 0.62, 0.64]); sun = sun / np.linalg.norm(sun)
+    cosang = dx * sun[0] + dy * sun[1] + dz * sun[2]
+    disc = np.clip((cosang - 0.995) / 0.005, 0, 1) ** 2
+    img[..., :3] += disc[..., None] * np.array([24000.0, 22000.0, 18000.0])
+    img[..., 3] = 1.0
+    write_exr(path, img)
+
+
+def scene_c5(outdir: str, res=(3840, 2160), spp: int = 1024, name: str = "c5", depth: int = 8) -> str:
+    """C5: Cornell box (open front) with BRDF materials, HDR environment light + emissive quad (object light, with a
+    co-located AreaLight for NEE / for the reference's direct lighting), meant for the path tracer + tone map."""
+    os.makedirs(outdir, exist_ok=True)
+    sky_exr(os.path.join(outdir, f"{name}_sky.exr"))
+    X, Y, Z0, Z1 = 10.0, 20.0, -10.0, 10.0
+    verts = [(-X, 0, Z1), (X, 0, Z1), (X, 0, Z0), (-X, 0, Z0), (-X, Y, Z1), (X, Y, Z1), (X, Y, Z0), (-X, Y, Z0),
+             (-2.5, 19.95, 2.5), (2.5, 19.95, 2.5), (2.5, 19.95, -2.5), (-2.5, 19.95, -2.5),   # emissive quad 8-11
+             (-4.5, 4.0, 1.0), (4.5, 3.0, 3.5)]                                                  # spheres 12, 13
+    white = (_quad_faces(verts, (0, 1, 2, 3), (0, 1, 0)) + _quad_faces(verts, (4, 5, 6, 7), (0, -1, 0)) + _quad_faces(verts, (3, 2, 6, 7), (0, 0, 1)))
+    red = _quad_faces(verts, (0, 3, 7, 4), (1, 0, 0))
+    green = _quad_faces(verts, (1, 2, 6, 5), (-1, 0, 0))
+    lamp = _quad_faces(verts, (8, 9, 10, 11), (0, -1, 0))
+    mats = (_material(1, (0, 0, 0), (0.75, 0.75, 0.75), (0.15, 0.15, 0.15), 1, brdf=1) + _material(2, (0, 0, 0), (0.75, 0.1, 0.08), (0.1, 0.1, 0.1), 1, brdf=1) +
+            _material(3, (0, 0, 0), (0.1, 0.65, 0.12), (0.1, 0.1, 0.1), 1, brdf=1) +
+            _material(4, (0, 0, 0), (0.35, 0.3, 0.2), (0.6, 0.55, 0.45), 1, brdf=2, extra="      <RefractionIndex>1.8</RefractionIndex>\n      <AbsorptionIndex>2.2</AbsorptionIndex>\n") +
+            _material(5, (0, 0, 0), (0, 0, 0), (0, 0, 0), 1, "mirror", (0.92, 0.92, 0.92)) +
+            _material(6, (0, 0, 0), (0, 0, 0), (0, 0, 0), 1, extra="      <Emission>1800 1700 1500</Emission>\n"))
+    xml = f"""<Scene>
+  <MaxRecursionDepth>{depth}</MaxRecursionDepth>
+  <BackgroundColor>0 0 0</BackgroundColor>
+  <ShadowRayEpsilon>1e-3</ShadowRayEpsilon>
+  <IntersectionTestEpsilon>1e-6</IntersectionTestEpsilon>
+  <Cameras>
+    <Camera id="1">
+      <Position>0.4 10.2 41.5</Position>
+      <Gaze>-0.011 -0.017 -1</Gaze>
+      <Up>0 1 0</Up>
+      <FovY>36</FovY>
+      <NearDistance>1</NearDistance>
+      <ImageResolution>{res[0]} {res[1]}</ImageResolution>
+      <NumSamples>{spp}</NumSamples>
+      <ImageName>{name}.exr</ImageName>
+    </Camera>
+  </Cameras>
+  <BRDFs>
+    <ModifiedBlinnPhong id="1" normalized="true"><Exponent>40</Exponent></ModifiedBlinnPhong>
+    <TorranceSparrow id="2" kdfresnel="true"><Exponent>60</Exponent></TorranceSparrow>
+  </BRDFs>
+  <Lights>
+    <AmbientLight>0 0 0</AmbientLight>
+    <AreaLight id="1">
+      <Position>0 19.9 0</Position>
+      <Normal>0 -1 0</Normal>
+      <Size>5</Size>
+      <Radiance>1800 1700 1500</Radiance>
+    </AreaLight>
+    <SphericalDirectionalLight id="2">
+      <ImageId>1</ImageId>
+    </SphericalDirectionalLight>
+  </Lights>
+  <Materials>
+{mats}  </Materials>
+  <Textures>
+    <Images>
+      <Image id="1">{name}_sky.exr</Image>
+    </Images>
+  </Textures>
+  <VertexData>
+{chr(10).join("    " + _fmt(p) for p in verts)}
+  </VertexData>
+  <Objects>
+    <Sphere id="1"><Material>4</Material><Center>13</Center><Radius>4.0</Radius></Sphere>
+    <Sphere id="2"><Material>5</Material><Center>14</Center><Radius>3.0</Radius></Sphere>
+    <Mesh id="3"><Material>1</Material><Faces>
+{_faces_text(white)}
+    </Faces></Mesh>
+    <Mesh id="4"><Material>2</Material><Faces>
+{_faces_text(red)}
+    </Faces></Mesh>
+    <Mesh id="5"><Material>3</Material><Faces>
+{_faces_text(green)}
+    </Faces></Mesh>
+    <Mesh id="6"><Material>6</Material><Faces>
+{_faces_text(lamp)}
+    </Faces></Mesh>
+  </Objects>
+</Scene>
+"""
+    path = os.path.join(outdir, f"{name}.xml")
+    with open(path, "w") as fh:
+        fh.write(xml)
+    return path
+
+
+CONFIGS = {
+    "c1": dict(gen=scene_c1, label="C1 Whitted: 5 spheres + 4 triangles, 1 point light, 800x800, 1 spp, depth 6"),
+    "c2": dict(gen=scene_c2, label="C2 Cornell box, dielectric + conductor spheres, area light, glossy, 1024x1024, 100 spp"),
+    "c3": dict(gen=scene_c3, label="C3 ~69k-triangle smooth PLY mesh, point + area light, 1920x1080, 16 spp"),
+    "c4": dict(gen=scene_c4, label="C4 ~870k-triangle mesh x16 (TLAS/BLAS), transforms + motion blur, Perlin bump/kd + image texture, 1920x1080, 64 spp"),
+    "c5": dict(gen=scene_c5, label="C5 path-traced Cornell box, BRDF materials, NEE + RR, HDR env light + tone map, 3840x2160, 1024 spp"),
+}

@@ -73,3 +73,151 @@ def test_c1_radiance_vs_reference_binary(c1, have_ref, tmp_path):
     r = rel_err(img, ref).max(axis=-1)
     assert r.mean() <= 1e-3, r.mean()
     assert np.quantile(r, 0.995) <= 1e-2, np.quantile(r, 0.995)
+
+
+# ------------------------------------------------------------------------------------------------ C2..C5 (reduced sizes)
+def _load(rt, xml):
+    hs = rt.HostScene(xml)
+    return hs, rt.Scene(hs.desc, 0)
+
+
+def _block_means(img, b=8):
+    h, w, _ = img.shape
+    return img[: h // b * b, : w // b * b].reshape(h // b, b, w // b, b, 3).mean(axis=(1, 3))
+
+
+def _check_vs_oracle(rt, hs, sc, opts=None, mean_tol=2e-3, q=0.98, q_tol=1e-2):
+    """Same scene, same Philox streams: GPU and oracle take the same samples, so pixels agree to float rounding except
+    where a sample straddles a geometric / shadow discontinuity."""
+    cam = hs.camera(0)
+    img = sc.render(cam, opts)
+    ref = rt.oracle_render(hs.desc, cam, opts)
+    assert np.isfinite(img).all()
+    r = rel_err(img, ref).max(axis=-1)
+    assert np.quantile(r, q) <= q_tol, (np.quantile(r, q), r.mean())
+    assert abs(img.mean() - ref.mean()) <= mean_tol * ref.mean(), (img.mean(), ref.mean())
+    bm = rel_err(_block_means(img), _block_means(ref))
+    assert np.median(bm) <= 1e-3, np.median(bm)
+    return img, ref
+
+
+def _check_vs_reference_statistical(rt, xml, hs, img, tmp_path, k=2.0):
+    """Unmodified reference binary, its own (irreproducible) mt19937 streams: compare 8x8 block means against the
+    reference's own run-to-run noise (two reference runs), SURVEY §7.3 #4."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_raytracer")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref not built")
+    refs = []
+    for i in range(2):
+        d = os.path.join(tmp_path, f"run{i}")
+        os.makedirs(d)
+        subprocess.run([exe, xml], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        refs.append(rt.read_f32(os.path.join(d, hs.image_name(0) + ".f32")))
+    a, b, g = _block_means(refs[0]), _block_means(refs[1]), _block_means(img)
+    noise = np.sqrt(np.mean((a - b) ** 2))
+    err = np.sqrt(np.mean((g - 0.5 * (a + b)) ** 2))
+    # RMSE(g - mean(a,b)) for an unbiased g is sqrt(1.5/2) * RMSE(a - b); allow k x
+    assert err <= k * noise + 1e-3 * np.abs(a).mean(), (err, noise)
+    assert abs(g.mean() - 0.5 * (a.mean() + b.mean())) <= 0.01 * a.mean() + 3 * abs(a.mean() - b.mean()), (g.mean(), a.mean(), b.mean())
+
+
+def test_c2_distributed_vs_oracle_and_reference(rt, scene_dir, tmp_path):
+    """C2 (reduced): dielectric + rough conductor + area light, depth 6: the weighted-ray tree with Beer/Fresnel."""
+    xml = rt.scenes.scene_c2(os.path.join(scene_dir, "c2"), res=160, spp=16)
+    hs, sc = _load(rt, xml)
+    img, _ = _check_vs_oracle(rt, hs, sc)
+    st = sc.stats()
+    assert st.rays_secondary > 0          # reflection / refraction rays were spawned
+    _check_vs_reference_statistical(rt, xml, hs, img, str(tmp_path))
+    sc.close(); hs.close()
+
+
+def test_c3_mesh_vs_oracle_and_reference(rt, scene_dir, tmp_path):
+    """C3 (reduced mesh): smooth PLY mesh in a BLAS, point + area light, multisampling."""
+    xml = rt.scenes.scene_c3(os.path.join(scene_dir, "c3"), res=(320, 180), spp=4, n=64)
+    hs, sc = _load(rt, xml)
+    cam = hs.camera(0)
+    same = hit_agreement(sc.trace_primary(cam), rt.oracle_trace_primary(hs.desc, cam))
+    assert same.mean() >= 0.999, same.mean()
+    img, _ = _check_vs_oracle(rt, hs, sc)
+    _check_vs_reference_statistical(rt, xml, hs, img, str(tmp_path))
+    sc.close(); hs.close()
+
+
+def test_c4_instances_vs_oracle_and_reference(rt, scene_dir, tmp_path):
+    """C4 (reduced mesh): 1 base mesh + 15 instances (scale / rotation / translation), motion blur, Perlin bump,
+    Perlin kd, image texture (EXR, bilinear, blend_kd)."""
+    xml = rt.scenes.scene_c4(os.path.join(scene_dir, "c4"), res=(320, 180), spp=4, n=48)
+    hs, sc = _load(rt, xml)
+    cam = hs.camera(0)
+    g, o = sc.trace_primary(cam), rt.oracle_trace_primary(hs.desc, cam)
+    same = hit_agreement(g, o)
+    assert same.mean() >= 0.999, same.mean()
+    both = same & (g["full"] == 1)
+    assert np.quantile(np.abs(g["normal"][both] - o["normal"][both]).max(axis=-1), 0.995) <= 2e-3   # bump-mapped normals
+    img, _ = _check_vs_oracle(rt, hs, sc)
+    _check_vs_reference_statistical(rt, xml, hs, img, str(tmp_path))
+    sc.close(); hs.close()
+
+
+def test_c5_path_tracer_vs_oracle(rt, scene_dir):
+    """C5 (reduced): path tracer (NEE + Russian roulette + cosine sampling) against its CPU restatement with the same
+    Philox streams.  No reference code exists for this integrator: parity unpinned by the reference."""
+    xml = rt.scenes.scene_c5(os.path.join(scene_dir, "c5"), res=(160, 90), spp=16)
+    hs, sc = _load(rt, xml)
+    opts = rt.default_opts(integrator=rt.RT_INTEGRATOR_PATH)
+    _check_vs_oracle(rt, hs, sc, opts, mean_tol=5e-3, q=0.95, q_tol=2e-2)
+    # NEE on vs off converge to the same image (internal consistency; NEE-off has far more variance)
+    cam = hs.camera(0)
+    a = sc.render(cam, rt.default_opts(integrator=rt.RT_INTEGRATOR_PATH, pt_nee=1, seed=1))
+    b = sc.render(cam, rt.default_opts(integrator=rt.RT_INTEGRATOR_PATH, pt_nee=0, seed=2))
+    assert abs(a.mean() - b.mean()) <= 0.15 * a.mean(), (a.mean(), b.mean())
+    sc.close(); hs.close()
+
+
+def test_tile_partition_is_exact(rt, scene_dir):
+    """Multi-GPU image partition: the sum of the per-rank tile renders equals the single-GPU frame
+    bit for bit when every pixel is touched by one rank only (counter-based RNG keyed by pixel, not by rank)."""
+    xml = rt.scenes.scene_c3(os.path.join(scene_dir, "c3t"), res=(200, 120), spp=4, n=32)
+    hs, sc = _load(rt, xml)
+    cam = hs.camera(0)
+    full = sc.render(cam)
+    for world in (2, 4):
+        acc = np.zeros_like(full)
+        cover = np.zeros(full.shape[:2], dtype=np.int32)
+        for r in range(world):
+            part = sc.render(cam, rt.default_opts(tile_rank=r, tile_count=world))
+            cover += (np.abs(part).sum(axis=-1) > 0)
+            acc += part
+        assert cover.max() <= 1
+        assert np.allclose(acc, full, rtol=1e-5, atol=1e-5)
+    sc.close(); hs.close()
+
+
+def test_tonemap_runs_and_is_monotone(rt, scene_dir):
+    xml = rt.scenes.scene_c1(os.path.join(scene_dir, "c1tm"), res=128)
+    hs, sc = _load(rt, xml)
+    img = sc.render(hs.camera(0))
+    ldr = sc.tonemap(img, key=0.18, burn=1.0, saturation=1.0, gamma=2.2)
+    assert ldr.dtype == np.uint8 and ldr.shape == img.shape and ldr.max() > 100
+    lum = img @ np.array([0.2126, 0.7152, 0.0722], dtype=np.float32)
+    l8 = ldr.astype(np.float32) @ np.array([0.2126, 0.7152, 0.0722], dtype=np.float32)
+    idx = np.argsort(lum.ravel())
+    # brighter in -> not darker out (up to quantisation)
+    assert (np.diff(l8.ravel()[idx][::97]) >= -3).mean() > 0.99
+    sc.close(); hs.close()
+
+
+def test_errors_are_reported_not_fatal(rt):
+    with pytest.raises(rt.RtError) as e:
+        rt.HostScene("/nonexistent/dir/scene.xml")
+    assert e.value.code == rt.RT_ERR_IO
+    d = rt.RtSceneDesc()
+    with pytest.raises(rt.RtError) as e2:
+        rt.Scene(ctypes_byref(d), 0)
+    assert e2.value.code == rt.RT_ERR_INVALID
+
+
+def ctypes_byref(x):
+    import ctypes
+    return ctypes.byref(x)
