@@ -126,7 +126,12 @@ public:
     Loader(const char* path, RtHostScene* hs) : path_(path), hs_(hs) {}
     bool Run(std::string* err) {
         XmlDoc doc;
-        if (!doc.LoadFile(path_.c_str(), err)) { io_error_ = true; return false; }
+        {
+            FILE* probe = fopen(path_.c_str(), "rb");
+            if (!probe) { io_error_ = true; *err = "cannot open " + path_; return false; }
+            fclose(probe);
+        }
+        if (!doc.LoadFile(path_.c_str(), err)) return false;
         root_ = doc.root();
         // directory prefix exactly as src/Parser.h:488-498: everything up to and including the last '/',
         // and, when there is no '/', the FIRST CHARACTER of the path (lastIndex defaults to 0) - SURVEY A.11.

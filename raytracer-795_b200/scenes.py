@@ -347,7 +347,7 @@ def scene_c2(outdir: str, res: int = 1024, spp: int = 100, name: str = "c2", dep
     return path
 
 
-def scene_c3(outdir: str, res=(1920, 1080), spp: int = 16, n: int = 187, name: str = "c3") -> str:
+def scene_c3(outdir: str, res=(1920, 1080), spp: int = 16, n: int = 187, name: str = "c3", deterministic: bool = False) -> str:
     """C3: bunny-scale (~69k triangle) smooth PLY mesh + floor, point + area light, 16 spp."""
     os.makedirs(outdir, exist_ok=True)
     v, f, uv = displaced_sphere(n)
@@ -355,6 +355,13 @@ def scene_c3(outdir: str, res=(1920, 1080), spp: int = 16, n: int = 187, name: s
     verts = [(-9.0, -1.35, 9.0), (9.0, -1.35, 9.0), (9.0, -1.35, -9.0), (-9.0, -1.35, -9.0)]
     floor = _quad_faces(verts, (0, 1, 2, 3), (0, 1, 0))
     mats = (_material(1, (1, 1, 1), (0.75, 0.55, 0.3), (0.5, 0.5, 0.5), 60) + _material(2, (1, 1, 1), (0.6, 0.6, 0.65), (0.05, 0.05, 0.05), 4))
+    area = "" if deterministic else """    <AreaLight id="1">
+      <Position>-4 5 2</Position>
+      <Normal>0.6 -0.75 -0.28</Normal>
+      <Size>2</Size>
+      <Radiance>900 950 1100</Radiance>
+    </AreaLight>
+"""
     xml = f"""<Scene>
   <MaxRecursionDepth>2</MaxRecursionDepth>
   <BackgroundColor>20 24 36</BackgroundColor>
@@ -378,13 +385,7 @@ def scene_c3(outdir: str, res=(1920, 1080), spp: int = 16, n: int = 187, name: s
       <Position>4 6 5</Position>
       <Intensity>9000 8600 8000</Intensity>
     </PointLight>
-    <AreaLight id="1">
-      <Position>-4 5 2</Position>
-      <Normal>0.6 -0.75 -0.28</Normal>
-      <Size>2</Size>
-      <Radiance>900 950 1100</Radiance>
-    </AreaLight>
-  </Lights>
+{area}  </Lights>
   <Materials>
 {mats}  </Materials>
   <VertexData>
@@ -423,7 +424,7 @@ def checker_exr(path: str, w: int = 256, h: int = 256, seed: int = 795) -> None:
     write_exr(path, img)
 
 
-def scene_c4(outdir: str, res=(1920, 1080), spp: int = 64, n: int = 660, name: str = "c4", grid: int = 4) -> str:
+def scene_c4(outdir: str, res=(1920, 1080), spp: int = 64, n: int = 660, name: str = "c4", grid: int = 4, deterministic: bool = False) -> str:
     """C4: dragon-scale (~870k triangle) smooth mesh, 1 base + grid*grid-1 instances (TLAS/BLAS), transformations,
     motion blur on every 5th entry, Perlin bump on the mesh, Perlin kd + image texture on the ground."""
     os.makedirs(outdir, exist_ok=True)
@@ -439,6 +440,13 @@ def scene_c4(outdir: str, res=(1920, 1080), spp: int = 64, n: int = 660, name: s
     mats = (_material(1, (1, 1, 1), (0.7, 0.45, 0.25), (0.6, 0.6, 0.6), 80) + _material(2, (1, 1, 1), (0.5, 0.5, 0.5), (0.05, 0.05, 0.05), 4) +
             _material(3, (1, 1, 1), (0.25, 0.4, 0.75), (0.7, 0.7, 0.7), 120) + _material(4, (1, 1, 1), (0.3, 0.7, 0.35), (0.4, 0.4, 0.4), 30) +
             _material(5, (1, 1, 1), (0.8, 0.8, 0.8), (0, 0, 0), 1))
+    area = "" if deterministic else """    <AreaLight id="1">
+      <Position>-7 12 3</Position>
+      <Normal>0.5 -0.8 -0.2</Normal>
+      <Size>3</Size>
+      <Radiance>2600 2700 3000</Radiance>
+    </AreaLight>
+"""
     trans, objs = [], []
     tid = 0
     sid = [0]
@@ -487,13 +495,7 @@ def scene_c4(outdir: str, res=(1920, 1080), spp: int = 64, n: int = 660, name: s
       <Position>6 14 9</Position>
       <Intensity>52000 50000 47000</Intensity>
     </PointLight>
-    <AreaLight id="1">
-      <Position>-7 12 3</Position>
-      <Normal>0.5 -0.8 -0.2</Normal>
-      <Size>3</Size>
-      <Radiance>2600 2700 3000</Radiance>
-    </AreaLight>
-  </Lights>
+{area}  </Lights>
   <Materials>
 {mats}  </Materials>
   <Textures>
@@ -555,7 +557,7 @@ def scene_c4(outdir: str, res=(1920, 1080), spp: int = 64, n: int = 660, name: s
     return path
 
 
-def sky_exr(path: str, w: int = 1024, h: int = 512) -> None:
+def sky_exr(path: str, w: int = 1024, h: int = 512, sun_scale: float = 1.0) -> None:
     """Procedural lat-long HDR environment: sky gradient + ground + sun disc (float RGBA EXR)."""
     v = (np.arange(h) + 0.5) / h
     u = (np.arange(w) + 0.5) / w
@@ -572,16 +574,16 @@ def sky_exr(path: str, w: int = 1024, h: int = 512) -> None:
     sun = np.array([0.45, 0.62, 0.64]); sun = sun / np.linalg.norm(sun)
     cosang = dx * sun[0] + dy * sun[1] + dz * sun[2]
     disc = np.clip((cosang - 0.995) / 0.005, 0, 1) ** 2
-    img[..., :3] += disc[..., None] * np.array([24000.0, 22000.0, 18000.0])
+    img[..., :3] += disc[..., None] * np.array([24000.0, 22000.0, 18000.0]) * sun_scale
     img[..., 3] = 1.0
     write_exr(path, img)
 
 
-def scene_c5(outdir: str, res=(3840, 2160), spp: int = 1024, name: str = "c5", depth: int = 8) -> str:
+def scene_c5(outdir: str, res=(3840, 2160), spp: int = 1024, name: str = "c5", depth: int = 8, sun_scale: float = 1.0) -> str:
     """C5: Cornell box (open front) with BRDF materials, HDR environment light + emissive quad (object light, with a
     co-located AreaLight for NEE / for the reference's direct lighting), meant for the path tracer + tone map."""
     os.makedirs(outdir, exist_ok=True)
-    sky_exr(os.path.join(outdir, f"{name}_sky.exr"))
+    sky_exr(os.path.join(outdir, f"{name}_sky.exr"), sun_scale=sun_scale)
     X, Y, Z0, Z1 = 10.0, 20.0, -10.0, 10.0
     verts = [(-X, 0, Z1), (X, 0, Z1), (X, 0, Z0), (-X, 0, Z0), (-X, Y, Z1), (X, Y, Z1), (X, Y, Z0), (-X, Y, Z0),
              (-2.5, 19.95, 2.5), (2.5, 19.95, 2.5), (2.5, 19.95, -2.5), (-2.5, 19.95, -2.5),   # emissive quad 8-11

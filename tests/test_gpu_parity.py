@@ -113,12 +113,8 @@ def _check_vs_reference_statistical(rt, xml, hs, img, tmp_path, k=2.0):
         os.makedirs(d)
         subprocess.run([exe, xml], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         refs.append(rt.read_f32(os.path.join(d, hs.image_name(0) + ".f32")))
-    a, b, g = _block_means(refs[0]), _block_means(refs[1]), _block_means(img)
-    noise = np.sqrt(np.mean((a - b) ** 2))
-    err = np.sqrt(np.mean((g - 0.5 * (a + b)) ** 2))
-    # RMSE(g - mean(a,b)) for an unbiased g is sqrt(1.5/2) * RMSE(a - b); allow k x
-    assert err <= k * noise + 1e-3 * np.abs(a).mean(), (err, noise)
-    assert abs(g.mean() - 0.5 * (a.mean() + b.mean())) <= 0.01 * a.mean() + 3 * abs(a.mean() - b.mean()), (g.mean(), a.mean(), b.mean())
+    from conftest import assert_statistically_equal
+    assert_statistically_equal(refs[0], refs[1], img)
 
 
 def test_c2_distributed_vs_oracle_and_reference(rt, scene_dir, tmp_path):

@@ -1,0 +1,239 @@
+"""Host shell (XML / PLY / image I/O / scene preparation) against the behaviour of src/Parser.h, src/Helper.cpp:135-226
+and src/Scene.cpp:303-318, including the parser quirks catalogued in SURVEY.md Appendix A.  CPU only."""
+import math
+import os
+import struct
+
+import numpy as np
+import pytest
+
+BASE = """<Scene>
+  <MaxRecursionDepth>3</MaxRecursionDepth>
+  <Cameras><Camera id="1"{camattr}><Position>0 0 0</Position>{gaze}<Up>0 1 0</Up>{plane}
+    <NearDistance>2</NearDistance><ImageResolution>8 4</ImageResolution><ImageName>x.png</ImageName>{camextra}</Camera></Cameras>
+  <Lights>{lights}</Lights>
+  <Materials>{materials}</Materials>
+  {textures}
+  {transformations}
+  <VertexData>{verts}</VertexData>
+  {texcoords}
+  <Objects>{objects}</Objects>
+</Scene>"""
+
+MAT = '<Material id="1"><AmbientReflectance>1 1 1</AmbientReflectance><DiffuseReflectance>.5 .5 .5</DiffuseReflectance><SpecularReflectance>0 0 0</SpecularReflectance></Material>'
+
+
+def write_scene(tmp, **kw):
+    d = dict(camattr="", gaze="<Gaze>0 0 -1</Gaze>", plane="<NearPlane>-1 1 -1 1</NearPlane>", camextra="", lights="<AmbientLight>1 2 3</AmbientLight>",
+             materials=MAT, textures="", transformations="", verts="0 0 -5\n1 0 -5\n0 1 -5\n1 1 -5", texcoords="", objects="")
+    d.update(kw)
+    os.makedirs(tmp, exist_ok=True)
+    p = os.path.join(tmp, "scene.xml")
+    with open(p, "w") as f:
+        f.write(BASE.format(**d))
+    return p
+
+
+def mat_from_inv(o):
+    inv = np.eye(4)
+    inv[:3, :] = np.array(list(o.inv)).reshape(3, 4)
+    return np.linalg.inv(inv)
+
+
+def test_defaults_and_camera(rt, tmp_path):
+    p = write_scene(str(tmp_path), objects='<Sphere id="1"><Material>1</Material><Center>1</Center><Radius>2</Radius></Sphere>')
+    hs = rt.HostScene(p)
+    d = hs.desc.contents
+    assert d.max_recursion_depth == 3
+    assert d.shadow_ray_eps == pytest.approx(0.002) and d.int_test_eps == pytest.approx(0.001)   # Parser.h:23-25
+    assert list(d.ambient_light) == [1, 2, 3]
+    assert d.env_light_index == -1 and d.background_texture == -1
+    cam = hs.camera(0)
+    assert (cam.nx, cam.ny, cam.num_samples, cam.is_dof, cam.left_handed) == (8, 4, 1, 0, 0)
+    assert hs.image_name(0) == "x.png"
+    assert d.num_spheres == 1 and d.spheres[0].radius == 2 and list(d.spheres[0].center) == [0, 0, -5]
+    hs.close()
+
+
+def test_fovy_gazepoint_handedness_dof(rt, tmp_path):
+    p = write_scene(str(tmp_path), camattr=' handedness="left"', gaze="<GazePoint>0 0 -10</GazePoint>", plane="<FovY>90</FovY>",
+                    camextra="<NumSamples>9</NumSamples><FocusDistance>5</FocusDistance><ApertureSize>0.1</ApertureSize>",
+                    objects='<Sphere id="1"><Material>1</Material><Center>1</Center><Radius>2</Radius></Sphere>')
+    hs = rt.HostScene(p)
+    cam = hs.camera(0)
+    assert cam.left_handed == 1 and cam.is_dof == 1 and cam.num_samples == 9
+    assert list(cam.gaze) == [0, 0, -10]
+    assert cam.top == pytest.approx(2.0, rel=1e-6) and cam.right == pytest.approx(4.0, rel=1e-6)   # tan(45)*2, aspect 2
+    hs.close()
+
+
+def test_transform_composition_order_and_composite(rt, tmp_path):
+    """'s1 r1 t1': M = T.R.S (listed order = application order, Helper.cpp:153-176); a composite REPLACES (173-175);
+    'c' is only recognised as the first character of the list (Parser.h:792-794)."""
+    tr = ('<Transformations><Translation id="1">1 2 3</Translation><Scaling id="1">2 2 2</Scaling><Rotation id="1">90 0 0 1</Rotation>'
+          '<Composite id="1">1 0 0 5  0 1 0 6  0 0 1 7  0 0 0 1</Composite></Transformations>')
+    objs = ('<Sphere id="1"><Material>1</Material><Center>1</Center><Radius>1</Radius><Transformations>s1 r1 t1</Transformations></Sphere>'
+            '<Sphere id="2"><Material>1</Material><Center>1</Center><Radius>1</Radius><Transformations>c1 t1</Transformations></Sphere>'
+            '<Sphere id="3"><Material>1</Material><Center>1</Center><Radius>1</Radius><Transformations>t1 c1</Transformations></Sphere>')
+    hs = rt.HostScene(write_scene(str(tmp_path), transformations=tr, objects=objs))
+    d = hs.desc.contents
+    M = mat_from_inv(d.objects[0])
+    S = np.diag([2, 2, 2, 1.0]); R = np.array([[0, -1, 0, 0], [1, 0, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1.0]]); T = np.eye(4); T[:3, 3] = [1, 2, 3]
+    assert np.allclose(M, T @ R @ S, atol=1e-5)
+    # 'c1 t1': iterate j = n-1..0: t1 first (M = T), then the composite replaces it -> M = C
+    Cm = np.eye(4); Cm[:3, 3] = [5, 6, 7]
+    assert np.allclose(mat_from_inv(d.objects[1]), Cm, atol=1e-5)
+    # 't1 c1': the composite is not the first token -> skipped by the parser -> M = T
+    assert np.allclose(mat_from_inv(d.objects[2]), T, atol=1e-5)
+    # normal matrix is (M^-1)^T
+    nrm = np.array(list(d.objects[0].inv_t)).reshape(3, 3)
+    assert np.allclose(nrm, np.linalg.inv(M)[:3, :3].T, atol=1e-5)
+    hs.close()
+
+
+def test_instances_reset_transform_and_order(rt, tmp_path):
+    tr = '<Transformations><Translation id="1">1 0 0</Translation><Translation id="2">0 5 0</Translation></Transformations>'
+    objs = ('<Mesh id="7"><Material>1</Material><Transformations>t1</Transformations><Faces>1 2 3</Faces></Mesh>'
+            '<MeshInstance id="8" baseMeshId="7" resetTransform="false"><Material>1</Material><Transformations>t2</Transformations></MeshInstance>'
+            '<MeshInstance id="9" baseMeshId="7" resetTransform="true"><Material>1</Material><Transformations>t2</Transformations><MotionBlur>0 0 1</MotionBlur></MeshInstance>'
+            '<Sphere id="1"><Material>1</Material><Center>1</Center><Radius>1</Radius></Sphere>')
+    hs = rt.HostScene(write_scene(str(tmp_path), transformations=tr, objects=objs))
+    d = hs.desc.contents
+    # loop order of the reference: spheres, triangles, meshes, then instances (Helper.cpp:32-73)
+    assert [d.objects[i].kind for i in range(4)] == [0, 1, 1, 1]
+    assert np.allclose(mat_from_inv(d.objects[1])[:3, 3], [1, 0, 0])
+    assert np.allclose(mat_from_inv(d.objects[2])[:3, 3], [1, 5, 0])     # own . base
+    assert np.allclose(mat_from_inv(d.objects[3])[:3, 3], [0, 5, 0])     # reset
+    assert list(d.objects[3].blur) == [0, 0, 1] and list(d.objects[2].blur) == [0, 0, 0]
+    assert d.objects[2].geom == d.objects[1].geom == d.objects[3].geom
+    hs.close()
+
+
+def test_smooth_normals_and_standalone_triangles(rt, tmp_path):
+    """Standalone <Triangle>s are always smooth-shaded and share the GLOBAL vertex normals."""
+    objs = ('<Triangle id="1"><Material>1</Material><Indices>1 2 3</Indices></Triangle>'
+            '<Mesh id="2"><Material>1</Material><Faces>2 4 3</Faces></Mesh>'
+            '<Mesh id="3" shadingMode="smooth"><Material>1</Material><Faces>2 4 3</Faces></Mesh>')
+    hs = rt.HostScene(write_scene(str(tmp_path), objects=objs))
+    d = hs.desc.contents
+    assert [d.meshes[i].smooth for i in range(3)] == [1, 0, 1]
+    n = np.array([d.vertex_normals[i] for i in range(12)]).reshape(4, 3)
+    assert np.allclose(n, [[0, 0, 1]] * 4, atol=1e-6)    # all faces lie in z = -5, CCW seen from +z
+    hs.close()
+
+
+def test_texture_state_persists_across_texture_maps(rt, tmp_path):
+    """dm / interpolation / normalizer / scale / bump are declared outside the <TextureMap> loop (Parser.h:479-486)."""
+    tex = ('<Textures><TextureMap id="1" type="perlin"><DecalMode>bump_normal</DecalMode><NoiseConversion>absval</NoiseConversion><NoiseScale>6</NoiseScale>'
+           '<BumpFactor>0.3</BumpFactor></TextureMap><TextureMap id="2" type="perlin"><DecalMode>replace_kd</DecalMode></TextureMap></Textures>')
+    objs = '<Sphere id="1"><Material>1</Material><Center>1</Center><Radius>1</Radius><Textures>1 2</Textures></Sphere>'
+    hs = rt.HostScene(write_scene(str(tmp_path), textures=tex, objects=objs))
+    d = hs.desc.contents
+    t0, t1 = d.textures[0], d.textures[1]
+    assert (t0.type, t0.decal_mode, t0.noise_conversion) == (1, 2, 0)
+    assert t0.noise_scale == 6 and t0.bump_factor == pytest.approx(0.3)
+    assert (t1.decal_mode, t1.noise_conversion) == (0, 0) and t1.noise_scale == 6 and t1.bump_factor == pytest.approx(0.3)   # inherited
+    assert list(d.objects[0].tex) == [1, 2]
+    hs.close()
+
+
+def test_ply_quads_uv_and_offsets(rt, tmp_path):
+    os.makedirs(tmp_path / "s", exist_ok=True)
+    v = np.array([[0, 0, -5], [1, 0, -5], [1, 1, -5], [0, 1, -5]], dtype=np.float32)
+    uv = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], dtype=np.float32)
+    rt.scenes.write_ply(str(tmp_path / "s" / "q.ply"), v, np.array([[0, 1, 2, 3]]), uv)
+    tex = '<Textures><TextureMap id="1" type="perlin"><DecalMode>replace_kd</DecalMode></TextureMap></Textures>'
+    objs = '<Mesh id="1"><Material>1</Material><Textures>1</Textures><Faces plyFile="q.ply" /></Mesh>'
+    p = write_scene(str(tmp_path / "s"), textures=tex, objects=objs, texcoords="<TexCoordData>9 9\n 8 8</TexCoordData>")
+    hs = rt.HostScene(p)
+    d = hs.desc.contents
+    assert d.num_vertices == 8 and d.num_triangles == 2          # 4 XML vertices + 4 PLY vertices; quad split (0,1,2),(2,3,0)
+    assert [d.tri_indices[i] for i in range(6)] == [4, 5, 6, 6, 7, 4]
+    assert d.num_texcoords == 6
+    assert d.objects[0].tex_offset == (2 + 1) - (4 + 1)           # textureOffset - vertexOffset (Parser.h:1051,1065,1102)
+    uvi = d.tri_indices[0] + d.objects[0].tex_offset
+    assert (d.texcoords[2 * uvi], d.texcoords[2 * uvi + 1]) == (0.0, 0.0)
+    hs.close()
+
+
+def test_lights_order_and_env(rt, tmp_path):
+    os.makedirs(tmp_path / "s", exist_ok=True)
+    img = np.full((4, 8, 4), 2.5, dtype=np.float32)
+    rt.scenes.write_exr(str(tmp_path / "s" / "env.exr"), img)
+    lights = ('<SphericalDirectionalLight id="9"><ImageId>1</ImageId></SphericalDirectionalLight><AreaLight id="4"><Position>0 1 0</Position><Normal>0 -2 0</Normal>'
+              '<Size>2</Size><Radiance>1 1 1</Radiance></AreaLight><SpotLight id="3"><Position>0 0 0</Position><Direction>0 0 -1</Direction><Intensity>1 1 1</Intensity>'
+              '<CoverageAngle>60</CoverageAngle><FalloffAngle>40</FalloffAngle></SpotLight><DirectionalLight id="2"><Direction>0 -1 0</Direction><Radiance>3 3 3</Radiance></DirectionalLight>'
+              '<PointLight id="1"><Position>1 1 1</Position><Intensity>5 5 5</Intensity></PointLight>')
+    tex = "<Textures><Images><Image id=\"1\">env.exr</Image></Images></Textures>"
+    objs = '<Sphere id="1"><Material>1</Material><Center>1</Center><Radius>1</Radius></Sphere>'
+    hs = rt.HostScene(write_scene(str(tmp_path / "s"), lights=lights, textures=tex, objects=objs))
+    d = hs.desc.contents
+    assert [d.lights[i].type for i in range(5)] == [0, 2, 3, 1, 4]   # point, directional, spot, area, environment (Parser.h:1197-1315)
+    assert d.env_light_index == 4 and d.lights[4].image == 0
+    im = d.images[0]
+    assert (im.width, im.height, im.format) == (8, 4, 1)
+    hs.close()
+
+
+def test_image_io_roundtrips(rt, tmp_path):
+    lib = rt.load_core()
+    rgb = (np.arange(6 * 5 * 3, dtype=np.float32).reshape(5, 6, 3) * 3.7) - 20
+    # P3 PPM for ".png" names: clamp to 255, (unsigned char) truncation (src/Image.cpp:62-103)
+    p = str(tmp_path / "out.png")
+    assert lib.rt_host_save_image(p.encode(), rgb.ctypes.data, 6, 5) == 0
+    toks = open(p).read().split()
+    assert toks[:4] == ["P3", "6", "5", "255"]
+    vals = np.array(toks[4:], dtype=np.int64).reshape(5, 6, 3)
+    assert (vals == np.clip(rgb, 0, 255).astype(np.uint8)).all()
+    # half-float B,G,R EXR otherwise (src/Helper.cpp:361-412); read it back through the texture path
+    e = str(tmp_path / "out.exr")
+    assert lib.rt_host_save_image(e.encode(), rgb.ctypes.data, 6, 5) == 0
+    os.makedirs(tmp_path / "s", exist_ok=True)
+    os.replace(e, tmp_path / "s" / "t.exr")
+    tex = '<Textures><Images><Image id="1">t.exr</Image></Images><TextureMap id="1" type="image"><ImageId>1</ImageId><DecalMode>replace_kd</DecalMode></TextureMap></Textures>'
+    objs = '<Sphere id="1"><Material>1</Material><Center>1</Center><Radius>1</Radius><Textures>1</Textures></Sphere>'
+    hs = rt.HostScene(write_scene(str(tmp_path / "s"), textures=tex, objects=objs))
+    im = hs.desc.contents.images[0]
+    import ctypes as C
+    px = np.ctypeslib.as_array(C.cast(im.pixels, C.POINTER(C.c_float)), shape=(5, 6, 4))
+    assert np.allclose(px[..., :3], rgb.astype(np.float16).astype(np.float32))
+    assert np.allclose(px[..., 3], 1.0)
+    hs.close()
+
+
+def test_png_decoder(rt, tmp_path):
+    from PIL import Image
+    os.makedirs(tmp_path / "s", exist_ok=True)
+    a = (np.random.default_rng(1).integers(0, 255, size=(7, 9, 3))).astype(np.uint8)
+    Image.fromarray(a).save(tmp_path / "s" / "t.png")
+    tex = '<Textures><Images><Image id="1">t.png</Image></Images><TextureMap id="1" type="image"><ImageId>1</ImageId><DecalMode>replace_kd</DecalMode></TextureMap></Textures>'
+    objs = '<Sphere id="1"><Material>1</Material><Center>1</Center><Radius>1</Radius><Textures>1</Textures></Sphere>'
+    hs = rt.HostScene(write_scene(str(tmp_path / "s"), textures=tex, objects=objs))
+    im = hs.desc.contents.images[0]
+    import ctypes as C
+    px = np.ctypeslib.as_array(C.cast(im.pixels, C.POINTER(C.c_ubyte)), shape=(7, 9, 4))
+    assert (px[..., :3] == a).all() and (px[..., 3] == 255).all()
+    hs.close()
+
+
+def test_malformed_inputs_are_errors_not_crashes(rt, tmp_path):
+    with pytest.raises(rt.RtError) as e:
+        rt.HostScene(str(tmp_path / "missing.xml"))
+    assert e.value.code == rt.RT_ERR_IO
+    bad = tmp_path / "bad.xml"
+    bad.write_text("<Scene><Cameras></Scene>")
+    with pytest.raises(rt.RtError) as e:
+        rt.HostScene(str(bad))
+    assert e.value.code == rt.RT_ERR_PARSE
+    p = write_scene(str(tmp_path / "a"), objects='<Sphere id="1"><Material>3</Material><Center>1</Center><Radius>1</Radius></Sphere>')
+    with pytest.raises(rt.RtError) as e:
+        rt.HostScene(p)
+    assert e.value.code == rt.RT_ERR_PARSE and "Material" in str(e.value)
+    p = write_scene(str(tmp_path / "b"), objects='<MeshInstance id="2" baseMeshId="5" resetTransform="true"><Material>1</Material></MeshInstance>')
+    with pytest.raises(rt.RtError):
+        rt.HostScene(p)
+    # textured mesh without texture coordinates would read out of bounds in the reference
+    tex = '<Textures><TextureMap id="1" type="perlin"><DecalMode>replace_kd</DecalMode></TextureMap></Textures>'
+    p = write_scene(str(tmp_path / "c"), textures=tex, objects='<Mesh id="1"><Material>1</Material><Textures>1</Textures><Faces>1 2 3</Faces></Mesh>')
+    with pytest.raises(rt.RtError):
+        rt.HostScene(p)

@@ -1,0 +1,103 @@
+"""Known-answer tests derivable from the reference's code + the Philox stream definition.  CPU only."""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+
+
+def test_philox_known_answer_vectors(rt):
+    """Random123 kat_vectors for philox4x32-10.  The oracle returns floats (x >> 8) * 2^-24; compare the top 24 bits."""
+    lib = rt.load_oracle()
+    vecs = [((0, 0, 0, 0), 0, (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, 0xffffffffffffffff, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0x299f31d0 << 32) | 0xa4093822, (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, exp in vecs:
+        out = (C.c_float * 4)()
+        lib.oracle_philox(key, *ctr, out)
+        got = [int(round(x * 16777216.0)) for x in out]
+        assert got == [e >> 8 for e in exp]
+        assert all(0.0 <= x < 1.0 for x in out)
+
+
+def test_perlin_lattice_points(rt):
+    """Perlin value at lattice points is 0 -> 0.5 after the linear conversion, 0 after absval (src/Perlin.cpp:52-84)."""
+    lib = rt.load_oracle()
+    for p in [(0, 0, 0), (1, 2, 3), (-4, 7, -2)]:
+        assert lib.oracle_perlin(*map(float, p), 1.0, 1) == pytest.approx(0.5, abs=1e-6)
+        assert lib.oracle_perlin(*map(float, p), 1.0, 0) == pytest.approx(0.0, abs=1e-6)
+    v = lib.oracle_perlin(0.3, 0.7, 0.2, 2.0, 1)
+    assert 0.0 <= v <= 1.0
+
+
+def test_conductor_fresnel_normal_incidence(rt):
+    """rs = rp at normal incidence: ((n-1)^2 + k^2) / ((n+1)^2 + k^2) (src/Scene.cpp:135-146)."""
+    lib = rt.load_oracle()
+    n, k = 0.37, 2.82
+    expect = ((n - 1) ** 2 + k * k) / ((n + 1) ** 2 + k * k)
+    assert lib.oracle_conductor_fresnel(n, k, 1.0) == pytest.approx(expect, rel=1e-5)
+
+
+def _one_object_scene(rt, tmp, body, lights="<AmbientLight>0 0 0</AmbientLight>", extra="", res=(4, 4), cam_extra="", verts="0 0 0\n 1 0 -5\n -1 0 -5\n 0 1 -5"):
+    xml = f"""<Scene>
+  <BackgroundColor>7 8 9</BackgroundColor>
+  <IntersectionTestEpsilon>1e-6</IntersectionTestEpsilon>
+  <Cameras><Camera id="1"><Position>0 0 0</Position><Gaze>0 0 -1</Gaze><Up>0 1 0</Up><NearPlane>-1 1 -1 1</NearPlane>
+    <NearDistance>1</NearDistance><ImageResolution>{res[0]} {res[1]}</ImageResolution><ImageName>t.ppm</ImageName>{cam_extra}</Camera></Cameras>
+  <Lights>{lights}</Lights>
+  <Materials><Material id="1"><AmbientReflectance>1 1 1</AmbientReflectance><DiffuseReflectance>1 1 1</DiffuseReflectance>
+    <SpecularReflectance>0 0 0</SpecularReflectance></Material></Materials>
+  {extra}
+  <VertexData>{verts}</VertexData>
+  <Objects>{body}</Objects>
+</Scene>"""
+    d = os.path.join(tmp, "s")
+    os.makedirs(d, exist_ok=True)
+    p = os.path.join(d, "scene.xml")
+    with open(p, "w") as f:
+        f.write(xml)
+    return p
+
+
+def test_camera_corner_rays_and_sphere_roots(rt, tmp_path):
+    """Camera ray through pixel centres (src/Camera.cpp:63-72) and the sphere's nearer root (src/Shape.cpp:355-388)."""
+    body = '<Sphere id="1"><Material>1</Material><Center>1</Center><Radius>1</Radius></Sphere>'
+    p = _one_object_scene(rt, str(tmp_path), body, verts="0 0 -5", res=(2, 2))
+    hs = rt.HostScene(p)
+    cam = hs.camera(0)
+    hits = rt.oracle_trace_primary(hs.desc, cam, threads=1)
+    # 2x2 image on a [-1,1]^2 plane at distance 1: pixel centres at (+-0.5, +-0.5, -1); the unit sphere at z=-5 is missed by all four
+    assert hits["full"].sum() == 0
+    img = rt.oracle_render(hs.desc, cam, threads=1)
+    assert np.allclose(img, [7, 8, 9])   # camera-ray miss -> BackgroundColor
+    hs.close()
+    p = _one_object_scene(rt, str(tmp_path / "b"), body, verts="0 0 -5", res=(1, 1))
+    hs = rt.HostScene(p)
+    hits = rt.oracle_trace_primary(hs.desc, hs.camera(0), threads=1)
+    assert hits["full"][0, 0] == 1 and hits["t"][0, 0] == pytest.approx(4.0, abs=1e-5)
+    assert np.allclose(hits["normal"][0, 0], [0, 0, 1], atol=1e-6)
+    hs.close()
+
+
+def test_triangle_edge_rule(rt, tmp_path):
+    """beta, gamma >= -eps and beta + gamma <= 1 (src/Shape.cpp:330-331): a ray through a vertex-adjacent point hits,
+    a ray just outside the hypotenuse misses."""
+    body = '<Triangle id="1"><Material>1</Material><Indices>2 3 4</Indices></Triangle>'
+    p = _one_object_scene(rt, str(tmp_path), body, res=(1, 1))
+    hs = rt.HostScene(p)
+    hits = rt.oracle_trace_primary(hs.desc, hs.camera(0), threads=1)
+    assert hits["full"][0, 0] == 1 and hits["t"][0, 0] == pytest.approx(5.0, rel=1e-6)   # (0,0,-5) lies on edge a-b
+    hs.close()
+
+
+def test_point_light_inverse_square_and_ambient(rt, tmp_path):
+    """E = I / d^2, diffuse = E kd max(0, n.wi); ambient added once (src/Light.cpp:168-250, src/Scene.cpp:243-267)."""
+    body = '<Triangle id="1"><Material>1</Material><Indices>3 2 4</Indices></Triangle>'   # CCW seen from the camera: normal +z
+    lights = "<AmbientLight>10 20 30</AmbientLight><PointLight id=\"1\"><Position>0 0 -3</Position><Intensity>400 400 400</Intensity></PointLight>"
+    p = _one_object_scene(rt, str(tmp_path), body, lights=lights, res=(1, 1), verts="0 0 0\n 3 -3 -5\n -3 -3 -5\n 0 3 -5")
+    hs = rt.HostScene(p)
+    img = rt.oracle_render(hs.desc, hs.camera(0), threads=1)
+    # hit point (0,0,-5), normal +z (towards the camera), light 2 units in front: E = 400/4 = 100, cos = 1
+    assert np.allclose(img[0, 0], [110, 120, 130], rtol=1e-5)
+    hs.close()
