@@ -220,7 +220,8 @@ typedef struct RtStats {
     uint64_t rays_primary, rays_secondary, rays_shadow;   /* queries issued in the last render */
     uint64_t launches;                                    /* kernels launched in the last render */
     uint64_t waves;
-    uint64_t node_visits, prim_tests;                     /* only with collect_counters */
+    uint64_t node_visits, prim_tests;                     /* closest-hit queries; only with collect_counters bit 1 */
+    uint64_t node_visits_shadow, prim_tests_shadow;       /* occlusion queries; only with collect_counters bit 1 */
     double ms_total;          /* first launch -> framebuffer ready (CUDA events) */
     double ms_extend, ms_shade, ms_shadow, ms_raygen, ms_resolve;  /* per-stage sums, CUDA events (only with collect_counters bit 0) */
     uint64_t launches_extend, launches_shade, launches_shadow;     /* launches per stage in the last render */

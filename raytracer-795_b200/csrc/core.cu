@@ -34,6 +34,11 @@ template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { Free(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
     void Alloc(size_t count) {
         if (count <= n && p) return;
         Free();
@@ -50,6 +55,9 @@ struct DevBuf {
 };
 
 struct QueueBufs {
+    QueueBufs() = default;
+    QueueBufs(QueueBufs&&) noexcept = default;
+    QueueBufs& operator=(QueueBufs&&) noexcept = default;
     DevBuf<float4> o_time, d_tmax, w_pixel, hit;
     DevBuf<int4> meta;
     DevBuf<int32_t> hit_obj;
@@ -76,6 +84,8 @@ struct RtScene {
     DevBuf<RtLight> lights;
     bool has_dielectric = false;
     int bvh_depth = 0;
+    bool persistent = true;            // K2/K4 as persistent warps with dynamic fetch (traverse_pt.cuh); RT795_TRAVERSAL=classic selects traverse.cuh
+    int grid_extend = 0, grid_shadow = 0;   // resident CTAs: SM count x occupancy
     // render state
     std::vector<QueueBufs> levels;
     size_t queue_cap = 0, shadow_cap = 0;
@@ -368,8 +378,14 @@ struct Driver {
         for (int first = 0; first < n; first += chunk) {
             int m = std::min(chunk, n - first);
             CK(cudaMemsetAsync(&sc->counters.p->next_count, 0, 2 * sizeof(int32_t), st));
+            if (sc->persistent) CK(cudaMemsetAsync(&sc->counters.p->ray_cursor, 0, sizeof(int32_t), st));
             Timed(&ms_extend, [&] {
-                if (count) k_extend<true><<<Blocks(m), kBlock, 0, st>>>(sc->d, q, first, m, sc->counters.p);
+                if (sc->persistent) {
+                    TraceIO io{q.o_time, q.d_tmax, first, m, &sc->counters.p->ray_cursor, q.hit, q.hit_obj, nullptr, nullptr};
+                    int grid = std::min(Blocks(m), sc->grid_extend);
+                    if (count) k_trace_persistent<false, true><<<grid, kBlock, 0, st>>>(sc->d, io, sc->counters.p);
+                    else k_trace_persistent<false, false><<<grid, kBlock, 0, st>>>(sc->d, io, sc->counters.p);
+                } else if (count) k_extend<true><<<Blocks(m), kBlock, 0, st>>>(sc->d, q, first, m, sc->counters.p);
                 else k_extend<false><<<Blocks(m), kBlock, 0, st>>>(sc->d, q, first, m, sc->counters.p);
             });
             Timed(&ms_shade, [&] {
@@ -383,8 +399,14 @@ struct Driver {
             int next_n = sc->h_counters->next_count, shadow_n = sc->h_counters->shadow_count;
             if (sc->h_counters->overflow) throw Invalid{"ray queue overflow (raise queue_capacity)"};
             if (shadow_n > 0) {
+                if (sc->persistent) CK(cudaMemsetAsync(&sc->counters.p->ray_cursor, 0, sizeof(int32_t), st));
                 Timed(&ms_shadow, [&] {
-                    if (count) k_shadow<true><<<Blocks(shadow_n), kBlock, 0, st>>>(sc->d, sq, shadow_n, accum, sc->counters.p);
+                    if (sc->persistent) {
+                        TraceIO io{sq.o_time, sq.d_tmax, 0, shadow_n, &sc->counters.p->ray_cursor, nullptr, nullptr, sq.c_pixel, accum};
+                        int grid = std::min(Blocks(shadow_n), sc->grid_shadow);
+                        if (count) k_trace_persistent<true, true><<<grid, kBlock, 0, st>>>(sc->d, io, sc->counters.p);
+                        else k_trace_persistent<true, false><<<grid, kBlock, 0, st>>>(sc->d, io, sc->counters.p);
+                    } else if (count) k_shadow<true><<<Blocks(shadow_n), kBlock, 0, st>>>(sc->d, sq, shadow_n, accum, sc->counters.p);
                     else k_shadow<false><<<Blocks(shadow_n), kBlock, 0, st>>>(sc->d, sq, shadow_n, accum, sc->counters.p);
                 });
                 launches++; n_shadow++;
@@ -489,7 +511,8 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
     if (dr.count) {
         CK(cudaMemcpy(sc->h_counters, sc->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost));
         s.node_visits = sc->h_counters->node_visits; s.prim_tests = sc->h_counters->prim_tests;
-    } else { s.node_visits = 0; s.prim_tests = 0; }
+        s.node_visits_shadow = sc->h_counters->node_visits_shadow; s.prim_tests_shadow = sc->h_counters->prim_tests_shadow;
+    } else { s.node_visits = s.prim_tests = s.node_visits_shadow = s.prim_tests_shadow = 0; }
 }
 
 template <typename F>
@@ -534,6 +557,17 @@ int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out) {
         sc->device = device;
         CK(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&sc->ev0)); CK(cudaEventCreate(&sc->ev1));
+        {
+            const char* tv = getenv("RT795_TRAVERSAL");
+            sc->persistent = !(tv && std::string(tv) == "classic");
+            cudaDeviceProp prop;
+            CK(cudaGetDeviceProperties(&prop, device));
+            int be = 1, bs = 1;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_persistent<false, false>, kBlock, 0));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_trace_persistent<true, false>, kBlock, 0));
+            sc->grid_extend = prop.multiProcessorCount * std::max(1, be);
+            sc->grid_shadow = prop.multiProcessorCount * std::max(1, bs);
+        }
         BuildAndUpload(sc, desc);
     });
     if (rcode != RT_OK) { if (sc) rt_scene_destroy(sc); return rcode; }

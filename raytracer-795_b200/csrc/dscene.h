@@ -81,8 +81,9 @@ struct DShadowQueue {
 enum : uint32_t { RAY_PRIMARY = 1u, RAY_BEER_SELF = 2u, RAY_BEER_SIBLING = 4u, RAY_SPECULAR = 8u };
 
 struct DCounters {
-    int32_t next_count, shadow_count, overflow, pad;
-    unsigned long long node_visits, prim_tests;
+    int32_t next_count, shadow_count, overflow, ray_cursor;
+    unsigned long long node_visits, prim_tests;                 // closest-hit queries
+    unsigned long long node_visits_shadow, prim_tests_shadow;   // occlusion queries
 };
 
 }  // namespace rt795

@@ -9,6 +9,7 @@
 //   K8 k_resolve  box-filter mean (src/Scene.cpp:409) into Image::_data layout (src/Image.cpp:17-24)
 #pragma once
 #include "shade.cuh"
+#include "traverse_pt.cuh"
 
 namespace rt795 {
 
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow(DScene sc, DShadowQueue sq, i
     if (!(any_nan(o) || any_nan(d))) {
         unsigned cn = 0, cp = 0;
         occluded = trace<true, COUNT>(sc, o, d, ot.w, dt.w, h, cn, cp);
-        if (COUNT) { atomicAdd(&ctr->node_visits, (unsigned long long)cn); atomicAdd(&ctr->prim_tests, (unsigned long long)cp); }
+        if (COUNT) { atomicAdd(&ctr->node_visits_shadow, (unsigned long long)cn); atomicAdd(&ctr->prim_tests_shadow, (unsigned long long)cp); }
     }
     if (!occluded) {
         float4 c = sq.c_pixel[i];

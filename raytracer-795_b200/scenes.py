@@ -671,3 +671,167 @@ CONFIGS = {
     "c4": dict(gen=scene_c4, label="C4 ~870k-triangle mesh x16 (TLAS/BLAS), transforms + motion blur, Perlin bump/kd + image texture, 1920x1080, 64 spp"),
     "c5": dict(gen=scene_c5, label="C5 path-traced Cornell box, BRDF materials, NEE + RR, HDR env light + tone map, 3840x2160, 1024 spp"),
 }
+
+
+# ------------------------------------------------------------------------------------------ feature-matrix scenes (parity coverage)
+def _write_png_rgb(path: str, w: int = 64, h: int = 48, seed: int = 3) -> None:
+    """Small RGB8 PNG (non-interlaced) written with zlib only, readable by the oracle's png shim and the host shell."""
+    import zlib
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = np.stack([(xx * 255 // max(1, w - 1)), (yy * 255 // max(1, h - 1)), ((xx // 8 + yy // 8) % 2) * 200 + rng.integers(0, 40, size=(h, w))], axis=-1).astype(np.uint8)
+    raw = b"".join(b"\x00" + img[y].tobytes() for y in range(h))
+
+    def chunk(t, d):
+        c = struct.pack(">I", len(d)) + t + d
+        return c + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+
+
+def scene_features(outdir: str, variant: str = "lights", res=(192, 144), spp: int = 1, name: str = "feat") -> str:
+    """Small scenes that exercise every branch of the hot path the reference implements:
+      lights    point + directional + spot lights, Blinn-Phong, mirror / conductor / dielectric recursion, transforms (deterministic)
+      brdf      the eight BRDF models (Light.cpp:62-155) under point + directional light (deterministic)
+      textures  PNG + EXR image textures (replace_kd / blend_kd / replace_all / replace_normal / bump_normal, nearest + bilinear),
+                Perlin kd + bump on spheres and meshes, replace_background, non-uniform scale + rotation (deterministic)
+      stochastic  depth of field, motion blur, glossy mirror, area light, non-square sample count
+      env       environment (SphericalDirectionalLight) lighting + left-handed camera
+    """
+    os.makedirs(outdir, exist_ok=True)
+    W, H = res
+    cam_extra, lights, textures, objects, transformations, brdfs = "", "", "", "", "", ""
+    background = "9 11 15"
+    handed = ""
+    verts = [(-8, 0, 8), (8, 0, 8), (8, 0, -8), (-8, 0, -8),          # floor 1-4
+             (-8, 10, 8), (8, 10, 8), (8, 10, -8), (-8, 10, -8),      # ceiling 5-8
+             (-4.0, 1.5, 0.0), (0.0, 1.5, -1.0), (4.0, 1.5, 0.5), (-2.0, 1.0, 3.5), (2.2, 1.0, 3.2), (0.0, 4.5, -3.0)]   # centres 9-14
+    uvs = [(0, 0), (3, 0), (3, 3), (0, 3), (0, 0), (1, 0), (1, 1), (0, 1)] + [(0, 0)] * 6
+    room = (_quad_faces(verts, (0, 1, 2, 3), (0, 1, 0)) + _quad_faces(verts, (4, 5, 6, 7), (0, -1, 0)) + _quad_faces(verts, (3, 2, 6, 7), (0, 0, 1)) +
+            _quad_faces(verts, (0, 1, 5, 4), (0, 0, -1)) + _quad_faces(verts, (0, 3, 7, 4), (1, 0, 0)) + _quad_faces(verts, (1, 2, 6, 5), (-1, 0, 0)))
+    floor_only = _quad_faces(verts, (0, 1, 2, 3), (0, 1, 0))
+    mats = _material(1, (1, 1, 1), (0.7, 0.7, 0.7), (0.2, 0.2, 0.2), 10)
+    sphere = lambda i, m, c, r, extra="": f'    <Sphere id="{i}"><Material>{m}</Material><Center>{c}</Center><Radius>{r}</Radius>{extra}</Sphere>\n'
+    room_mesh = lambda m, extra="": f'    <Mesh id="90"><Material>{m}</Material>{extra}<Faces>\n{_faces_text(room)}\n    </Faces></Mesh>\n'
+    floor_mesh = lambda m, extra="": f'    <Mesh id="91"><Material>{m}</Material>{extra}<Faces>\n{_faces_text(floor_only)}\n    </Faces></Mesh>\n'
+    depth = 4
+    if variant == "lights":
+        lights = ('<AmbientLight>12 12 12</AmbientLight>\n<PointLight id="1"><Position>-3 8 5</Position><Intensity>2500 2400 2300</Intensity></PointLight>\n'
+                  '<DirectionalLight id="1"><Direction>0.3 -1 -0.4</Direction><Radiance>40 42 50</Radiance></DirectionalLight>\n'
+                  '<SpotLight id="1"><Position>4 9 4</Position><Direction>-0.3 -1 -0.35</Direction><Intensity>6000 6000 5000</Intensity>'
+                  '<CoverageAngle>50</CoverageAngle><FalloffAngle>30</FalloffAngle></SpotLight>')
+        mats += (_material(2, (1, 1, 1), (0.1, 0.1, 0.1), (0.5, 0.5, 0.5), 80, "mirror", (0.8, 0.8, 0.8)) +
+                 _material(3, (0, 0, 0), (0.05, 0.05, 0.05), (0.3, 0.3, 0.3), 40, "conductor", (0.9, 0.7, 0.4), "      <RefractionIndex>0.37</RefractionIndex>\n      <AbsorptionIndex>2.82</AbsorptionIndex>\n") +
+                 _material(4, (0, 0, 0), (0, 0, 0), (0, 0, 0), 1, "dielectric", None, "      <RefractionIndex>1.5</RefractionIndex>\n      <AbsorptionCoefficient>0.02 0.05 0.03</AbsorptionCoefficient>\n") +
+                 _material(5, (1, 1, 1), (0.2, 0.5, 0.8), (0.6, 0.6, 0.6), 30))
+        transformations = ('<Transformations><Translation id="1">0 0.5 0</Translation><Scaling id="1">1 1.4 0.8</Scaling><Rotation id="1">35 0.2 1 0.1</Rotation>'
+                           '<Composite id="1">0.9 0 0.1 1.0  0 1.1 0 0.3  -0.1 0 0.9 0.2  0 0 0 1</Composite></Transformations>')
+        objects = (sphere(1, 2, 10, 1.5) + sphere(2, 3, 11, 1.5) + sphere(3, 4, 9, 1.5) + sphere(4, 5, 12, 1.0, "<Transformations>s1 r1 t1</Transformations>") +
+                   sphere(5, 5, 13, 1.0, "<Transformations>c1</Transformations>") +
+                   '    <Triangle id="6"><Material>2</Material><Indices>14 11 10</Indices></Triangle>\n' + room_mesh(1))
+    elif variant == "brdf":
+        depth = 1
+        lights = ('<AmbientLight>5 5 5</AmbientLight>\n<PointLight id="1"><Position>0 9 6</Position><Intensity>3000 3000 3000</Intensity></PointLight>\n'
+                  '<DirectionalLight id="1"><Direction>-0.4 -1 -0.6</Direction><Radiance>60 60 60</Radiance></DirectionalLight>')
+        brdfs = ('<BRDFs><OriginalBlinnPhong id="1"><Exponent>30</Exponent></OriginalBlinnPhong><ModifiedBlinnPhong id="2"><Exponent>30</Exponent></ModifiedBlinnPhong>'
+                 '<ModifiedBlinnPhong id="3" normalized="true"><Exponent>30</Exponent></ModifiedBlinnPhong><OriginalPhong id="4"><Exponent>20</Exponent></OriginalPhong>'
+                 '<ModifiedPhong id="5"><Exponent>20</Exponent></ModifiedPhong><ModifiedPhong id="6" normalized="true"><Exponent>20</Exponent></ModifiedPhong>'
+                 '<TorranceSparrow id="7"><Exponent>50</Exponent></TorranceSparrow><TorranceSparrow id="8" kdfresnel="true"><Exponent>50</Exponent></TorranceSparrow></BRDFs>')
+        cx = [(-5.2 + 1.5 * k, 1.0 + 2.2 * (k % 2), 0.5 * (k % 3)) for k in range(8)]
+        verts = verts[:8] + cx
+        uvs = uvs[:8] + [(0, 0)] * 8
+        for k in range(8):
+            mats += _material(2 + k, (1, 1, 1), (0.5, 0.3 + 0.05 * k, 0.2), (0.8, 0.8, 0.8), 1, brdf=k + 1,
+                              extra="      <RefractionIndex>1.6</RefractionIndex>\n      <AbsorptionIndex>2.5</AbsorptionIndex>\n")
+            objects += sphere(k + 1, 2 + k, 9 + k, 0.7)
+        objects += floor_mesh(1)
+    elif variant == "textures":
+        depth = 2
+        _write_png_rgb(os.path.join(outdir, f"{name}_t.png"))
+        checker_exr(os.path.join(outdir, f"{name}_t.exr"), 96, 64)
+        _write_png_rgb(os.path.join(outdir, f"{name}_bg.png"), 80, 60, seed=9)
+        lights = ('<AmbientLight>20 20 20</AmbientLight>\n<PointLight id="1"><Position>1 9 7</Position><Intensity>4200 4200 4200</Intensity></PointLight>')
+        maps = [("image", 1, "replace_kd", "nearest", 255, None, None, None), ("image", 2, "blend_kd", "bilinear", 255, None, None, None),
+                ("image", 1, "replace_all", "bilinear", 1, None, None, None), ("image", 1, "replace_normal", "bilinear", 255, None, None, None),
+                ("image", 2, "bump_normal", "nearest", 255, None, None, 0.02), ("perlin", 0, "replace_kd", "nearest", 255, "linear", 2.5, 1.0),
+                ("perlin", 0, "bump_normal", "nearest", 255, "absval", 3.0, 0.4), ("image", 3, "replace_background", "bilinear", 255, None, None, None),
+                ("image", 2, "replace_kd", "bilinear", 255, None, None, None)]
+        tm = ""
+        for k, (ty, im, dm, ip, nz, nc, ns, bf) in enumerate(maps):
+            tm += f'<TextureMap id="{k + 1}" type="{ty}">' + (f"<ImageId>{im}</ImageId>" if ty == "image" else "") + f"<DecalMode>{dm}</DecalMode><Interpolation>{ip}</Interpolation><Normalizer>{nz}</Normalizer>"
+            tm += (f"<NoiseConversion>{nc}</NoiseConversion>" if nc else "") + (f"<NoiseScale>{ns}</NoiseScale>" if ns else "") + (f"<BumpFactor>{bf}</BumpFactor>" if bf else "") + "</TextureMap>\n"
+        textures = f'<Textures><Images><Image id="1">{name}_t.png</Image><Image id="2">{name}_t.exr</Image><Image id="3">{name}_bg.png</Image></Images>\n{tm}</Textures>'
+        transformations = '<Transformations><Scaling id="1">1.3 0.8 1</Scaling><Rotation id="1">40 0 1 0.3</Rotation><Translation id="1">0 0.4 0</Translation></Transformations>'
+        tex = lambda ids: f"<Textures>{ids}</Textures>"
+        objects = (sphere(1, 1, 9, 1.3, tex("1")) + sphere(2, 1, 10, 1.3, tex("2") + "<Transformations>s1 r1 t1</Transformations>") + sphere(3, 1, 11, 1.3, tex("4")) +
+                   sphere(4, 1, 12, 1.0, tex("5 6")) + sphere(5, 1, 13, 1.0, tex("7")) + sphere(6, 1, 14, 1.2, tex("3")) + floor_mesh(1, tex("9 7")))
+        # a textured quad mesh with its own uv: replace_normal + bump from image on triangles
+        verts += [(-7.5, 0.2, -6), (-2.5, 0.2, -6), (-2.5, 5.2, -7), (-7.5, 5.2, -7), (2.5, 0.2, -6), (7.5, 0.2, -6), (7.5, 5.2, -7), (2.5, 5.2, -7)]
+        uvs += [(0, 0), (1, 0), (1, 1), (0, 1), (0, 0), (2, 0), (2, 2), (0, 2)]
+        q1 = _quad_faces(verts, (14, 15, 16, 17), (0, 0.2, 1)); q2 = _quad_faces(verts, (18, 19, 20, 21), (0, 0.2, 1))
+        objects += f'    <Mesh id="92"><Material>1</Material>{tex("4")}<Faces>\n{_faces_text(q1)}\n    </Faces></Mesh>\n'
+        objects += f'    <Mesh id="93" shadingMode="smooth"><Material>1</Material>{tex("5 1")}<Faces>\n{_faces_text(q2)}\n    </Faces></Mesh>\n'
+    elif variant == "stochastic":
+        cam_extra = f"<NumSamples>{max(spp, 5)}</NumSamples><FocusDistance>14</FocusDistance><ApertureSize>0.35</ApertureSize>"
+        lights = ('<AmbientLight>10 10 10</AmbientLight>\n<AreaLight id="1"><Position>0 9.2 2</Position><Normal>0 -1 0</Normal><Size>3</Size><Radiance>900 900 850</Radiance></AreaLight>\n'
+                  '<PointLight id="1"><Position>-5 6 6</Position><Intensity>900 900 1000</Intensity></PointLight>')
+        mats += (_material(2, (1, 1, 1), (0.1, 0.1, 0.1), (0.5, 0.5, 0.5), 80, "mirror", (0.8, 0.8, 0.8), "      <Roughness>0.2</Roughness>\n") + _material(3, (1, 1, 1), (0.8, 0.3, 0.2), (0.4, 0.4, 0.4), 20))
+        objects = (sphere(1, 2, 10, 1.5) + sphere(2, 3, 9, 1.5, "<MotionBlur>0.6 0.9 0</MotionBlur>") + sphere(3, 3, 11, 1.5) + room_mesh(1))
+    elif variant == "stochastic_blur":   # same without depth of field: the reference applies motion blur only when DoF is off (Camera.cpp:105-112)
+        cam_extra = f"<NumSamples>{max(spp, 4)}</NumSamples>"
+        lights = ('<AmbientLight>10 10 10</AmbientLight>\n<AreaLight id="1"><Position>0 9.2 2</Position><Normal>0 -1 0</Normal><Size>3</Size><Radiance>900 900 850</Radiance></AreaLight>')
+        mats += _material(2, (1, 1, 1), (0.8, 0.3, 0.2), (0.4, 0.4, 0.4), 20)
+        objects = (sphere(1, 2, 10, 1.5, "<MotionBlur>1.2 0.6 0</MotionBlur>") + sphere(2, 2, 9, 1.2) + room_mesh(1))
+    elif variant == "env":
+        handed = ' handedness="left"'
+        sky_exr(os.path.join(outdir, f"{name}_sky.exr"), 128, 64, sun_scale=0.002)
+        textures = f'<Textures><Images><Image id="1">{name}_sky.exr</Image></Images></Textures>'
+        cam_extra = f"<NumSamples>{max(spp, 4)}</NumSamples>"
+        lights = '<AmbientLight>0 0 0</AmbientLight>\n<SphericalDirectionalLight id="1"><ImageId>1</ImageId></SphericalDirectionalLight>'
+        mats += _material(2, (0, 0, 0), (0.6, 0.4, 0.3), (0.5, 0.5, 0.5), 30)
+        objects = sphere(1, 2, 10, 1.5) + sphere(2, 1, 9, 1.5) + floor_mesh(1)
+    else:
+        raise ValueError(variant)
+    xml = f"""<Scene>
+  <MaxRecursionDepth>{depth}</MaxRecursionDepth>
+  <BackgroundColor>{background}</BackgroundColor>
+  <ShadowRayEpsilon>1e-3</ShadowRayEpsilon>
+  <IntersectionTestEpsilon>1e-6</IntersectionTestEpsilon>
+  <Cameras>
+    <Camera id="1"{handed}>
+      <Position>0.23 4.1 7.7</Position>
+      <GazePoint>0.02 1.9 0.03</GazePoint>
+      <Up>0 1 0</Up>
+      <FovY>58</FovY>
+      <NearDistance>1</NearDistance>
+      <ImageResolution>{W} {H}</ImageResolution>
+      <ImageName>{name}_{variant}.ppm</ImageName>
+      {cam_extra}
+    </Camera>
+  </Cameras>
+  {brdfs}
+  <Lights>
+{lights}
+  </Lights>
+  <Materials>
+{mats}  </Materials>
+  {textures}
+  {transformations}
+  <VertexData>
+{chr(10).join("    " + _fmt(p) for p in verts)}
+  </VertexData>
+  <TexCoordData>
+{chr(10).join("    " + _fmt(p) for p in uvs)}
+  </TexCoordData>
+  <Objects>
+{objects}  </Objects>
+</Scene>
+"""
+    path = os.path.join(outdir, f"{name}_{variant}.xml")
+    with open(path, "w") as fh:
+        fh.write(xml)
+    return path
+
+
+FEATURE_VARIANTS_DETERMINISTIC = ["lights", "brdf", "textures"]
+FEATURE_VARIANTS_STOCHASTIC = ["stochastic", "stochastic_blur", "env"]

@@ -217,3 +217,72 @@ def test_errors_are_reported_not_fatal(rt):
 def ctypes_byref(x):
     import ctypes
     return ctypes.byref(x)
+
+
+# ------------------------------------------------------------------------------------------------ feature matrix + edge cases
+@pytest.mark.parametrize("variant", ["lights", "brdf", "textures"])
+def test_feature_matrix_deterministic(rt, scene_dir, tmp_path, variant):
+    """GPU vs oracle AND vs the unmodified reference binary on deterministic scenes covering every light type, BRDF,
+    texture mode and material type."""
+    xml = rt.scenes.scene_features(os.path.join(scene_dir, "gfeat_" + variant), variant)
+    hs, sc = _load(rt, xml)
+    cam = hs.camera(0)
+    same = hit_agreement(sc.trace_primary(cam), rt.oracle_trace_primary(hs.desc, cam))
+    assert same.mean() >= 0.999, same.mean()
+    img = sc.render(cam)
+    ref = rt.oracle_render(hs.desc, cam)
+    r = rel_err(img, ref).max(axis=-1)
+    assert r[same].mean() <= 1e-3, r[same].mean()
+    assert np.quantile(r[same], 0.995) <= 1e-2, np.quantile(r[same], 0.995)
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_raytracer")
+    if os.path.exists(exe):
+        subprocess.run([exe, xml], cwd=tmp_path, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        rb = rt.read_f32(os.path.join(tmp_path, hs.image_name(0) + ".f32"))
+        r2 = rel_err(img, rb).max(axis=-1)
+        assert r2.mean() <= 1e-3 and np.quantile(r2, 0.99) <= 1e-2, (r2.mean(), np.quantile(r2, 0.99))
+    sc.close(); hs.close()
+
+
+@pytest.mark.parametrize("variant", ["stochastic", "stochastic_blur", "env"])
+def test_feature_matrix_stochastic(rt, scene_dir, tmp_path, variant):
+    xml = rt.scenes.scene_features(os.path.join(scene_dir, "gfeat_" + variant), variant, res=(128, 96), spp=16)
+    hs, sc = _load(rt, xml)
+    img, _ = _check_vs_oracle(rt, hs, sc, q=0.97)
+    _check_vs_reference_statistical(rt, xml, hs, img, str(tmp_path))
+    sc.close(); hs.close()
+
+
+def test_edge_cases(rt, scene_dir):
+    """Empty scene, 1x1 image, resolution that is not a tile multiple, tiny queue capacity (many waves / chunks),
+    non-square sample count - all must equal the oracle."""
+    d = os.path.join(scene_dir, "edge")
+    os.makedirs(d, exist_ok=True)
+    base = """<Scene><BackgroundColor>3 4 5</BackgroundColor><Cameras><Camera id="1"><Position>0 0 0</Position><Gaze>0 0 -1</Gaze><Up>0 1 0</Up>
+<NearPlane>-1 1 -1 1</NearPlane><NearDistance>1</NearDistance><ImageResolution>{nx} {ny}</ImageResolution><ImageName>e.ppm</ImageName>{extra}</Camera></Cameras>
+<Lights><AmbientLight>1 1 1</AmbientLight></Lights><Materials><Material id="1"><AmbientReflectance>1 1 1</AmbientReflectance>
+<DiffuseReflectance>1 1 1</DiffuseReflectance><SpecularReflectance>0 0 0</SpecularReflectance></Material></Materials>
+<VertexData>0 0 -5</VertexData><Objects>{objects}</Objects></Scene>"""
+    for tag, nx, ny, extra, objects in [("empty", 33, 17, "", ""), ("one", 1, 1, "", '<Sphere id="1"><Material>1</Material><Center>1</Center><Radius>1</Radius></Sphere>'),
+                                        ("odd", 37, 21, "<NumSamples>5</NumSamples>", '<Sphere id="1"><Material>1</Material><Center>1</Center><Radius>3</Radius></Sphere>')]:
+        p = os.path.join(d, tag + ".xml")
+        with open(p, "w") as f:
+            f.write(base.format(nx=nx, ny=ny, extra=extra, objects=objects))
+        hs, sc = _load(rt, p)
+        cam = hs.camera(0)
+        img = sc.render(cam)
+        ref = rt.oracle_render(hs.desc, cam)
+        assert np.allclose(img, ref, rtol=1e-5, atol=1e-5), tag
+        if tag == "empty":
+            assert np.allclose(img, [3, 4, 5])
+        sc.close(); hs.close()
+    # tiny queues: same image through many waves and chunks
+    xml = rt.scenes.scene_c2(os.path.join(scene_dir, "c2q"), res=64, spp=4)
+    hs, sc = _load(rt, xml)
+    cam = hs.camera(0)
+    a = sc.render(cam)
+    hs2, sc2 = _load(rt, xml)
+    b = sc2.render(cam, rt.default_opts(queue_capacity=2048, wave_rays=1000))
+    assert sc2.stats().waves > 10
+    assert np.allclose(a, b, rtol=2e-5, atol=1e-4)
+    for x in (sc, sc2, hs, hs2):
+        x.close()

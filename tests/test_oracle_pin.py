@@ -114,3 +114,40 @@ def test_oracle_statistical_vs_live_reference(rt, scene_dir, have_ref, tmp_path,
     from conftest import assert_statistically_equal
     assert_statistically_equal(refs[0], refs[1], img, b=6)
     hs.close()
+
+
+@pytest.mark.parametrize("variant", ["lights", "brdf", "textures"])
+def test_oracle_feature_matrix_deterministic_vs_live_reference(rt, scene_dir, have_ref, tmp_path, variant):
+    """Every light type, all eight BRDFs, every texture decal mode / interpolation / image format, transforms and the
+    mirror / conductor / dielectric recursion, against the unmodified reference on deterministic scenes."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    xml = rt.scenes.scene_features(os.path.join(scene_dir, "feat_" + variant), variant)
+    subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_raytracer"), xml], cwd=tmp_path, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    hs = rt.HostScene(xml)
+    ref = rt.read_f32(os.path.join(tmp_path, hs.image_name(0) + ".f32"))
+    img = rt.oracle_render(hs.desc, hs.camera(0))
+    r = np.abs(img - ref) / np.maximum(np.abs(ref), 1.0)
+    assert r.mean() <= 1e-5, r.mean()
+    assert np.quantile(r, 0.999) <= 1e-3, np.quantile(r, 0.999)
+    assert r.max() <= 5e-2, r.max()      # a nearest-neighbour texel can flip on a rounding difference
+    hs.close()
+
+
+@pytest.mark.parametrize("variant", ["stochastic", "stochastic_blur", "env"])
+def test_oracle_feature_matrix_stochastic_vs_live_reference(rt, scene_dir, have_ref, tmp_path, variant):
+    """Depth of field, motion blur, glossy reflection, area and environment lights, left-handed camera."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from conftest import assert_statistically_equal
+    xml = rt.scenes.scene_features(os.path.join(scene_dir, "feat_" + variant), variant, res=(96, 72), spp=25)
+    hs = rt.HostScene(xml)
+    refs = []
+    for i in range(2):
+        d = os.path.join(tmp_path, f"r{i}")
+        os.makedirs(d)
+        subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_raytracer"), xml], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        refs.append(rt.read_f32(os.path.join(d, hs.image_name(0) + ".f32")))
+    img = rt.oracle_render(hs.desc, hs.camera(0))
+    assert_statistically_equal(refs[0], refs[1], img, b=6)
+    hs.close()
