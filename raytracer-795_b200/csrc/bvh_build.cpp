@@ -159,4 +159,67 @@ void BuildSahBvh(const Aabb* prim_bounds, int n, int max_leaf, BuiltBvh* out) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------- BVH2 -> BVH4 collapse
+namespace {
+struct Child4 { Aabb box; int32_t ref; };
+
+void ReadChildren2(const BvhNode64& n, std::vector<Child4>* out) {
+    for (int slot = 0; slot < 2; slot++) {
+        Child4 c;
+        memcpy(&c.ref, &n.q[12 + slot], 4);
+        if (c.ref == kNoChild) continue;
+        c.box.lo[0] = n.q[slot * 4 + 0]; c.box.hi[0] = n.q[slot * 4 + 1]; c.box.lo[1] = n.q[slot * 4 + 2]; c.box.hi[1] = n.q[slot * 4 + 3];
+        c.box.lo[2] = n.q[8 + slot * 2 + 0]; c.box.hi[2] = n.q[8 + slot * 2 + 1];
+        out->push_back(c);
+    }
+}
+}  // namespace
+
+void CollapseToBvh4(const BuiltBvh& b2, BuiltBvh4* out) {
+    out->nodes.clear();
+    out->max_stack = 0;
+    struct Item { int node2; int node4; int stack_before; };
+    std::vector<Item> work;
+    out->nodes.emplace_back();
+    work.push_back({0, 0, 0});
+    while (!work.empty()) {
+        Item it = work.back(); work.pop_back();
+        std::vector<Child4> ch;
+        ReadChildren2(b2.nodes[it.node2], &ch);
+        while (ch.size() < 4) {
+            int best = -1; float best_area = -1.f;
+            for (size_t i = 0; i < ch.size(); i++)
+                if (ch[i].ref >= 0 && ch[i].box.HalfArea() > best_area) { best_area = ch[i].box.HalfArea(); best = (int)i; }
+            if (best < 0) break;
+            std::vector<Child4> sub;
+            ReadChildren2(b2.nodes[ch[best].ref], &sub);
+            if (ch.size() - 1 + sub.size() > 4) break;
+            ch.erase(ch.begin() + best);
+            ch.insert(ch.end(), sub.begin(), sub.end());
+        }
+        BvhNode128 nd;
+        memset(&nd, 0, sizeof nd);
+        int stack_here = it.stack_before + (int)ch.size() - 1;
+        out->max_stack = std::max(out->max_stack, stack_here);
+        for (int k = 0; k < 4; k++) {
+            int32_t ref = kNoChild;
+            if (k < (int)ch.size()) {
+                const Child4& c = ch[k];
+                nd.q[0 + k] = c.box.lo[0]; nd.q[4 + k] = c.box.hi[0]; nd.q[8 + k] = c.box.lo[1]; nd.q[12 + k] = c.box.hi[1];
+                nd.q[16 + k] = c.box.lo[2]; nd.q[20 + k] = c.box.hi[2];
+                ref = c.ref;
+                if (ref >= 0) {
+                    int idx4 = (int)out->nodes.size();
+                    out->nodes.emplace_back();
+                    work.push_back({c.ref, idx4, stack_here});
+                    ref = idx4;
+                }
+            }
+            memcpy(&nd.q[24 + k], &ref, 4);
+        }
+        out->nodes[it.node4] = nd;
+    }
+}
+
 }  // namespace rt795

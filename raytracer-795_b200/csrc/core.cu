@@ -72,7 +72,8 @@ struct RtScene {
     cudaStream_t stream = nullptr;
     DScene d{};
     // geometry + shading buffers
-    DevBuf<float4> nodes, tris, spheres;
+    DevBuf<float4> nodes, nodes4, tris, spheres;
+    DevBuf<int32_t> obj_root4;
     DevBuf<DObjectXf> obj_xf;
     DevBuf<DObjectSh> obj_sh;
     DevBuf<int32_t> tri_idx;
@@ -86,6 +87,8 @@ struct RtScene {
     int bvh_depth = 0;
     bool persistent = true;            // K2/K4 as persistent warps with dynamic fetch (traverse_pt.cuh); RT795_TRAVERSAL=classic selects traverse.cuh
     int grid_extend = 0, grid_shadow = 0;   // resident CTAs: SM count x occupancy
+    int trav_flags = 2, trav_flags_shadow = 3;   // TraceIO.flags for closest-hit / occlusion launches (measured best on C4; RT795_TRAVERSAL_FLAGS overrides both)
+    bool full_grid = false;                 // RT795_FULL_GRID=1: one thread per ray instead of resident warps
     // render state
     std::vector<QueueBufs> levels;
     size_t queue_cap = 0, shadow_cap = 0;
@@ -173,8 +176,9 @@ void BuildAndUpload(RtScene* sc, const RtSceneDesc* s) {
 
     // ---- BLAS per mesh
     std::vector<BvhNode64> nodes;
+    std::vector<BvhNode128> nodes4;
     std::vector<float4> tris;
-    std::vector<int> mesh_root(s->num_meshes, 0), mesh_depth(s->num_meshes, 0);
+    std::vector<int> mesh_root(s->num_meshes, 0), mesh_depth(s->num_meshes, 0), mesh_root4(s->num_meshes, 0), mesh_stack4(s->num_meshes, 0);
     std::vector<Aabb> mesh_bounds(s->num_meshes);
     tris.reserve((size_t)s->num_triangles * 3);
     for (int m = 0; m < s->num_meshes; m++) {
@@ -197,6 +201,22 @@ void BuildAndUpload(RtScene* sc, const RtSceneDesc* s) {
         BuiltBvh bv;
         BuildSahBvh(pb.data(), me.tri_count, 4, &bv);
         int node_base = (int)nodes.size(), tri_base = (int)(tris.size() / 3);
+        {
+            BuiltBvh4 b4;
+            CollapseToBvh4(bv, &b4);
+            int base4 = (int)nodes4.size();
+            mesh_root4[m] = base4; mesh_stack4[m] = b4.max_stack;
+            for (BvhNode128 nd : b4.nodes) {
+                for (int c = 0; c < 4; c++) {
+                    int32_t ch; memcpy(&ch, &nd.q[24 + c], 4);
+                    if (ch == kNoChild) continue;
+                    if (ch >= 0) ch += base4;
+                    else { int payload = ~ch; int first = (payload >> 3) + tri_base; ch = ~((first << 3) | (payload & 7)); }
+                    memcpy(&nd.q[24 + c], &ch, 4);
+                }
+                nodes4.push_back(nd);
+            }
+        }
         mesh_root[m] = node_base;
         mesh_depth[m] = bv.max_depth;
         mesh_bounds[m] = bv.bounds;
@@ -226,7 +246,8 @@ void BuildAndUpload(RtScene* sc, const RtSceneDesc* s) {
     std::vector<Aabb> obounds(s->num_objects);
     std::vector<float4> spheres(s->num_spheres);
     for (int i = 0; i < s->num_spheres; i++) spheres[i] = make_float4(s->spheres[i].center[0], s->spheres[i].center[1], s->spheres[i].center[2], s->spheres[i].radius);
-    int max_blas_depth = 0;
+    int max_blas_depth = 0, max_blas_stack4 = 0;
+    std::vector<int32_t> root4(std::max(1, s->num_objects), 0);
     for (int i = 0; i < s->num_objects; i++) {
         const RtObject& o = s->objects[i];
         DObjectXf& x = oxf[i];
@@ -239,7 +260,10 @@ void BuildAndUpload(RtScene* sc, const RtSceneDesc* s) {
             const RtSphere& sp = s->spheres[o.geom];
             for (int k = 0; k < 3; k++) { ob.lo[k] = sp.center[k] - sp.radius; ob.hi[k] = sp.center[k] + sp.radius; }
             root = ~o.geom;
-        } else { ob = mesh_bounds[o.geom]; root = mesh_root[o.geom]; max_blas_depth = std::max(max_blas_depth, mesh_depth[o.geom]); }
+        } else {
+            ob = mesh_bounds[o.geom]; root = mesh_root[o.geom]; max_blas_depth = std::max(max_blas_depth, mesh_depth[o.geom]);
+            root4[i] = mesh_root4[o.geom]; max_blas_stack4 = std::max(max_blas_stack4, mesh_stack4[o.geom]);
+        }
         x.blur_root = make_float4(o.blur[0], o.blur[1], o.blur[2], BitsToFloat(root));
         // forward matrix M = (M^-1)^-1 (affine): invert the 3x3 part in double
         double A[3][3], t[3];
@@ -287,13 +311,33 @@ void BuildAndUpload(RtScene* sc, const RtSceneDesc* s) {
         }
         nodes.push_back(nd);
     }
+    int tlas_base4 = (int)nodes4.size();
+    {
+        BuiltBvh4 t4;
+        CollapseToBvh4(tl, &t4);
+        for (BvhNode128 nd : t4.nodes) {
+            for (int c = 0; c < 4; c++) {
+                int32_t ch; memcpy(&ch, &nd.q[24 + c], 4);
+                if (ch == kNoChild) continue;
+                if (ch >= 0) ch += tlas_base4;
+                else { int payload = ~ch; int obj = tl.order[payload >> 3]; ch = ~(obj << 3); }
+                memcpy(&nd.q[24 + c], &ch, 4);
+            }
+            nodes4.push_back(nd);
+        }
+        int need4 = t4.max_stack + max_blas_stack4 + 4;
+        if (need4 > kStackSize) throw Invalid{"4-wide BVH needs a deeper traversal stack (" + std::to_string(need4) + " > " + std::to_string(kStackSize) + ")"};
+    }
     sc->bvh_depth = tl.max_depth + max_blas_depth + 3;
     if (sc->bvh_depth > kStackSize) throw Invalid{"BVH too deep for the traversal stack (" + std::to_string(sc->bvh_depth) + " > " + std::to_string(kStackSize) + ")"};
     auto t1 = std::chrono::steady_clock::now();
 
     // ---- upload
     static_assert(sizeof(BvhNode64) == 64, "node size");
+    static_assert(sizeof(BvhNode128) == 128, "node4 size");
     sc->nodes.Upload((const float4*)nodes.data(), nodes.size() * 4, st);
+    sc->nodes4.Upload((const float4*)nodes4.data(), nodes4.size() * 8, st);
+    sc->obj_root4.Upload(root4.data(), root4.size(), st);
     sc->tris.Upload(tris.data(), tris.size(), st);
     sc->spheres.Upload(spheres.data(), spheres.size(), st);
     sc->obj_xf.Upload(oxf.data(), oxf.size(), st);
@@ -319,6 +363,7 @@ void BuildAndUpload(RtScene* sc, const RtSceneDesc* s) {
     auto t2 = std::chrono::steady_clock::now();
 
     DScene& d = sc->d;
+    d.nodes4 = sc->nodes4.p; d.obj_root4 = sc->obj_root4.p; d.tlas_root4 = tlas_base4;
     d.nodes = sc->nodes.p; d.tris = sc->tris.p; d.obj_xf = sc->obj_xf.p; d.spheres = sc->spheres.p; d.tlas_root = tlas_base;
     d.obj_sh = sc->obj_sh.p; d.tri_idx = sc->tri_idx.p; d.vertices = sc->vertices.p; d.normals = sc->normals.p; d.texcoords = sc->texcoords.p;
     d.materials = sc->materials.p; d.textures = sc->textures.p; d.images = sc->images.p; d.lights = sc->lights.p;
@@ -328,7 +373,7 @@ void BuildAndUpload(RtScene* sc, const RtSceneDesc* s) {
     d.env_light = s->env_light_index; d.background_texture = s->background_texture;
     for (int i = 0; i < s->num_materials; i++) if (s->materials[i].type == RT_MAT_DIELECTRIC) sc->has_dielectric = true;
 
-    sc->stats.bvh_nodes = nodes.size(); sc->stats.bvh_bytes = nodes.size() * 64; sc->stats.tri_bytes = tris.size() * 16;
+    sc->stats.bvh_nodes = nodes4.size(); sc->stats.bvh_bytes = nodes4.size() * 128; sc->stats.tri_bytes = tris.size() * 16;   // the 4-wide BVH is the one the render kernels walk sc->stats.tri_bytes = tris.size() * 16;
     sc->stats.ms_bvh_build = std::chrono::duration<double, std::milli>(t1 - t0).count();
     sc->stats.ms_upload = std::chrono::duration<double, std::milli>(t2 - t1).count();
 }
@@ -381,8 +426,8 @@ struct Driver {
             if (sc->persistent) CK(cudaMemsetAsync(&sc->counters.p->ray_cursor, 0, sizeof(int32_t), st));
             Timed(&ms_extend, [&] {
                 if (sc->persistent) {
-                    TraceIO io{q.o_time, q.d_tmax, first, m, &sc->counters.p->ray_cursor, q.hit, q.hit_obj, nullptr, nullptr};
-                    int grid = std::min(Blocks(m), sc->grid_extend);
+                    TraceIO io{q.o_time, q.d_tmax, first, m, &sc->counters.p->ray_cursor, q.hit, q.hit_obj, nullptr, nullptr, sc->trav_flags};
+                    int grid = sc->full_grid ? Blocks(m) : std::min(Blocks(m), sc->grid_extend);
                     if (count) k_trace_persistent<false, true><<<grid, kBlock, 0, st>>>(sc->d, io, sc->counters.p);
                     else k_trace_persistent<false, false><<<grid, kBlock, 0, st>>>(sc->d, io, sc->counters.p);
                 } else if (count) k_extend<true><<<Blocks(m), kBlock, 0, st>>>(sc->d, q, first, m, sc->counters.p);
@@ -402,8 +447,8 @@ struct Driver {
                 if (sc->persistent) CK(cudaMemsetAsync(&sc->counters.p->ray_cursor, 0, sizeof(int32_t), st));
                 Timed(&ms_shadow, [&] {
                     if (sc->persistent) {
-                        TraceIO io{sq.o_time, sq.d_tmax, 0, shadow_n, &sc->counters.p->ray_cursor, nullptr, nullptr, sq.c_pixel, accum};
-                        int grid = std::min(Blocks(shadow_n), sc->grid_shadow);
+                        TraceIO io{sq.o_time, sq.d_tmax, 0, shadow_n, &sc->counters.p->ray_cursor, nullptr, nullptr, sq.c_pixel, accum, sc->trav_flags_shadow};
+                        int grid = sc->full_grid ? Blocks(shadow_n) : std::min(Blocks(shadow_n), sc->grid_shadow);
                         if (count) k_trace_persistent<true, true><<<grid, kBlock, 0, st>>>(sc->d, io, sc->counters.p);
                         else k_trace_persistent<true, false><<<grid, kBlock, 0, st>>>(sc->d, io, sc->counters.p);
                     } else if (count) k_shadow<true><<<Blocks(shadow_n), kBlock, 0, st>>>(sc->d, sq, shadow_n, accum, sc->counters.p);
@@ -560,6 +605,8 @@ int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out) {
         {
             const char* tv = getenv("RT795_TRAVERSAL");
             sc->persistent = !(tv && std::string(tv) == "classic");
+            if (const char* f = getenv("RT795_TRAVERSAL_FLAGS")) sc->trav_flags = sc->trav_flags_shadow = atoi(f);
+            if (const char* g = getenv("RT795_FULL_GRID")) sc->full_grid = atoi(g) != 0;
             cudaDeviceProp prop;
             CK(cudaGetDeviceProperties(&prop, device));
             int be = 1, bs = 1;

@@ -6,7 +6,7 @@
 
 namespace rt795 {
 
-constexpr int kStackSize = 64;          // traversal stack entries per thread (node, t_entry)
+constexpr int kStackSize = 64;          // traversal stack entries per thread (node, t_entry); core.cu checks both BVHs against it
 constexpr int kMaxLights = 1 << 16;
 
 // Traversal record of a top-level entry: 64 bytes = the "64-B instance record" of SURVEY §8d.
@@ -29,7 +29,10 @@ struct DImage { const void* pixels; int32_t width, height, format, pad; };
 
 struct DScene {
     // geometry for traversal
-    const float4* nodes;                // BvhNode64 as 4 x float4
+    const float4* nodes4;               // BvhNode128 as 8 x float4 (4-wide collapse of `nodes`; used by k_trace_persistent)
+    const int32_t* obj_root4;           // per top-level entry: BLAS root in nodes4 (spheres: unused)
+    int32_t tlas_root4;
+    const float4* nodes;                // BvhNode64 as 4 x float4 (binary; classic kernels + rt_trace_primary)
     const float4* tris;                 // 3 x float4 per triangle in leaf order: (v0, bits prim), (e1, 0), (e2, 0)
     const DObjectXf* obj_xf;
     const float4* spheres;              // center.xyz, R

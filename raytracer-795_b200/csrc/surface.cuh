@@ -26,19 +26,36 @@ struct Surface {
     int prim_in_mesh;    // triangle index within its mesh (face order); 0 for spheres
 };
 
-__constant__ float c_perlin_table[16][3] = {{1, 1, 0}, {-1, 1, 0}, {1, -1, 0}, {-1, -1, 0}, {1, 0, 1}, {-1, 0, 1}, {1, 0, -1}, {-1, 0, -1},
-                                            {0, 1, 1}, {0, -1, 1}, {0, 1, -1}, {0, -1, -1}, {1, 1, 0}, {-1, 1, 0}, {0, -1, 1}, {0, -1, -1}};
-__constant__ int c_perlin_shuffle[16] = {12, 7, 15, 6, 11, 0, 4, 9, 13, 3, 14, 8, 2, 5, 1, 10};
-
-RT_D int perlin_shuffled(int i) { return c_perlin_shuffle[i & 15]; }   // i % 16 folded to [0,16) (src/Perlin.cpp:91-97)
+// Perlin tables of the reference (src/Perlin.cpp:4-25) packed into immediates: no constant-memory lookups with
+// lane-divergent indices (those serialise), just shifts.
+//   gradient component = ((bits >> (2*idx)) & 3) - 1, idx in [0,16):  table = {1,1,0},{-1,1,0},{1,-1,0},{-1,-1,0},{1,0,1},{-1,0,1},{1,0,-1},
+//   {-1,0,-1},{0,1,1},{0,-1,1},{0,1,-1},{0,-1,-1},{1,1,0},{-1,1,0},{0,-1,1},{0,-1,-1}
+//   permutation = 4-bit nibbles of {12,7,15,6,11,0,4,9 | 13,3,14,8,2,5,1,10}
+RT_D int perlin_shuffled(int i) {                      // i % 16 folded to [0,16) (src/Perlin.cpp:91-97)
+    unsigned k = (unsigned)i & 15u;
+    unsigned w = (k & 8u) ? 0xa1528e3du : 0x940b6f7cu;
+    return (int)((w >> ((k & 7u) * 4u)) & 15u);
+}
+RT_D float3 perlin_grad(int idx) {
+    // 2-bit codes: 0 -> -1, 1 -> 0, 2 -> +1
+    unsigned sh = (unsigned)idx * 2u;
+    const unsigned X = 0x52552222u, Y = 0xa22550au, Z = 0x250a0a55u;
+    return v3((float)((int)((X >> sh) & 3u) - 1), (float)((int)((Y >> sh) & 3u) - 1), (float)((int)((Z >> sh) & 3u) - 1));
+}
 RT_D float perlin_weight(float x) {
     x = fabsf(x);
     float x3 = x * x * x;
     return (-6.0f * x3 * x * x) + (15.0f * x3 * x) - (10.0f * x3) + 1.0f;
 }
+// Perlin::ComputePerlin, src/Perlin.cpp:52-84.  Same corner order and the same per-corner arithmetic
+// (dot(g, d) * ((wx*wy)*wz), accumulated i-major, k-minor); only the shared sub-expressions (per-axis weights, the
+// nested permutation lookups) are evaluated once instead of once per corner.
 RT_D float perlin(float3 p, float scale, int nc) {
     float3 pt = p * scale;
     int ii = (int)floorf(pt.x), jj = (int)floorf(pt.y), kk = (int)floorf(pt.z);
+    float dx[2] = {pt.x - (float)ii, pt.x - (float)(ii + 1)}, dy[2] = {pt.y - (float)jj, pt.y - (float)(jj + 1)}, dz[2] = {pt.z - (float)kk, pt.z - (float)(kk + 1)};
+    float wx[2] = {perlin_weight(dx[0]), perlin_weight(dx[1])}, wy[2] = {perlin_weight(dy[0]), perlin_weight(dy[1])}, wz[2] = {perlin_weight(dz[0]), perlin_weight(dz[1])};
+    int pz[2] = {perlin_shuffled(kk), perlin_shuffled(kk + 1)};
     float value = 0.f;
 #pragma unroll
     for (int i = 0; i < 2; i++)
@@ -46,11 +63,9 @@ RT_D float perlin(float3 p, float scale, int nc) {
         for (int j = 0; j < 2; j++)
 #pragma unroll
             for (int k = 0; k < 2; k++) {
-                int lx = ii + i, ly = jj + j, lz = kk + k;
-                int idx = perlin_shuffled(lx + perlin_shuffled(ly + perlin_shuffled(lz)));
-                float3 g = v3(c_perlin_table[idx][0], c_perlin_table[idx][1], c_perlin_table[idx][2]);
-                float3 d = pt - v3((float)lx, (float)ly, (float)lz);
-                value += dot(g, d) * (perlin_weight(d.x) * perlin_weight(d.y) * perlin_weight(d.z));
+                int idx = perlin_shuffled(ii + i + perlin_shuffled(jj + j + pz[k]));
+                float3 g = perlin_grad(idx);
+                value += dot(g, v3(dx[i], dy[j], dz[k])) * (wx[i] * wy[j] * wz[k]);
             }
     if (nc == RT_NC_LINEAR) value = (value + 1.0f) * 0.5f;
     else if (nc == RT_NC_ABSVAL) value = fabsf(value);

@@ -26,6 +26,7 @@ struct TraceIO {
     // shadow outputs
     const float4* c_pixel;
     float* accum;
+    int flags;                 // bit 0: dynamic ray fetch, bit 1: postpone leaves (tuning knobs; results do not depend on them)
 };
 
 RT_D void pt_accum(float* accum, float4 c) {
@@ -44,9 +45,12 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
     const unsigned lt = (1u << lane) - 1u;
     const float eps = sc.int_eps;
 
-    int stack_n[kStackSize];
-    float stack_t[kStackSize];
+    // Traversal stack: (node, t_entry) packed into 64 bits (one LDL.64 / STL.64 per entry) with the TOP entry cached in
+    // registers, so a pop hands out the cached entry and the reload of the next one overlaps the work on the popped node
+    // (ncu r01b: 26 % of the samples sat in the pop loop waiting on two dependent local loads with ~7 lanes active).
+    unsigned long long stack[kStackSize];
     int sp = 0;
+    int top_n = kSentinel; float top_t = 0.f;
     int node = kSentinel, cur_obj = -1, rayidx = -1;
     float3 o = v3(0.f, 0.f, 0.f), d = o, id = o, ood = o, wo = o, wd = o;
     float time = 0.f, tmax = 0.f;
@@ -55,10 +59,20 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
     bool exhausted = false;
     unsigned cnt_nodes = 0, cnt_prims = 0;
 
-#define RT_POP()                                                                                       \
+#define RT_PUSH(N, T)                                                                                  \
     do {                                                                                               \
-        --sp; node = stack_n[sp];                                                                      \
-    } while (node != kSentinel && node != kBlasExit && stack_t[sp] >= tmax)
+        stack[sp++] = ((unsigned long long)__float_as_uint(top_t) << 32) | (unsigned)top_n;            \
+        top_n = (N); top_t = (T);                                                                      \
+    } while (0)
+#define RT_POP()                                                                                       \
+    do { for (;;) {                                                                                    \
+        node = top_n;                                                                                  \
+        if (node == kSentinel) break;                                                                  \
+        float tt_ = top_t;                                                                             \
+        unsigned long long e_ = stack[--sp];                                                           \
+        top_n = (int)(unsigned)e_; top_t = __uint_as_float((unsigned)(e_ >> 32));                      \
+        if (node == kBlasExit || tt_ < tmax) break;                                                    \
+    } } while (0)
 
     while (true) {
         // ---------------- retire finished rays, fetch new ones
@@ -82,8 +96,8 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
                 if (any_nan(wo) || any_nan(wd)) { node = kSentinel; if (!ANY_HIT) tmax = 0.f; }   // src/Helper.cpp:28-30: NaN ray = no hit
                 else {
                     o = wo; d = wd; id = safe_rcp(d); ood = v3(o.x * id.x, o.y * id.y, o.z * id.z);
-                    sp = 0; stack_n[sp] = kSentinel; stack_t[sp] = 0.f; sp++;
-                    node = sc.tlas_root; cur_obj = -1;
+                    sp = 0; top_n = kSentinel; top_t = 0.f;
+                    node = sc.tlas_root4; cur_obj = -1;
                 }
             }
         }
@@ -100,25 +114,47 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
                     cur_obj = -1;
                     RT_POP();
                 } else if (node >= 0) {
+                    // 4-wide inner node: one 128-byte line, four independent slab tests
                     if (COUNT) ++cnt_nodes;
-                    const float4* np = sc.nodes + (size_t)node * 4;
-                    float4 q0 = ldg4(np), q1 = ldg4(np + 1), q2 = ldg4(np + 2), q3 = ldg4(np + 3);
-                    float c0lox = q0.x * id.x - ood.x, c0hix = q0.y * id.x - ood.x, c0loy = q0.z * id.y - ood.y, c0hiy = q0.w * id.y - ood.y;
-                    float c1lox = q1.x * id.x - ood.x, c1hix = q1.y * id.x - ood.x, c1loy = q1.z * id.y - ood.y, c1hiy = q1.w * id.y - ood.y;
-                    float c0loz = q2.x * id.z - ood.z, c0hiz = q2.y * id.z - ood.z, c1loz = q2.z * id.z - ood.z, c1hiz = q2.w * id.z - ood.z;
-                    float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.f));
-                    float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tmax));
-                    float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.f));
-                    float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tmax));
-                    int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
-                    bool h0 = (t0n <= t0f) && c0 != kNoChildDev, h1 = (t1n <= t1f) && c1 != kNoChildDev;
-                    if (h0 && h1) {
-                        bool swap = t1n < t0n;
-                        stack_n[sp] = swap ? c0 : c1; stack_t[sp] = swap ? t0n : t1n; sp++;
-                        node = swap ? c1 : c0;
-                    } else if (h0) node = c0;
-                    else if (h1) node = c1;
-                    else RT_POP();
+                    const float4* np = sc.nodes4 + (size_t)node * 8;
+                    float4 lx = ldg4(np), hx = ldg4(np + 1), ly = ldg4(np + 2), hy = ldg4(np + 3), lz = ldg4(np + 4), hz = ldg4(np + 5), cr = ldg4(np + 6);
+                    float tn[4]; int rf[4];
+#define RT_SLAB(K, C)                                                                                                                   \
+                    {                                                                                                                   \
+                        float ax = lx.C * id.x - ood.x, bx = hx.C * id.x - ood.x, ay = ly.C * id.y - ood.y, by = hy.C * id.y - ood.y;      \
+                        float az = lz.C * id.z - ood.z, bz = hz.C * id.z - ood.z;                                                        \
+                        float n_ = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));                               \
+                        float f_ = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));                              \
+                        rf[K] = __float_as_int(cr.C);                                                                                   \
+                        tn[K] = (n_ <= f_ && rf[K] != kNoChildDev) ? n_ : 3.0e38f;                                                      \
+                    }
+                    RT_SLAB(0, x) RT_SLAB(1, y) RT_SLAB(2, z) RT_SLAB(3, w)
+#undef RT_SLAB
+                    int nh = (tn[0] < 3.0e38f) + (tn[1] < 3.0e38f) + (tn[2] < 3.0e38f) + (tn[3] < 3.0e38f);
+                    if (nh == 0) RT_POP();
+                    else {
+                        if (ANY_HIT) {
+                            // occlusion query: visiting order is irrelevant for the result; push every hit child but one
+                            int keep = 0; bool have = false;   // (leaf refs are negative: track "have one" separately)
+#pragma unroll
+                            for (int k = 3; k >= 0; k--) {
+                                if (tn[k] < 3.0e38f) {
+                                    if (have) RT_PUSH(keep, 0.f);
+                                    keep = rf[k]; have = true;
+                                }
+                            }
+                            rf[0] = keep;
+                        } else if (nh > 1 || tn[0] >= 3.0e38f) {
+                            // sort ascending by entry distance (5-comparator network); misses (3e38) sink to the end
+#define RT_CSWAP(A, B) { bool s_ = tn[B] < tn[A]; float ta_ = s_ ? tn[B] : tn[A], tb_ = s_ ? tn[A] : tn[B]; int ra_ = s_ ? rf[B] : rf[A], rb_ = s_ ? rf[A] : rf[B]; tn[A] = ta_; tn[B] = tb_; rf[A] = ra_; rf[B] = rb_; }
+                            RT_CSWAP(0, 1) RT_CSWAP(2, 3) RT_CSWAP(0, 2) RT_CSWAP(1, 3) RT_CSWAP(1, 2)
+#undef RT_CSWAP
+                            if (nh > 3) RT_PUSH(rf[3], tn[3]);
+                            if (nh > 2) RT_PUSH(rf[2], tn[2]);
+                            if (nh > 1) RT_PUSH(rf[1], tn[1]);
+                        }
+                        node = rf[0];
+                    }
                 } else if (cur_obj < 0) {
                     // TLAS leaf: one top-level entry
                     int obj = (~node) >> 3;
@@ -135,16 +171,17 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
                     } else {
                         o = oo; d = od; id = safe_rcp(d); ood = v3(o.x * id.x, o.y * id.y, o.z * id.z);
                         cur_obj = obj;
-                        stack_n[sp] = kBlasExit; stack_t[sp] = -1.f; sp++;
-                        node = root;
+                        RT_PUSH(kBlasExit, -1.f);
+                        node = __ldg(sc.obj_root4 + obj);
                     }
                 } else {
                     // triangle leaf: postpone the first one, stop at the second
                     if (leaf < 0) break;
                     leaf = node; searching = false;
                     RT_POP();
+                    if (!(io.flags & 2)) break;
                 }
-                if (!__any_sync(__activemask(), searching)) break;
+                if ((io.flags & 2) && !__any_sync(__activemask(), searching)) break;
             }
             // ---------------- postponed leaves
             while (leaf < 0) {
@@ -164,10 +201,11 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
                 if (ANY_HIT && done) { node = kSentinel; break; }
                 if (node < 0 && cur_obj >= 0) { leaf = node; RT_POP(); }   // a second leaf was reached while the first was pending
             }
-            if (!exhausted && __popc(__activemask()) < kFetchThreshold) break;
+            if ((io.flags & 1) && !exhausted && __popc(__activemask()) < kFetchThreshold) break;
         }
     }
 #undef RT_POP
+#undef RT_PUSH
     if (COUNT) {
         atomicAdd(ANY_HIT ? &ctr->node_visits_shadow : &ctr->node_visits, (unsigned long long)cnt_nodes);
         atomicAdd(ANY_HIT ? &ctr->prim_tests_shadow : &ctr->prim_tests, (unsigned long long)cnt_prims);
