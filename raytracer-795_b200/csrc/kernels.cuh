@@ -144,8 +144,11 @@ RT_D void write_ray(const DRayQueue& q, int slot, uint32_t pixel, const RayOut& 
     q.meta[slot] = make_int4(r.sample, r.meta, r.node, __float_as_int(r.beer_s));
 }
 
+#ifndef RT795_SHADE_MIN_BLOCKS
+#define RT795_SHADE_MIN_BLOCKS 5
+#endif
 template <int INTEGRATOR>
-__global__ void __launch_bounds__(kBlock) k_shade(DScene sc, DCamera cam, RenderConsts rc, DRayQueue in, int first, int count, DRayQueue out, DShadowQueue sq,
+__global__ void __launch_bounds__(kBlock, RT795_SHADE_MIN_BLOCKS) k_shade(DScene sc, DCamera cam, RenderConsts rc, DRayQueue in, int first, int count, DRayQueue out, DShadowQueue sq,
                                                   DCounters* ctr, float* accum) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool active = i < count;

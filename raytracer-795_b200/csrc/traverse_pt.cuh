@@ -13,7 +13,7 @@
 
 namespace rt795 {
 
-constexpr int kFetchThreshold = 20;
+constexpr int kFetchThreshold = 20;   // default; TraceIO.flags bits 8..15 override (tuning)
 
 struct TraceIO {
     const float4* o_time;      // ray queue (read)
@@ -51,14 +51,21 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
     unsigned long long stack[kStackSize];
     int sp = 0;
     int top_n = kSentinel; float top_t = 0.f;
+    int sgx = 0, sgy = 0, sgz = 0;   // 1 where the current (world or object space) direction component is negative
     int node = kSentinel, cur_obj = -1, rayidx = -1;
     float3 o = v3(0.f, 0.f, 0.f), d = o, id = o, ood = o, wo = o, wd = o;
     float time = 0.f, tmax = 0.f;
     float hb = 0.f, hg = 0.f;
     int hprim = -1, hobj = -1;
     bool exhausted = false;
+    const int fetch_threshold = (io.flags >> 8) & 0xff ? (io.flags >> 8) & 0xff : kFetchThreshold;
     unsigned cnt_nodes = 0, cnt_prims = 0;
 
+#define RT_SET_RAY(O, D)                                                                               \
+    do {                                                                                               \
+        o = (O); d = (D); id = safe_rcp(d); ood = v3(o.x * id.x, o.y * id.y, o.z * id.z);              \
+        sgx = id.x < 0.f; sgy = id.y < 0.f; sgz = id.z < 0.f;                                          \
+    } while (0)
 #define RT_PUSH(N, T)                                                                                  \
     do {                                                                                               \
         stack[sp++] = ((unsigned long long)__float_as_uint(top_t) << 32) | (unsigned)top_n;            \
@@ -95,7 +102,7 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
                 hprim = -1; hobj = -1; hb = hg = 0.f;
                 if (any_nan(wo) || any_nan(wd)) { node = kSentinel; if (!ANY_HIT) tmax = 0.f; }   // src/Helper.cpp:28-30: NaN ray = no hit
                 else {
-                    o = wo; d = wd; id = safe_rcp(d); ood = v3(o.x * id.x, o.y * id.y, o.z * id.z);
+                    RT_SET_RAY(wo, wd);
                     sp = 0; top_n = kSentinel; top_t = 0.f;
                     node = sc.tlas_root4; cur_obj = -1;
                 }
@@ -110,21 +117,23 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
                 if (node == kSentinel) break;
                 if (node == kBlasExit) {
                     if (leaf < 0) break;   // the pending leaf lives in this instance's object space: test it before leaving
-                    o = wo; d = wd; id = safe_rcp(d); ood = v3(o.x * id.x, o.y * id.y, o.z * id.z);
+                    RT_SET_RAY(wo, wd);
                     cur_obj = -1;
                     RT_POP();
                 } else if (node >= 0) {
                     // 4-wide inner node: one 128-byte line, four independent slab tests
                     if (COUNT) ++cnt_nodes;
                     const float4* np = sc.nodes4 + (size_t)node * 8;
-                    float4 lx = ldg4(np), hx = ldg4(np + 1), ly = ldg4(np + 2), hy = ldg4(np + 3), lz = ldg4(np + 4), hz = ldg4(np + 5), cr = ldg4(np + 6);
+                    // near / far planes are picked by the ray's direction signs through the LOAD ADDRESS (lo and hi of an axis are
+                    // adjacent float4s of the same 128-byte line), so no min/max per axis is needed: 6 FMA + 2 three-input min/max
+                    // + 2 clamps per child instead of 6 FMA + 10 min/max (the ALU pipe is the busiest pipe of this kernel, ncu r01c).
+                    float4 nx4 = ldg4(np + sgx), fx4 = ldg4(np + (1 - sgx)), ny4 = ldg4(np + 2 + sgy), fy4 = ldg4(np + (3 - sgy));
+                    float4 nz4 = ldg4(np + 4 + sgz), fz4 = ldg4(np + (5 - sgz)), cr = ldg4(np + 6);
                     float tn[4]; int rf[4];
 #define RT_SLAB(K, C)                                                                                                                   \
                     {                                                                                                                   \
-                        float ax = lx.C * id.x - ood.x, bx = hx.C * id.x - ood.x, ay = ly.C * id.y - ood.y, by = hy.C * id.y - ood.y;      \
-                        float az = lz.C * id.z - ood.z, bz = hz.C * id.z - ood.z;                                                        \
-                        float n_ = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));                               \
-                        float f_ = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));                              \
+                        float n_ = fmaxf(fmaxf(nx4.C * id.x - ood.x, ny4.C * id.y - ood.y), fmaxf(nz4.C * id.z - ood.z, 0.f));             \
+                        float f_ = fminf(fminf(fx4.C * id.x - ood.x, fy4.C * id.y - ood.y), fminf(fz4.C * id.z - ood.z, tmax));            \
                         rf[K] = __float_as_int(cr.C);                                                                                   \
                         tn[K] = (n_ <= f_ && rf[K] != kNoChildDev) ? n_ : 3.0e38f;                                                      \
                     }
@@ -135,14 +144,11 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
                     else {
                         if (ANY_HIT) {
                             // occlusion query: visiting order is irrelevant for the result; push every hit child but one
-                            int keep = 0; bool have = false;   // (leaf refs are negative: track "have one" separately)
-#pragma unroll
-                            for (int k = 3; k >= 0; k--) {
-                                if (tn[k] < 3.0e38f) {
-                                    if (have) RT_PUSH(keep, 0.f);
-                                    keep = rf[k]; have = true;
-                                }
-                            }
+                            bool h0 = tn[0] < 3.0e38f, h1 = tn[1] < 3.0e38f, h2 = tn[2] < 3.0e38f, h3 = tn[3] < 3.0e38f;
+                            if (h3 && (h0 || h1 || h2)) RT_PUSH(rf[3], 0.f);
+                            if (h2 && (h0 || h1)) RT_PUSH(rf[2], 0.f);
+                            if (h1 && h0) RT_PUSH(rf[1], 0.f);
+                            int keep = h0 ? rf[0] : (h1 ? rf[1] : (h2 ? rf[2] : rf[3]));
                             rf[0] = keep;
                         } else if (nh > 1 || tn[0] >= 3.0e38f) {
                             // sort ascending by entry distance (5-comparator network); misses (3e38) sink to the end
@@ -169,7 +175,7 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
                         }
                         RT_POP();
                     } else {
-                        o = oo; d = od; id = safe_rcp(d); ood = v3(o.x * id.x, o.y * id.y, o.z * id.z);
+                        RT_SET_RAY(oo, od);
                         cur_obj = obj;
                         RT_PUSH(kBlasExit, -1.f);
                         node = __ldg(sc.obj_root4 + obj);
@@ -201,11 +207,12 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
                 if (ANY_HIT && done) { node = kSentinel; break; }
                 if (node < 0 && cur_obj >= 0) { leaf = node; RT_POP(); }   // a second leaf was reached while the first was pending
             }
-            if ((io.flags & 1) && !exhausted && __popc(__activemask()) < kFetchThreshold) break;
+            if ((io.flags & 1) && !exhausted && __popc(__activemask()) < fetch_threshold) break;
         }
     }
 #undef RT_POP
 #undef RT_PUSH
+#undef RT_SET_RAY
     if (COUNT) {
         atomicAdd(ANY_HIT ? &ctr->node_visits_shadow : &ctr->node_visits, (unsigned long long)cnt_nodes);
         atomicAdd(ANY_HIT ? &ctr->prim_tests_shadow : &ctr->prim_tests, (unsigned long long)cnt_prims);
