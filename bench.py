@@ -292,7 +292,7 @@ def run_ours(args, rt):
     achieved = ext_rays * b_ray / (st.ms_extend * 1e-3) / 1e9 if st.ms_extend > 0 else 0.0
     stage = {"ms_extend": st.ms_extend, "ms_shade": st.ms_shade, "ms_shadow": st.ms_shadow, "ms_raygen": st.ms_raygen, "ms_resolve": st.ms_resolve,
              "launches_extend": int(st.launches_extend), "launches_shadow": int(st.launches_shadow)}
-    roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.config),
+    roofline = {"bound": "hbm", "kernel": "k_trace_persistent<closest-hit> (K2 extend)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.config),
                 "peak_source": peak_src, "algorithmic_bytes_per_ray": b_ray, "rays_per_launch": ext_rays / max(1, int(st.launches_extend)),
                 "avg_launch_ms": st.ms_extend / max(1, int(st.launches_extend)), "stage_ms": stage,
                 "note": "scene (tris+BVH) fits the 126 MB L2, so the HBM roofline is a reference line, not the binding limit; see DESIGN.md"}
