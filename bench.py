@@ -206,10 +206,14 @@ def run_ours(args, rt):
     full_kw, sample_kw = WORKLOADS[args.config]
     if args.small:
         full_kw = sample_kw
+    tag = "small" if args.small else "full"
+    if args.spp > 0 and "spp" in full_kw:
+        full_kw = dict(full_kw, spp=args.spp)
+        tag += f"_spp{args.spp}"
     if rank == 0:
-        xml = make_scene(rt, args.config, full_kw, "small" if args.small else "full")
+        xml = make_scene(rt, args.config, full_kw, tag)
     barrier()
-    xml = make_scene(rt, args.config, full_kw, "small" if args.small else "full")
+    xml = make_scene(rt, args.config, full_kw, tag)
     hs = rt.HostScene(xml)
     cam = hs.camera(0)
     sc = rt.Scene(hs.desc, local)
@@ -309,7 +313,7 @@ def run_ours(args, rt):
     if rank == 0:
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": rt.scenes.CONFIGS[args.config]["label"] + (" [--small sample]" if args.small else ""),
+                "config": {"workload": rt.scenes.CONFIGS[args.config]["label"] + (" [--small sample]" if args.small else "") + (f" [--spp {args.spp}]" if args.spp else ""),
                            "resolution": [cam.nx, cam.ny], "spp": cam.num_samples, "rays_per_frame": {"primary": rays[0], "secondary": rays[1], "shadow": rays[2]},
                            "integrator": "path" if integrator else "reference", "parallelism": f"tiles16x16-interleaved-x{world}", "l2": "flushed between steps (256 MB write)",
                            "scene_bytes": {"bvh": int(sstats.bvh_bytes), "triangles": int(sstats.tri_bytes)}, "bvh_build_ms": sstats.ms_bvh_build},
@@ -331,6 +335,7 @@ def main():
     ap.add_argument("--config", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--small", action="store_true", help="use the bounded sample configuration (smoke runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel of the workload (exploration; the headline run uses the configuration's own)")
     args = ap.parse_args()
     rt = ge.load_package()
     if args.impl == "reference":
