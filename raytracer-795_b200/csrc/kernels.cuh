@@ -158,6 +158,8 @@ __global__ void __launch_bounds__(kBlock, RT795_SHADE_MIN_BLOCKS) k_shade(DScene
     int n_out = 0;
     RayOut r0, r1;
     bool lit = false;                 // evaluate lights at this hit
+    float3 pend = v3(0.f, 0.f, 0.f);  // this lane's direct accumulate (background / replace_all / ambient / emission), added warp-aggregated below
+    bool has_pend = false;
     Surface s;
     RtMaterial mat;
     float3 W = v3(0.f, 0.f, 0.f), rd = W;
@@ -192,12 +194,12 @@ __global__ void __launch_bounds__(kBlock, RT795_SHADE_MIN_BLOCKS) k_shade(DScene
                 }   // miss / TIR: indeterminate in the reference; defined as distance 0 here and in the oracle
             }
             if (h.prim < 0) {
-                if (flags & RAY_PRIMARY) accum_add(accum, pixel, W * background(sc, cam, pixel, rd));   // secondary miss = black (src/Scene.cpp:150-153)
+                if (flags & RAY_PRIMARY) { pend = W * background(sc, cam, pixel, rd); has_pend = true; }   // secondary miss = black (src/Scene.cpp:150-153)
             } else {
                 s = eval_surface(sc, ro, rd, rtime, h);
                 mat = sc.materials[s.mat_index - 1];
                 if ((flags & RAY_PRIMARY) && s.dm == RT_DM_REPLACE_ALL) {                              // Scene::Shading, src/Scene.cpp:232-234
-                    accum_add(accum, pixel, W * s.tex_color);
+                    pend = W * s.tex_color; has_pend = true;
                 } else {
                     const float eps = sc.shadow_eps;
                     auto reflect_ray = [&](float3 weight, uint32_t fl, int bmat, float bs) {            // MirrorReflectance, src/Scene.cpp:32-55
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(kBlock, RT795_SHADE_MIN_BLOCKS) k_shade(DScene
                             if (okr) { r1 = reflect_ray(wr, RAY_BEER_SIBLING, s.mat_index, tr.beer_s); n_out = 2; }
                         }
                     }
-                    if (lit) accum_add(accum, pixel, W * (v3(sc.ambient) * v3(mat.ambient)));          // Scene::ambient, src/Scene.cpp:22-30
+                    if (lit) { pend = W * (v3(sc.ambient) * v3(mat.ambient)); has_pend = true; }       // Scene::ambient, src/Scene.cpp:22-30
                 }
             }
         } else {
@@ -274,12 +276,12 @@ __global__ void __launch_bounds__(kBlock, RT795_SHADE_MIN_BLOCKS) k_shade(DScene
             bool count_emission = (flags & RAY_SPECULAR) != 0;
             int max_depth = rc.pt_max_depth;
             if (h.prim < 0) {
-                if (node == 1u || (sc.env_light != -1 && (count_emission || !rc.pt_nee))) accum_add(accum, pixel, W * background(sc, cam, pixel, rd));
+                if (node == 1u || (sc.env_light != -1 && (count_emission || !rc.pt_nee))) { pend = W * background(sc, cam, pixel, rd); has_pend = true; }
             } else {
                 s = eval_surface(sc, ro, rd, rtime, h);
                 mat = sc.materials[s.mat_index - 1];
                 float3 Le = v3(mat.emission);
-                if ((Le.x > 0.f || Le.y > 0.f || Le.z > 0.f) && (count_emission || !rc.pt_nee) && dot(s.N, rd) < 0.f) accum_add(accum, pixel, W * Le);
+                if ((Le.x > 0.f || Le.y > 0.f || Le.z > 0.f) && (count_emission || !rc.pt_nee) && dot(s.N, rd) < 0.f) { pend = W * Le; has_pend = true; }
                 if ((int)node < max_depth + 1) {
                     const float eps = sc.shadow_eps;
                     float3 n = s.N;
@@ -351,6 +353,7 @@ __global__ void __launch_bounds__(kBlock, RT795_SHADE_MIN_BLOCKS) k_shade(DScene
         }
     }
 
+    warp_accum(accum, has_pend, pixel, pend);
     // ---- continuation rays -> next queue (pairs stay adjacent: slot, slot+1)
     {
         int total;

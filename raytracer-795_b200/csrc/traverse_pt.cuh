@@ -9,6 +9,7 @@
 // cursor as soon as fewer than kFetchThreshold lanes are still busy.
 // Semantics are exactly those of traverse.cuh (same box / triangle / sphere tests, same hit record).
 #pragma once
+#include "shade.cuh"
 #include "traverse.cuh"
 
 namespace rt795 {
@@ -84,9 +85,14 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
     while (true) {
         // ---------------- retire finished rays, fetch new ones
         bool idle = node == kSentinel;
-        if (idle && rayidx >= 0) {
-            if (ANY_HIT) { if (hprim < 0) pt_accum(io.accum, __ldg(io.c_pixel + rayidx)); }
-            else { io.hit[rayidx] = make_float4(tmax, hb, hg, __int_as_float(hprim)); io.hit_obj[rayidx] = hobj; }
+        if (ANY_HIT) {
+            bool add = idle && rayidx >= 0 && hprim < 0;   // unoccluded: the light's contribution reaches the pixel
+            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (add) c = __ldg(io.c_pixel + rayidx);
+            warp_accum(io.accum, add, (uint32_t)__float_as_int(c.w), v3(c));
+            if (idle) rayidx = -1;
+        } else if (idle && rayidx >= 0) {
+            io.hit[rayidx] = make_float4(tmax, hb, hg, __int_as_float(hprim)); io.hit_obj[rayidx] = hobj;
             rayidx = -1;
         }
         unsigned m = __ballot_sync(full, idle);
