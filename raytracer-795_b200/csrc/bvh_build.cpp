@@ -2,8 +2,10 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <thread>
 
 namespace rt795 {
 namespace {
@@ -22,28 +24,28 @@ struct Tmp {
 struct Builder {
     const Aabb* pb;
     std::vector<int32_t>& order;
-    std::vector<float> cen;       // centroids, 3 per primitive
+    std::vector<float> cen_own;            // centroids, 3 per primitive (owned by the root builder)
+    const std::vector<float>* cen_ref = nullptr;
+    const std::vector<float>& cen;         // centroids as seen by this (sub-)builder
     std::vector<Tmp> tmp;
     int max_leaf;
     int max_depth = 0;
 
-    Builder(const Aabb* b, int n, int ml, std::vector<int32_t>& ord) : pb(b), order(ord), max_leaf(ml) {
-        cen.resize((size_t)n * 3);
+    Builder(const Aabb* b, int n, int ml, std::vector<int32_t>& ord) : pb(b), order(ord), cen(cen_own), max_leaf(ml) {
+        cen_own.resize((size_t)n * 3);
         for (int i = 0; i < n; i++)
-            for (int k = 0; k < 3; k++) cen[(size_t)i * 3 + k] = 0.5f * (b[i].lo[k] + b[i].hi[k]);
+            for (int k = 0; k < 3; k++) cen_own[(size_t)i * 3 + k] = 0.5f * (b[i].lo[k] + b[i].hi[k]);
+        cen_ref = &cen_own;
     }
 
-    int Build(int first, int count, int depth) {
-        max_depth = std::max(max_depth, depth);
-        int me = (int)tmp.size();
-        tmp.emplace_back();
+    // Decides what to do with primitives [first, first+count): returns -1 for "make a leaf", else the split position
+    // (the range is partitioned in place).  Fills the node box.
+    int Split(int first, int count, int depth, Aabb* box_out) {
         Aabb box, cbox;
         box.Reset(); cbox.Reset();
         for (int i = first; i < first + count; i++) { box.Grow(pb[order[i]]); cbox.Grow(&cen[(size_t)order[i] * 3]); }
-        tmp[me].box = box;
-        auto make_leaf = [&]() { tmp[me].leaf = true; tmp[me].first = first; tmp[me].count = count; return me; };
-        if (count <= 1) return make_leaf();
-
+        *box_out = box;
+        if (count <= 1) return -1;
         int mid = -1;
         if (depth < kMaxDepth) {
             // binned SAH over the three axes
@@ -75,7 +77,7 @@ struct Builder {
             float area = box.HalfArea();
             float leaf_cost = kIntersectCost * count;
             float split_cost = best_axis >= 0 && area > 0 ? kTraversalCost + kIntersectCost * best_cost / area : std::numeric_limits<float>::max();
-            if (count <= max_leaf && leaf_cost <= split_cost) return make_leaf();
+            if (count <= max_leaf && leaf_cost <= split_cost) return -1;
             if (best_axis >= 0) {
                 float lo = cbox.lo[best_axis], scale = kBins / (cbox.hi[best_axis] - lo);
                 auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](int32_t p) {
@@ -87,7 +89,7 @@ struct Builder {
             }
         }
         if (mid < 0) {
-            if (count <= max_leaf) return make_leaf();
+            if (count <= max_leaf) return -1;
             // centroids coincide (or depth cap reached): median split along the widest box axis
             int axis = 0;
             float e0 = box.hi[0] - box.lo[0], e1 = box.hi[1] - box.lo[1], e2 = box.hi[2] - box.lo[2];
@@ -96,11 +98,42 @@ struct Builder {
             std::nth_element(order.begin() + first, order.begin() + mid, order.begin() + first + count,
                              [&](int32_t a, int32_t b) { return cen[(size_t)a * 3 + axis] < cen[(size_t)b * 3 + axis]; });
         }
-        int l = Build(first, mid - first, depth + 1);
-        int r = Build(mid, first + count - mid, depth + 1);
+        return mid;
+    }
+
+    // `par` > 0: the two halves of a large range are built by separate threads into private node vectors and stitched in
+    // (the tree does not depend on the thread count: every split is a function of its range only).
+    int Build(int first, int count, int depth, int par = 0) {
+        max_depth = std::max(max_depth, depth);
+        int me = (int)tmp.size();
+        tmp.emplace_back();
+        Aabb box;
+        int mid = Split(first, count, depth, &box);
+        tmp[me].box = box;
+        if (mid < 0) { tmp[me].leaf = true; tmp[me].first = first; tmp[me].count = count; return me; }
+        if (par > 0 && count >= 32768) {
+            Builder lb(*this, Shared()), rb(*this, Shared());
+            int lroot = 0, rroot = 0;
+            std::thread tl([&] { lroot = lb.Build(first, mid - first, depth + 1, par - 1); });
+            rroot = rb.Build(mid, first + count - mid, depth + 1, par - 1);
+            tl.join();
+            auto stitch = [&](Builder& sb, int root) {
+                int off = (int)tmp.size();
+                for (Tmp t : sb.tmp) { if (t.left >= 0) t.left += off; if (t.right >= 0) t.right += off; tmp.push_back(t); }
+                max_depth = std::max(max_depth, sb.max_depth);
+                return root + off;
+            };
+            int l = stitch(lb, lroot), r = stitch(rb, rroot);
+            tmp[me].left = l; tmp[me].right = r;
+            return me;
+        }
+        int l = Build(first, mid - first, depth + 1, 0);
+        int r = Build(mid, first + count - mid, depth + 1, 0);
         tmp[me].left = l; tmp[me].right = r;
         return me;
     }
+    struct Shared {};
+    Builder(const Builder& o, Shared) : pb(o.pb), order(o.order), cen_ref(o.cen_ref), cen(o.cen_ref ? *o.cen_ref : o.cen_own), max_leaf(o.max_leaf) {}
 };
 
 void PutChild(BvhNode64& n, int slot, const Aabb* box, int32_t child) {
@@ -127,7 +160,10 @@ void BuildSahBvh(const Aabb* prim_bounds, int n, int max_leaf, BuiltBvh* out) {
     }
     Builder b(prim_bounds, n, std::min(8, std::max(1, max_leaf)), out->order);
     b.tmp.reserve((size_t)n);
-    int root = b.Build(0, n, 0);
+    unsigned hw = std::thread::hardware_concurrency();
+    int par = hw >= 16 ? 4 : hw >= 8 ? 3 : hw >= 4 ? 2 : hw >= 2 ? 1 : 0;   // 2^par concurrent subtree builds
+    if (const char* e = getenv("RT795_BVH_PAR")) par = atoi(e);             // 0 = single-threaded (same tree either way)
+    int root = b.Build(0, n, 0, par);
     out->bounds = b.tmp[root].box;
     out->max_depth = b.max_depth;
 
