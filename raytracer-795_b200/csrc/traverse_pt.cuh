@@ -72,6 +72,14 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
         stack[sp++] = ((unsigned long long)__float_as_uint(top_t) << 32) | (unsigned)top_n;            \
         top_n = (N); top_t = (T);                                                                      \
     } while (0)
+#define RT_POP1()                                                                                      \
+    do {                                                                                               \
+        node = top_n;                                                                                  \
+        if (node != kSentinel) {                                                                       \
+            unsigned long long e_ = stack[--sp];                                                       \
+            top_n = (int)(unsigned)e_; top_t = __uint_as_float((unsigned)(e_ >> 32));                  \
+        }                                                                                              \
+    } while (0)
 #define RT_POP()                                                                                       \
     do { for (;;) {                                                                                    \
         node = top_n;                                                                                  \
@@ -145,27 +153,30 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
                     }
                     RT_SLAB(0, x) RT_SLAB(1, y) RT_SLAB(2, z) RT_SLAB(3, w)
 #undef RT_SLAB
-                    int nh = (tn[0] < 3.0e38f) + (tn[1] < 3.0e38f) + (tn[2] < 3.0e38f) + (tn[3] < 3.0e38f);
-                    if (nh == 0) RT_POP();
-                    else {
-                        if (ANY_HIT) {
-                            // occlusion query: visiting order is irrelevant for the result; push every hit child but one
-                            bool h0 = tn[0] < 3.0e38f, h1 = tn[1] < 3.0e38f, h2 = tn[2] < 3.0e38f, h3 = tn[3] < 3.0e38f;
-                            if (h3 && (h0 || h1 || h2)) RT_PUSH(rf[3], 0.f);
-                            if (h2 && (h0 || h1)) RT_PUSH(rf[2], 0.f);
-                            if (h1 && h0) RT_PUSH(rf[1], 0.f);
-                            int keep = h0 ? rf[0] : (h1 ? rf[1] : (h2 ? rf[2] : rf[3]));
-                            rf[0] = keep;
-                        } else if (nh > 1 || tn[0] >= 3.0e38f) {
-                            // sort ascending by entry distance (5-comparator network); misses (3e38) sink to the end
+                    if (ANY_HIT) {
+                        // occlusion query: visiting order cannot change the answer and stack entries are never culled (t = 0), so
+                        // the whole step is straight-line: predicated pushes of all hit children but one, else one pop.
+                        bool h0 = tn[0] < 3.0e38f, h1 = tn[1] < 3.0e38f, h2 = tn[2] < 3.0e38f, h3 = tn[3] < 3.0e38f;
+                        if (h3 && (h0 || h1 || h2)) RT_PUSH(rf[3], 0.f);
+                        if (h2 && (h0 || h1)) RT_PUSH(rf[2], 0.f);
+                        if (h1 && h0) RT_PUSH(rf[1], 0.f);
+                        if (h0 || h1 || h2 || h3) node = h0 ? rf[0] : (h1 ? rf[1] : (h2 ? rf[2] : rf[3]));
+                        else RT_POP1();
+                    } else {
+                        int nh = (tn[0] < 3.0e38f) + (tn[1] < 3.0e38f) + (tn[2] < 3.0e38f) + (tn[3] < 3.0e38f);
+                        if (nh == 0) RT_POP();
+                        else {
+                            if (nh > 1 || tn[0] >= 3.0e38f) {
+                                // sort ascending by entry distance (5-comparator network); misses (3e38) sink to the end
 #define RT_CSWAP(A, B) { bool s_ = tn[B] < tn[A]; float ta_ = s_ ? tn[B] : tn[A], tb_ = s_ ? tn[A] : tn[B]; int ra_ = s_ ? rf[B] : rf[A], rb_ = s_ ? rf[A] : rf[B]; tn[A] = ta_; tn[B] = tb_; rf[A] = ra_; rf[B] = rb_; }
-                            RT_CSWAP(0, 1) RT_CSWAP(2, 3) RT_CSWAP(0, 2) RT_CSWAP(1, 3) RT_CSWAP(1, 2)
+                                RT_CSWAP(0, 1) RT_CSWAP(2, 3) RT_CSWAP(0, 2) RT_CSWAP(1, 3) RT_CSWAP(1, 2)
 #undef RT_CSWAP
-                            if (nh > 3) RT_PUSH(rf[3], tn[3]);
-                            if (nh > 2) RT_PUSH(rf[2], tn[2]);
-                            if (nh > 1) RT_PUSH(rf[1], tn[1]);
+                                if (nh > 3) RT_PUSH(rf[3], tn[3]);
+                                if (nh > 2) RT_PUSH(rf[2], tn[2]);
+                                if (nh > 1) RT_PUSH(rf[1], tn[1]);
+                            }
+                            node = rf[0];
                         }
-                        node = rf[0];
                     }
                 } else if (cur_obj < 0) {
                     // TLAS leaf: one top-level entry
@@ -217,6 +228,7 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
         }
     }
 #undef RT_POP
+#undef RT_POP1
 #undef RT_PUSH
 #undef RT_SET_RAY
     if (COUNT) {

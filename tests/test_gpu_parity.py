@@ -346,3 +346,57 @@ def test_direct_lighting_is_linear_in_light_intensity(rt, scene_dir):
     assert np.allclose(dbl - amb_img, 2.0 * (base - amb_img), rtol=2e-4, atol=2e-3)
     for x in (sc, sc2, sc3, hs):
         x.close()
+
+
+def test_many_lights_chunking_and_levels(rt, scene_dir):
+    """More than 8 lights: the shadow queue can no longer take a whole level at once, so levels are processed in chunks
+    and every depth gets its own queue buffers (core.cu ProcessLevel); result must still equal the oracle."""
+    d = os.path.join(scene_dir, "manylights")
+    os.makedirs(d, exist_ok=True)
+    lights = "".join(f'<PointLight id="{i + 1}"><Position>{-6 + 1.2 * i} {6 + (i % 3)} {4 - 0.7 * i}</Position><Intensity>{300 + 40 * i} {320 + 10 * i} {280 + 25 * i}</Intensity></PointLight>'
+                     for i in range(11))
+    xml = f"""<Scene><MaxRecursionDepth>3</MaxRecursionDepth><BackgroundColor>2 3 4</BackgroundColor><ShadowRayEpsilon>1e-3</ShadowRayEpsilon><IntersectionTestEpsilon>1e-6</IntersectionTestEpsilon>
+<Cameras><Camera id="1"><Position>0 3 9</Position><GazePoint>0 1 0</GazePoint><Up>0 1 0</Up><FovY>50</FovY><NearDistance>1</NearDistance>
+<ImageResolution>96 64</ImageResolution><ImageName>ml.ppm</ImageName></Camera></Cameras>
+<Lights><AmbientLight>5 5 5</AmbientLight>{lights}</Lights>
+<Materials><Material id="1"><AmbientReflectance>1 1 1</AmbientReflectance><DiffuseReflectance>.7 .7 .7</DiffuseReflectance><SpecularReflectance>.3 .3 .3</SpecularReflectance><PhongExponent>20</PhongExponent></Material>
+<Material id="2" type="mirror"><AmbientReflectance>0 0 0</AmbientReflectance><DiffuseReflectance>.1 .1 .1</DiffuseReflectance><SpecularReflectance>.2 .2 .2</SpecularReflectance><MirrorReflectance>.8 .8 .8</MirrorReflectance></Material></Materials>
+<VertexData>-8 0 8  8 0 8  8 0 -8  -8 0 -8  -1.5 1.2 0  1.8 1.0 1</VertexData>
+<Objects><Mesh id="1"><Material>1</Material><Faces>1 2 3 1 3 4</Faces></Mesh>
+<Sphere id="2"><Material>2</Material><Center>5</Center><Radius>1.2</Radius></Sphere><Sphere id="3"><Material>1</Material><Center>6</Center><Radius>1.0</Radius></Sphere></Objects></Scene>"""
+    p = os.path.join(d, "ml.xml")
+    with open(p, "w") as f:
+        f.write(xml)
+    hs, sc = _load(rt, p)
+    cam = hs.camera(0)
+    ref = rt.oracle_render(hs.desc, cam)
+    img = sc.render(cam, rt.default_opts(queue_capacity=1024, wave_rays=1024))
+    r = rel_err(img, ref).max(axis=-1)
+    assert r.mean() <= 1e-3 and np.quantile(r, 0.99) <= 1e-2, (r.mean(), np.quantile(r, 0.99))
+    assert sc.stats().rays_shadow > cam.nx * cam.ny * 3
+    sc.close(); hs.close()
+
+
+def test_cli_writes_the_reference_file_formats(rt, scene_dir, tmp_path):
+    """bin/raytracer scene.xml (the src/main.cpp contract): writes <ImageName>; names containing ".png" get the clamped
+    P3 PPM of src/Image.cpp:62-103 - compared with the same rule applied to the oracle's radiance."""
+    exe = os.path.join(ROOT, "raytracer-795_b200", "bin", "raytracer")
+    xml = rt.scenes.scene_c1(os.path.join(scene_dir, "c1cli"), res=96, name="c1cli")
+    txt = open(xml).read().replace("<ImageName>c1cli.ppm</ImageName>", "<ImageName>c1cli.png</ImageName>")
+    open(xml, "w").write(txt)
+    r = subprocess.run([exe, xml, "--f32"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    toks = open(os.path.join(tmp_path, "c1cli.png")).read().split()
+    assert toks[:4] == ["P3", "96", "96", "255"]
+    got = np.array(toks[4:], dtype=np.int64).reshape(96, 96, 3)
+    hs = rt.HostScene(xml)
+    ref = rt.oracle_render(hs.desc, hs.camera(0))
+    want = np.clip(ref, 0, 255).astype(np.uint8).astype(np.int64)
+    assert (np.abs(got - want) <= 1).mean() >= 0.999       # (unsigned char) truncation can flip at an integer boundary
+    assert (got == want).mean() >= 0.98
+    f32 = rt.read_f32(os.path.join(tmp_path, "c1cli.png.f32"))
+    assert np.allclose(f32, ref, rtol=1e-3, atol=1e-2)
+    # a missing scene file is an error exit, not a crash
+    r2 = subprocess.run([exe, os.path.join(str(tmp_path), "nope.xml")], cwd=tmp_path, capture_output=True, text=True)
+    assert r2.returncode == 1 and "cannot open" in r2.stderr
+    hs.close()
