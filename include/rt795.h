@@ -222,6 +222,8 @@ typedef struct RtStats {
     uint64_t waves;
     uint64_t node_visits, prim_tests;                     /* closest-hit queries; only with collect_counters bit 1 */
     uint64_t node_visits_shadow, prim_tests_shadow;       /* occlusion queries; only with collect_counters bit 1 */
+    uint64_t diag[8];         /* collect_counters bit 1, SIMT diagnostics of the traversal kernels (closest-hit [0..3], occlusion [4..7]):
+                                 node-step warp executions, sum of lanes holding an unfinished ray at those, leaf-phase executions, lanes in them */
     double ms_total;          /* first launch -> framebuffer ready (CUDA events) */
     double ms_extend, ms_shade, ms_shadow, ms_raygen, ms_resolve;  /* per-stage sums, CUDA events (only with collect_counters bit 0) */
     uint64_t launches_extend, launches_shade, launches_shadow;     /* launches per stage in the last render */

@@ -28,6 +28,9 @@ out = {"config": cfg, "kw": str(kw), "rays": {"primary": st.rays_primary, "secon
                        "measured_bytes_per_ray": 64 * st.node_visits / max(1, ext) + 48 * st.prim_tests / max(1, ext) + 48},
        "occlusion": {"nodes_per_ray": st.node_visits_shadow / max(1, st.rays_shadow), "prims_per_ray": st.prim_tests_shadow / max(1, st.rays_shadow),
                      "measured_bytes_per_ray": 64 * st.node_visits_shadow / max(1, st.rays_shadow) + 48 * st.prim_tests_shadow / max(1, st.rays_shadow) + 48},
+       "simt": {k: {"lanes_at_node_step": nv / max(1, st.diag[o]), "lanes_alive_at_node_step": st.diag[o + 1] / max(1, st.diag[o]),
+                    "lanes_in_leaf_phase": st.diag[o + 3] / max(1, st.diag[o + 2]), "node_step_execs": st.diag[o], "leaf_phase_execs": st.diag[o + 2]}
+                for k, o, nv in (("closest_hit", 0, st.node_visits), ("occlusion", 4, st.node_visits_shadow))},
        "stage_ms_with_counters": {"extend": st.ms_extend, "shade": st.ms_shade, "shadow": st.ms_shadow},
        "bvh": {"nodes": st.bvh_nodes, "bytes": st.bvh_bytes, "tri_bytes": st.tri_bytes, "build_ms": st.ms_bvh_build}}
 print(json.dumps(out))

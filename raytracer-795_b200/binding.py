@@ -99,7 +99,7 @@ class RtHit(C.Structure):
 class RtStats(C.Structure):
     _fields_ = [("rays_primary", C.c_uint64), ("rays_secondary", C.c_uint64), ("rays_shadow", C.c_uint64),
                 ("launches", C.c_uint64), ("waves", C.c_uint64), ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64),
-                ("node_visits_shadow", C.c_uint64), ("prim_tests_shadow", C.c_uint64),
+                ("node_visits_shadow", C.c_uint64), ("prim_tests_shadow", C.c_uint64), ("diag", C.c_uint64 * 8),
                 ("ms_total", C.c_double), ("ms_extend", C.c_double), ("ms_shade", C.c_double), ("ms_shadow", C.c_double),
                 ("ms_raygen", C.c_double), ("ms_resolve", C.c_double),
                 ("launches_extend", C.c_uint64), ("launches_shade", C.c_uint64), ("launches_shadow", C.c_uint64),

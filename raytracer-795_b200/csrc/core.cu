@@ -557,6 +557,7 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
         CK(cudaMemcpy(sc->h_counters, sc->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost));
         s.node_visits = sc->h_counters->node_visits; s.prim_tests = sc->h_counters->prim_tests;
         s.node_visits_shadow = sc->h_counters->node_visits_shadow; s.prim_tests_shadow = sc->h_counters->prim_tests_shadow;
+        for (int k = 0; k < 8; k++) s.diag[k] = sc->h_counters->diag[k];
     } else { s.node_visits = s.prim_tests = s.node_visits_shadow = s.prim_tests_shadow = 0; }
 }
 

@@ -87,6 +87,7 @@ struct DCounters {
     int32_t next_count, shadow_count, overflow, ray_cursor;
     unsigned long long node_visits, prim_tests;                 // closest-hit queries
     unsigned long long node_visits_shadow, prim_tests_shadow;   // occlusion queries
+    unsigned long long diag[8];   // COUNT builds: [0/4] node-step warp executions, [1/5] sum of lanes alive (ray unfinished) at those, [2/6] leaf-phase executions, [3/7] lanes in them (closest / occlusion)
 };
 
 }  // namespace rt795

@@ -8,6 +8,11 @@
 // tests run warp-wide; (2) warps are persistent and lanes whose ray has terminated pull the next ray from a global
 // cursor as soon as fewer than kFetchThreshold lanes are still busy.
 // Semantics are exactly those of traverse.cuh (same box / triangle / sphere tests, same hit record).
+//
+// Measured dead end (kept here so it is not retried blindly): making the phases strictly warp-synchronous (every vote over
+// the full warp, blocked lanes idling inside the phase) raises the leaf-phase batch from 3.0 to 10.8 lanes (occlusion) and
+// 12.9 to 18.9 (closest hit) but drops the node-step batch from 15.9 to 11.8 and 24.2 to 20.0 lanes because leaf holders
+// wait for the slowest searcher: C4 frame 68.7 -> 77.0 ms.  The loose votes over __activemask() below are faster.
 #pragma once
 #include "shade.cuh"
 #include "traverse.cuh"
@@ -61,6 +66,11 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
     bool exhausted = false;
     const int fetch_threshold = (io.flags >> 8) & 0xff ? (io.flags >> 8) & 0xff : kFetchThreshold;
     unsigned cnt_nodes = 0, cnt_prims = 0;
+    // COUNT builds only: which lanes of each warp currently hold an unfinished ray (shared bitmask per warp), to split the
+    // inactive lanes at a node step into "busy elsewhere" and "ray finished, waiting for a refill"
+    __shared__ unsigned s_alive[4];
+    unsigned d_exec = 0, d_alive = 0, d_leafexec = 0, d_leaflanes = 0;
+    if (COUNT) { if (lane == 0) s_alive[threadIdx.x >> 5] = 0; __syncwarp(); }
 
 #define RT_SET_RAY(O, D)                                                                               \
     do {                                                                                               \
@@ -93,6 +103,7 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
     while (true) {
         // ---------------- retire finished rays, fetch new ones
         bool idle = node == kSentinel;
+        if (COUNT && idle) atomicAnd(&s_alive[threadIdx.x >> 5], ~(1u << lane));
         if (ANY_HIT) {
             bool add = idle && rayidx >= 0 && hprim < 0;   // unoccluded: the light's contribution reaches the pixel
             float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -117,6 +128,7 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
                 if (any_nan(wo) || any_nan(wd)) { node = kSentinel; if (!ANY_HIT) tmax = 0.f; }   // src/Helper.cpp:28-30: NaN ray = no hit
                 else {
                     RT_SET_RAY(wo, wd);
+                    if (COUNT) atomicOr(&s_alive[threadIdx.x >> 5], 1u << lane);
                     sp = 0; top_n = kSentinel; top_t = 0.f;
                     node = sc.tlas_root4; cur_obj = -1;
                 }
@@ -136,7 +148,11 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
                     RT_POP();
                 } else if (node >= 0) {
                     // 4-wide inner node: one 128-byte line, four independent slab tests
-                    if (COUNT) ++cnt_nodes;
+                    if (COUNT) {
+                        ++cnt_nodes;
+                        unsigned am = __activemask();
+                        if ((int)lane == __ffs(am) - 1) { d_exec++; d_alive += __popc(*(volatile unsigned*)&s_alive[threadIdx.x >> 5]); }
+                    }
                     const float4* np = sc.nodes4 + (size_t)node * 8;
                     // near / far planes are picked by the ray's direction signs through the LOAD ADDRESS (lo and hi of an axis are
                     // adjacent float4s of the same 128-byte line), so no min/max per axis is needed: 6 FMA + 2 three-input min/max
@@ -208,6 +224,7 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
             }
             // ---------------- postponed leaves
             while (leaf < 0) {
+                if (COUNT) { unsigned am = __activemask(); if ((int)lane == __ffs(am) - 1) { d_leafexec++; d_leaflanes += __popc(am); } }
                 int payload = ~leaf;
                 int first = payload >> 3, count = (payload & 7) + 1;
                 const float4* tp = sc.tris + (size_t)first * 3;
@@ -234,6 +251,9 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
     if (COUNT) {
         atomicAdd(ANY_HIT ? &ctr->node_visits_shadow : &ctr->node_visits, (unsigned long long)cnt_nodes);
         atomicAdd(ANY_HIT ? &ctr->prim_tests_shadow : &ctr->prim_tests, (unsigned long long)cnt_prims);
+        int b = ANY_HIT ? 4 : 0;
+        atomicAdd(&ctr->diag[b + 0], (unsigned long long)d_exec); atomicAdd(&ctr->diag[b + 1], (unsigned long long)d_alive);
+        atomicAdd(&ctr->diag[b + 2], (unsigned long long)d_leafexec); atomicAdd(&ctr->diag[b + 3], (unsigned long long)d_leaflanes);
     }
 }
 
