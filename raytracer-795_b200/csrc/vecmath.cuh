@@ -21,7 +21,14 @@ RT_HD float3 operator/(float3 a, float s) { float r = 1.0f / s; return v3(a.x * 
 RT_HD float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 RT_HD float3 cross(float3 a, float3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 RT_HD float length(float3 a) { return sqrtf(dot(a, a)); }
-RT_HD float3 normalize0(float3 a) { float n = length(a); return n > 0.f ? a / n : a; }        // Eigen normalized(): unchanged at 0
+RT_HD float3 normalize0(float3 a) {                                                           // Eigen normalized(): unchanged at 0
+#ifdef __CUDA_ARCH__
+    float n2 = dot(a, a);
+    return n2 > 0.f ? a * rsqrtf(n2) : a;      // MUFU.RSQ (<= 2 ulp) instead of sqrt + reciprocal
+#else
+    float n = length(a); return n > 0.f ? a / n : a;
+#endif
+}
 RT_HD bool any_nan(float3 a) { return a.x != a.x || a.y != a.y || a.z != a.z; }
 RT_HD bool is_zero(float3 a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f; }
 RT_HD float comp(float3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
