@@ -14,7 +14,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace rt795 {
@@ -67,6 +69,19 @@ struct QueueBufs {
 
 }  // namespace
 
+// Per-pipeline render state.  Two pipelines (own stream, ray queues, shadow queue, counters) process alternate waves of a
+// frame from two host threads, so the tail of one wave's kernels (last rays finishing on a mostly idle GPU) and the host
+// round trips of its queue-size readbacks overlap with the other wave's work.
+struct Pipe {
+    cudaStream_t st = nullptr;
+    std::vector<QueueBufs> levels;
+    DevBuf<float4> sq_o, sq_d, sq_c;
+    DevBuf<DCounters> counters;
+    DCounters* h_counters = nullptr;   // pinned
+    cudaEvent_t done = nullptr;
+};
+constexpr int kPipes = 2;
+
 struct RtScene {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -90,17 +105,15 @@ struct RtScene {
     int trav_flags = 2, trav_flags_shadow = 3;   // TraceIO.flags for closest-hit / occlusion launches (measured best on C4; RT795_TRAVERSAL_FLAGS overrides both)
     bool full_grid = false;                 // RT795_FULL_GRID=1: one thread per ray instead of resident warps
     // render state
-    std::vector<QueueBufs> levels;
+    Pipe pipes[kPipes];
     size_t queue_cap = 0, shadow_cap = 0;
-    DevBuf<float4> sq_o, sq_d, sq_c;
     DevBuf<float> accum, out_dev;
-    DevBuf<DCounters> counters;
-    DCounters* h_counters = nullptr;   // pinned
     DevBuf<RtHit> hits_dev;
     // tone map scratch
     DevBuf<double> tm_sum; DevBuf<float> tm_max; DevBuf<unsigned> tm_hist; DevBuf<float> tm_in; DevBuf<uint8_t> tm_out;
     RtStats stats{};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_start = nullptr;
+    bool single_pipe = false;   // RT795_PIPES=1: disable the second wave pipeline (A/B)
 };
 
 namespace {
@@ -382,6 +395,7 @@ inline int Blocks(long long n) { return (int)((n + kBlock - 1) / kBlock); }
 
 struct Driver {
     RtScene* sc;
+    Pipe* pp;
     cudaStream_t st;
     DCamera cam;
     DTiling tl;
@@ -412,8 +426,8 @@ struct Driver {
 
     // Processes rays [0, n) of level `lv`; recursion depth is bounded by the queue level count.
     void ProcessLevel(int lv, int n) {
-        QueueBufs& qb = sc->levels[lv % nlevels];
-        QueueBufs& nb = sc->levels[(lv + 1) % nlevels];
+        QueueBufs& qb = pp->levels[lv % nlevels];
+        QueueBufs& nb = pp->levels[(lv + 1) % nlevels];
         DRayQueue q = qb.View(), nq = nb.View();
         int nl = std::max(1, sc->d.num_lights);
         // chunk so that neither the next level (<= 2 rays per ray when a dielectric can branch) nor the shadow queue can overflow
@@ -422,37 +436,37 @@ struct Driver {
         int chunk = (int)std::max(1LL, std::min(by_next, by_shadow));
         for (int first = 0; first < n; first += chunk) {
             int m = std::min(chunk, n - first);
-            CK(cudaMemsetAsync(&sc->counters.p->next_count, 0, 2 * sizeof(int32_t), st));
-            if (sc->persistent) CK(cudaMemsetAsync(&sc->counters.p->ray_cursor, 0, sizeof(int32_t), st));
+            CK(cudaMemsetAsync(&pp->counters.p->next_count, 0, 2 * sizeof(int32_t), st));
+            if (sc->persistent) CK(cudaMemsetAsync(&pp->counters.p->ray_cursor, 0, sizeof(int32_t), st));
             Timed(&ms_extend, [&] {
                 if (sc->persistent) {
-                    TraceIO io{q.o_time, q.d_tmax, first, m, &sc->counters.p->ray_cursor, q.hit, q.hit_obj, nullptr, nullptr, sc->trav_flags};
+                    TraceIO io{q.o_time, q.d_tmax, first, m, &pp->counters.p->ray_cursor, q.hit, q.hit_obj, nullptr, nullptr, sc->trav_flags};
                     int grid = sc->full_grid ? Blocks(m) : std::min(Blocks(m), sc->grid_extend);
-                    if (count) k_trace_persistent<false, true><<<grid, kBlock, 0, st>>>(sc->d, io, sc->counters.p);
-                    else k_trace_persistent<false, false><<<grid, kBlock, 0, st>>>(sc->d, io, sc->counters.p);
-                } else if (count) k_extend<true><<<Blocks(m), kBlock, 0, st>>>(sc->d, q, first, m, sc->counters.p);
-                else k_extend<false><<<Blocks(m), kBlock, 0, st>>>(sc->d, q, first, m, sc->counters.p);
+                    if (count) k_trace_persistent<false, true><<<grid, kBlock, 0, st>>>(sc->d, io, pp->counters.p);
+                    else k_trace_persistent<false, false><<<grid, kBlock, 0, st>>>(sc->d, io, pp->counters.p);
+                } else if (count) k_extend<true><<<Blocks(m), kBlock, 0, st>>>(sc->d, q, first, m, pp->counters.p);
+                else k_extend<false><<<Blocks(m), kBlock, 0, st>>>(sc->d, q, first, m, pp->counters.p);
             });
             Timed(&ms_shade, [&] {
-                if (rc.integrator == RT_INTEGRATOR_PATH) k_shade<RT_INTEGRATOR_PATH><<<Blocks(m), kBlock, 0, st>>>(sc->d, cam, rc, q, first, m, nq, sq, sc->counters.p, accum);
-                else k_shade<RT_INTEGRATOR_REFERENCE><<<Blocks(m), kBlock, 0, st>>>(sc->d, cam, rc, q, first, m, nq, sq, sc->counters.p, accum);
+                if (rc.integrator == RT_INTEGRATOR_PATH) k_shade<RT_INTEGRATOR_PATH><<<Blocks(m), kBlock, 0, st>>>(sc->d, cam, rc, q, first, m, nq, sq, pp->counters.p, accum);
+                else k_shade<RT_INTEGRATOR_REFERENCE><<<Blocks(m), kBlock, 0, st>>>(sc->d, cam, rc, q, first, m, nq, sq, pp->counters.p, accum);
             });
             launches += 2; n_extend++; n_shade++;
-            CK(cudaMemcpyAsync(sc->h_counters, sc->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(pp->h_counters, pp->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             CK(cudaGetLastError());
-            int next_n = sc->h_counters->next_count, shadow_n = sc->h_counters->shadow_count;
-            if (sc->h_counters->overflow) throw Invalid{"ray queue overflow (raise queue_capacity)"};
+            int next_n = pp->h_counters->next_count, shadow_n = pp->h_counters->shadow_count;
+            if (pp->h_counters->overflow) throw Invalid{"ray queue overflow (raise queue_capacity)"};
             if (shadow_n > 0) {
-                if (sc->persistent) CK(cudaMemsetAsync(&sc->counters.p->ray_cursor, 0, sizeof(int32_t), st));
+                if (sc->persistent) CK(cudaMemsetAsync(&pp->counters.p->ray_cursor, 0, sizeof(int32_t), st));
                 Timed(&ms_shadow, [&] {
                     if (sc->persistent) {
-                        TraceIO io{sq.o_time, sq.d_tmax, 0, shadow_n, &sc->counters.p->ray_cursor, nullptr, nullptr, sq.c_pixel, accum, sc->trav_flags_shadow};
+                        TraceIO io{sq.o_time, sq.d_tmax, 0, shadow_n, &pp->counters.p->ray_cursor, nullptr, nullptr, sq.c_pixel, accum, sc->trav_flags_shadow};
                         int grid = sc->full_grid ? Blocks(shadow_n) : std::min(Blocks(shadow_n), sc->grid_shadow);
-                        if (count) k_trace_persistent<true, true><<<grid, kBlock, 0, st>>>(sc->d, io, sc->counters.p);
-                        else k_trace_persistent<true, false><<<grid, kBlock, 0, st>>>(sc->d, io, sc->counters.p);
-                    } else if (count) k_shadow<true><<<Blocks(shadow_n), kBlock, 0, st>>>(sc->d, sq, shadow_n, accum, sc->counters.p);
-                    else k_shadow<false><<<Blocks(shadow_n), kBlock, 0, st>>>(sc->d, sq, shadow_n, accum, sc->counters.p);
+                        if (count) k_trace_persistent<true, true><<<grid, kBlock, 0, st>>>(sc->d, io, pp->counters.p);
+                        else k_trace_persistent<true, false><<<grid, kBlock, 0, st>>>(sc->d, io, pp->counters.p);
+                    } else if (count) k_shadow<true><<<Blocks(shadow_n), kBlock, 0, st>>>(sc->d, sq, shadow_n, accum, pp->counters.p);
+                    else k_shadow<false><<<Blocks(shadow_n), kBlock, 0, st>>>(sc->d, sq, shadow_n, accum, pp->counters.p);
                 });
                 launches++; n_shadow++;
                 shadow += (uint64_t)shadow_n;
@@ -465,17 +479,25 @@ struct Driver {
     }
 };
 
-void EnsureRenderBuffers(RtScene* sc, const RtRenderOpts* opts, int nlevels, size_t npix3) {
-    size_t cap = opts->queue_capacity > 0 ? (size_t)opts->queue_capacity : ((size_t)1 << 22);
+void EnsureRenderBuffers(RtScene* sc, const RtRenderOpts* opts, int nlevels, size_t npix3, int npipe) {
+    // default 8 Mi rays per wave: every launch ends in a tail where the last rays finish on a mostly idle GPU (measured on C4:
+    // 1 Mi 83.7 ms, 2 Mi 73.6, 4 Mi 67.6, 8 Mi 65.2, 16 Mi 64.9 per frame); 8 Mi costs 0.7 GB per queue level of the 180 GB
+    size_t cap = opts->queue_capacity > 0 ? (size_t)opts->queue_capacity : ((size_t)1 << 23);
+    if (opts->queue_capacity <= 0) if (const char* e = getenv("RT795_QUEUE_CAP")) cap = (size_t)atoll(e);   // tuning override of the default
     cap = std::max<size_t>(cap, 64);
     size_t scap = (size_t)std::min(8, std::max(2, sc->d.num_lights)) * cap;   // a shade pass over `cap` rays emits <= num_lights shadow rays per ray
-    if ((int)sc->levels.size() < nlevels) sc->levels.resize(nlevels);
-    for (int i = 0; i < nlevels; i++) sc->levels[i].Alloc(cap);
     sc->queue_cap = cap; sc->shadow_cap = scap;
-    sc->sq_o.Alloc(scap); sc->sq_d.Alloc(scap); sc->sq_c.Alloc(scap);
     sc->accum.Alloc(npix3);
-    sc->counters.Alloc(1);
-    if (!sc->h_counters) CK(cudaMallocHost((void**)&sc->h_counters, sizeof(DCounters)));
+    for (int p = 0; p < npipe; p++) {
+        Pipe& pp = sc->pipes[p];
+        if (!pp.st) CK(cudaStreamCreateWithFlags(&pp.st, cudaStreamNonBlocking));
+        if (!pp.done) CK(cudaEventCreateWithFlags(&pp.done, cudaEventDisableTiming));
+        if ((int)pp.levels.size() < nlevels) pp.levels.resize(nlevels);
+        for (int i = 0; i < nlevels; i++) pp.levels[i].Alloc(cap);
+        pp.sq_o.Alloc(scap); pp.sq_d.Alloc(scap); pp.sq_c.Alloc(scap);
+        pp.counters.Alloc(1);
+        if (!pp.h_counters) CK(cudaMallocHost((void**)&pp.h_counters, sizeof(DCounters)));
+    }
 }
 
 DTiling MakeTiling(const RtCameraDesc* cam, const RtRenderOpts* opts) {
@@ -498,67 +520,106 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
     if (opts_in) opts = *opts_in; else { memset(&opts, 0, sizeof opts); }
     CK(cudaSetDevice(sc->device));
     cudaStream_t st = user_stream ? user_stream : sc->stream;
-    Driver dr;
-    dr.sc = sc; dr.st = st;
-    CameraSetup(cam, &dr.cam);
-    dr.tl = MakeTiling(cam, &opts);
-    dr.count = (opts.collect_counters & 2) != 0;
-    dr.stage_time = (opts.collect_counters & 1) != 0;
+    Driver proto;
+    proto.sc = sc; proto.st = st; proto.pp = nullptr;
+    CameraSetup(cam, &proto.cam);
+    proto.tl = MakeTiling(cam, &opts);
+    proto.count = (opts.collect_counters & 2) != 0;
+    proto.stage_time = (opts.collect_counters & 1) != 0;
     bool path = opts.integrator == RT_INTEGRATOR_PATH;
     int max_depth = path ? (opts.pt_max_depth > 0 ? opts.pt_max_depth : sc->d.max_depth) : sc->d.max_depth;
     if (max_depth < 0) max_depth = 0;
     if (max_depth > 250) throw Invalid{"recursion depth above 250 is not supported"};
-    dr.branching = !path && sc->has_dielectric && max_depth > 0;
+    proto.branching = !path && sc->has_dielectric && max_depth > 0;
     // Two ping-pong levels suffice when a level is always processed in ONE chunk (no branching and the shadow queue can take
     // a full level); otherwise deeper levels must not overwrite a level that still has unprocessed chunks.
-    dr.nlevels = (dr.branching || sc->d.num_lights > 8) ? max_depth + 2 : 2;
+    proto.nlevels = (proto.branching || sc->d.num_lights > 8) ? max_depth + 2 : 2;
     size_t npix3 = (size_t)cam->nx * cam->ny * 3;
-    EnsureRenderBuffers(sc, &opts, dr.nlevels, npix3);
-    dr.rc.seed = opts.seed; dr.rc.integrator = opts.integrator; dr.rc.pt_max_depth = max_depth; dr.rc.pt_nee = opts.pt_nee; dr.rc.pt_rr = opts.pt_russian_roulette;
-    dr.rc.pt_importance = opts.pt_importance; dr.rc.queue_cap = (int)sc->queue_cap; dr.rc.shadow_cap = (int)sc->shadow_cap;
-    dr.accum = sc->accum.p;
-    dr.sq = DShadowQueue{sc->sq_o.p, sc->sq_d.p, sc->sq_c.p};
+
+    size_t cap_hint = opts.queue_capacity > 0 ? (size_t)opts.queue_capacity : ((size_t)1 << 23);
+    unsigned long long total = (unsigned long long)proto.tl.local_tiles * proto.tl.tw * proto.tl.th * (unsigned long long)proto.cam.spp;
+    // one pipeline when stages are timed / counted (clean per-stage numbers) or the frame is a single wave
+    int npipe = (proto.stage_time || proto.count || sc->single_pipe || total <= (unsigned long long)(opts.wave_rays > 0 ? (size_t)opts.wave_rays : cap_hint)) ? 1 : kPipes;
+    EnsureRenderBuffers(sc, &opts, proto.nlevels, npix3, npipe);
+    proto.rc.seed = opts.seed; proto.rc.integrator = opts.integrator; proto.rc.pt_max_depth = max_depth; proto.rc.pt_nee = opts.pt_nee; proto.rc.pt_rr = opts.pt_russian_roulette;
+    proto.rc.pt_importance = opts.pt_importance; proto.rc.queue_cap = (int)sc->queue_cap; proto.rc.shadow_cap = (int)sc->shadow_cap;
+    proto.accum = sc->accum.p;
 
     int wave = opts.wave_rays > 0 ? opts.wave_rays : (int)sc->queue_cap;
     wave = (int)std::min<size_t>((size_t)wave, sc->queue_cap);
     wave = std::max(32, wave / 32 * 32);
-    unsigned long long total = (unsigned long long)dr.tl.local_tiles * dr.tl.tw * dr.tl.th * (unsigned long long)dr.cam.spp;
 
     CK(cudaEventRecord(sc->ev0, st));
     CK(cudaMemsetAsync(sc->accum.p, 0, npix3 * sizeof(float), st));
-    CK(cudaMemsetAsync(sc->counters.p, 0, sizeof(DCounters), st));
-    uint64_t primary = 0, waves = 0;
-    double ms_raygen = 0;
-    for (unsigned long long base = 0; base < total; base += (unsigned long long)wave) {
-        int n = (int)std::min<unsigned long long>((unsigned long long)wave, total - base);
-        CK(cudaMemsetAsync(&sc->counters.p->next_count, 0, sizeof(int32_t), st));
-        dr.Timed(&ms_raygen, [&] {
-            k_raygen<<<Blocks(n), kBlock, 0, st>>>(dr.cam, dr.tl, dr.rc, max_depth, base, n, sc->levels[0].View(), &sc->counters.p->next_count, 0);
-        });
-        dr.launches++;
-        CK(cudaMemcpyAsync(sc->h_counters, sc->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        int n0 = sc->h_counters->next_count;
-        primary += (uint64_t)n0; waves++;
-        if (n0 > 0) dr.ProcessLevel(0, n0);
+    CK(cudaEventRecord(sc->ev_start, st));
+
+    struct PipeResult { uint64_t primary = 0, waves = 0; double ms_raygen = 0; std::exception_ptr err; };
+    Driver drs[kPipes];
+    PipeResult res[kPipes];
+    auto run_pipe = [&](int p) {
+        try {
+            CK(cudaSetDevice(sc->device));
+            Driver& dr = drs[p];
+            dr = proto;
+            dr.pp = &sc->pipes[p];
+            dr.st = dr.pp->st;
+            dr.sq = DShadowQueue{dr.pp->sq_o.p, dr.pp->sq_d.p, dr.pp->sq_c.p};
+            cudaStream_t ps = dr.st;
+            CK(cudaStreamWaitEvent(ps, sc->ev_start, 0));              // after the accumulator was cleared on the caller's stream
+            CK(cudaMemsetAsync(dr.pp->counters.p, 0, sizeof(DCounters), ps));
+            unsigned long long w = 0;
+            for (unsigned long long base = 0; base < total; base += (unsigned long long)wave, w++) {
+                if ((int)(w % (unsigned long long)npipe) != p) continue;
+                int n = (int)std::min<unsigned long long>((unsigned long long)wave, total - base);
+                CK(cudaMemsetAsync(&dr.pp->counters.p->next_count, 0, sizeof(int32_t), ps));
+                dr.Timed(&res[p].ms_raygen, [&] {
+                    k_raygen<<<Blocks(n), kBlock, 0, ps>>>(dr.cam, dr.tl, dr.rc, max_depth, base, n, dr.pp->levels[0].View(), &dr.pp->counters.p->next_count, 0);
+                });
+                dr.launches++;
+                CK(cudaMemcpyAsync(dr.pp->h_counters, dr.pp->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost, ps));
+                CK(cudaStreamSynchronize(ps));
+                int n0 = dr.pp->h_counters->next_count;
+                res[p].primary += (uint64_t)n0; res[p].waves++;
+                if (n0 > 0) dr.ProcessLevel(0, n0);
+            }
+            CK(cudaEventRecord(dr.pp->done, ps));
+        } catch (...) { res[p].err = std::current_exception(); }
+    };
+    if (npipe == 1) run_pipe(0);
+    else {
+        std::thread t1([&] { run_pipe(1); });
+        run_pipe(0);
+        t1.join();
     }
+    for (int p = 0; p < npipe; p++) if (res[p].err) { for (int q = 0; q < npipe; q++) cudaStreamSynchronize(sc->pipes[q].st); std::rethrow_exception(res[p].err); }
+    for (int p = 0; p < npipe; p++) CK(cudaStreamWaitEvent(st, sc->pipes[p].done, 0));
     double ms_resolve = 0;
-    dr.Timed(&ms_resolve, [&] { k_resolve<<<Blocks((long long)npix3), kBlock, 0, st>>>(sc->accum.p, d_out, (int)npix3, 1.0f / (float)dr.cam.spp); });
-    dr.launches++;
+    proto.Timed(&ms_resolve, [&] { k_resolve<<<Blocks((long long)npix3), kBlock, 0, st>>>(sc->accum.p, d_out, (int)npix3, 1.0f / (float)proto.cam.spp); });
     CK(cudaEventRecord(sc->ev1, st));
     CK(cudaEventSynchronize(sc->ev1));
     CK(cudaGetLastError());
     float ms = 0; CK(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1));
     RtStats& s = sc->stats;
-    s.rays_primary = primary; s.rays_secondary = dr.secondary; s.rays_shadow = dr.shadow; s.launches = dr.launches; s.waves = waves;
-    s.ms_total = ms; s.ms_extend = dr.ms_extend; s.ms_shade = dr.ms_shade; s.ms_shadow = dr.ms_shadow; s.ms_raygen = ms_raygen; s.ms_resolve = ms_resolve;
-    s.launches_extend = dr.n_extend; s.launches_shade = dr.n_shade; s.launches_shadow = dr.n_shadow;
-    if (dr.count) {
-        CK(cudaMemcpy(sc->h_counters, sc->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost));
-        s.node_visits = sc->h_counters->node_visits; s.prim_tests = sc->h_counters->prim_tests;
-        s.node_visits_shadow = sc->h_counters->node_visits_shadow; s.prim_tests_shadow = sc->h_counters->prim_tests_shadow;
-        for (int k = 0; k < 8; k++) s.diag[k] = sc->h_counters->diag[k];
-    } else { s.node_visits = s.prim_tests = s.node_visits_shadow = s.prim_tests_shadow = 0; }
+    s.rays_primary = s.rays_secondary = s.rays_shadow = s.launches = s.waves = 0;
+    s.ms_extend = s.ms_shade = s.ms_shadow = s.ms_raygen = 0;
+    s.launches_extend = s.launches_shade = s.launches_shadow = 0;
+    s.node_visits = s.prim_tests = s.node_visits_shadow = s.prim_tests_shadow = 0;
+    for (int k = 0; k < 8; k++) s.diag[k] = 0;
+    for (int p = 0; p < npipe; p++) {
+        const Driver& dr = drs[p];
+        s.rays_primary += res[p].primary; s.rays_secondary += dr.secondary; s.rays_shadow += dr.shadow; s.launches += dr.launches; s.waves += res[p].waves;
+        s.ms_extend += dr.ms_extend; s.ms_shade += dr.ms_shade; s.ms_shadow += dr.ms_shadow; s.ms_raygen += res[p].ms_raygen;
+        s.launches_extend += dr.n_extend; s.launches_shade += dr.n_shade; s.launches_shadow += dr.n_shadow;
+        if (proto.count) {
+            Pipe& pp = sc->pipes[p];
+            CK(cudaMemcpy(pp.h_counters, pp.counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost));
+            s.node_visits += pp.h_counters->node_visits; s.prim_tests += pp.h_counters->prim_tests;
+            s.node_visits_shadow += pp.h_counters->node_visits_shadow; s.prim_tests_shadow += pp.h_counters->prim_tests_shadow;
+            for (int k = 0; k < 8; k++) s.diag[k] += pp.h_counters->diag[k];
+        }
+    }
+    s.launches += 1;   // k_resolve
+    s.ms_total = ms; s.ms_resolve = ms_resolve;
 }
 
 template <typename F>
@@ -602,7 +663,8 @@ int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out) {
         sc = new RtScene();
         sc->device = device;
         CK(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
-        CK(cudaEventCreate(&sc->ev0)); CK(cudaEventCreate(&sc->ev1));
+        CK(cudaEventCreate(&sc->ev0)); CK(cudaEventCreate(&sc->ev1)); CK(cudaEventCreateWithFlags(&sc->ev_start, cudaEventDisableTiming));
+        if (const char* e = getenv("RT795_PIPES")) sc->single_pipe = atoi(e) == 1;
         {
             const char* tv = getenv("RT795_TRAVERSAL");
             sc->persistent = !(tv && std::string(tv) == "classic");
@@ -627,12 +689,20 @@ void rt_scene_destroy(RtScene* sc) {
     if (!sc) return;
     cudaSetDevice(sc->device);
     if (sc->stream) cudaStreamSynchronize(sc->stream);
-    if (sc->h_counters) cudaFreeHost(sc->h_counters);
+    for (Pipe& pp : sc->pipes) {
+        if (pp.st) cudaStreamSynchronize(pp.st);
+        if (pp.h_counters) cudaFreeHost(pp.h_counters);
+        if (pp.done) cudaEventDestroy(pp.done);
+    }
+    if (sc->ev_start) cudaEventDestroy(sc->ev_start);
     if (sc->ev0) cudaEventDestroy(sc->ev0);
     if (sc->ev1) cudaEventDestroy(sc->ev1);
     cudaStream_t st = sc->stream;
+    cudaStream_t pst[kPipes];
+    for (int p = 0; p < kPipes; p++) pst[p] = sc->pipes[p].st;
     delete sc;
     if (st) cudaStreamDestroy(st);
+    for (int p = 0; p < kPipes; p++) if (pst[p]) cudaStreamDestroy(pst[p]);
 }
 
 int rt_render_device(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts, float* d_out_rgb, void* cuda_stream) {
@@ -660,7 +730,8 @@ int rt_trace_primary(RtScene* sc, const RtCameraDesc* cam, RtHit* out_hits) {
         RtRenderOpts opts; memset(&opts, 0, sizeof opts);
         size_t npix = (size_t)cam->nx * cam->ny;
         opts.queue_capacity = (int)std::max<size_t>(sc->queue_cap, 1 << 20);
-        EnsureRenderBuffers(sc, &opts, 2, npix * 3);
+        EnsureRenderBuffers(sc, &opts, 2, npix * 3, 1);
+        Pipe* pp = &sc->pipes[0];
         sc->hits_dev.Alloc(npix);
         CK(cudaMemsetAsync(sc->hits_dev.p, 0, npix * sizeof(RtHit), st));
         DCamera dc; CameraSetup(cam, &dc);
@@ -670,14 +741,14 @@ int rt_trace_primary(RtScene* sc, const RtCameraDesc* cam, RtHit* out_hits) {
         unsigned long long total = (unsigned long long)tl.local_tiles * tl.tw * tl.th;
         for (unsigned long long base = 0; base < total; base += (unsigned long long)wave) {
             int n = (int)std::min<unsigned long long>((unsigned long long)wave, total - base);
-            CK(cudaMemsetAsync(sc->counters.p, 0, sizeof(DCounters), st));
-            k_raygen<<<Blocks(n), kBlock, 0, st>>>(dc, tl, rc, 0, base, n, sc->levels[0].View(), &sc->counters.p->next_count, 1);
-            CK(cudaMemcpyAsync(sc->h_counters, sc->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemsetAsync(pp->counters.p, 0, sizeof(DCounters), st));
+            k_raygen<<<Blocks(n), kBlock, 0, st>>>(dc, tl, rc, 0, base, n, pp->levels[0].View(), &pp->counters.p->next_count, 1);
+            CK(cudaMemcpyAsync(pp->h_counters, pp->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            int n0 = sc->h_counters->next_count;
+            int n0 = pp->h_counters->next_count;
             if (n0 <= 0) continue;
-            k_extend<false><<<Blocks(n0), kBlock, 0, st>>>(sc->d, sc->levels[0].View(), 0, n0, sc->counters.p);
-            k_primary_hits<<<Blocks(n0), kBlock, 0, st>>>(sc->d, sc->levels[0].View(), n0, sc->hits_dev.p);
+            k_extend<false><<<Blocks(n0), kBlock, 0, st>>>(sc->d, pp->levels[0].View(), 0, n0, pp->counters.p);
+            k_primary_hits<<<Blocks(n0), kBlock, 0, st>>>(sc->d, pp->levels[0].View(), n0, sc->hits_dev.p);
         }
         CK(cudaMemcpyAsync(out_hits, sc->hits_dev.p, npix * sizeof(RtHit), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
