@@ -80,7 +80,7 @@ struct Pipe {
     DCounters* h_counters = nullptr;   // pinned
     cudaEvent_t done = nullptr;
 };
-constexpr int kPipes = 2;
+constexpr int kPipes = 4;      // upper bound; RtScene::npipes_wanted (default 2, RT795_PIPES) are used
 
 struct RtScene {
     int device = 0;
@@ -113,7 +113,7 @@ struct RtScene {
     DevBuf<double> tm_sum; DevBuf<float> tm_max; DevBuf<unsigned> tm_hist; DevBuf<float> tm_in; DevBuf<uint8_t> tm_out;
     RtStats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_start = nullptr;
-    bool single_pipe = false;   // RT795_PIPES=1: disable the second wave pipeline (A/B)
+    int npipes_wanted = 2;      // concurrent wave pipelines (RT795_PIPES=1..4 for A/B)
 };
 
 namespace {
@@ -480,9 +480,10 @@ struct Driver {
 };
 
 void EnsureRenderBuffers(RtScene* sc, const RtRenderOpts* opts, int nlevels, size_t npix3, int npipe) {
-    // default 8 Mi rays per wave: every launch ends in a tail where the last rays finish on a mostly idle GPU (measured on C4:
-    // 1 Mi 83.7 ms, 2 Mi 73.6, 4 Mi 67.6, 8 Mi 65.2, 16 Mi 64.9 per frame); 8 Mi costs 0.7 GB per queue level of the 180 GB
-    size_t cap = opts->queue_capacity > 0 ? (size_t)opts->queue_capacity : ((size_t)1 << 23);
+    // default 4 Mi rays per wave.  Every launch ends in a tail where the last rays finish on a mostly idle GPU; measured on C4
+    // with ONE pipeline: 1 Mi 83.7 ms, 2 Mi 73.6, 4 Mi 67.6, 8 Mi 65.2, 16 Mi 64.9 per frame.  With two pipelines the tails
+    // overlap with the other wave and the size matters little: 2 x 4 Mi 61.8, 2 x 8 Mi 62.9, 4 x 4 Mi 61.6, 3 x 16 Mi 63.7.
+    size_t cap = opts->queue_capacity > 0 ? (size_t)opts->queue_capacity : ((size_t)1 << 22);
     if (opts->queue_capacity <= 0) if (const char* e = getenv("RT795_QUEUE_CAP")) cap = (size_t)atoll(e);   // tuning override of the default
     cap = std::max<size_t>(cap, 64);
     size_t scap = (size_t)std::min(8, std::max(2, sc->d.num_lights)) * cap;   // a shade pass over `cap` rays emits <= num_lights shadow rays per ray
@@ -536,10 +537,13 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
     proto.nlevels = (proto.branching || sc->d.num_lights > 8) ? max_depth + 2 : 2;
     size_t npix3 = (size_t)cam->nx * cam->ny * 3;
 
-    size_t cap_hint = opts.queue_capacity > 0 ? (size_t)opts.queue_capacity : ((size_t)1 << 23);
+    size_t cap_hint = opts.queue_capacity > 0 ? (size_t)opts.queue_capacity : ((size_t)1 << 22);
+    if (opts.queue_capacity <= 0) if (const char* e = getenv("RT795_QUEUE_CAP")) cap_hint = (size_t)atoll(e);
     unsigned long long total = (unsigned long long)proto.tl.local_tiles * proto.tl.tw * proto.tl.th * (unsigned long long)proto.cam.spp;
     // one pipeline when stages are timed / counted (clean per-stage numbers) or the frame is a single wave
-    int npipe = (proto.stage_time || proto.count || sc->single_pipe || total <= (unsigned long long)(opts.wave_rays > 0 ? (size_t)opts.wave_rays : cap_hint)) ? 1 : kPipes;
+    unsigned long long wave_hint = opts.wave_rays > 0 ? (unsigned long long)opts.wave_rays : (unsigned long long)cap_hint;
+    int npipe = (proto.stage_time || proto.count) ? 1 : (int)std::min<unsigned long long>((unsigned long long)sc->npipes_wanted, (total + wave_hint - 1) / wave_hint);
+    npipe = std::max(1, npipe);
     EnsureRenderBuffers(sc, &opts, proto.nlevels, npix3, npipe);
     proto.rc.seed = opts.seed; proto.rc.integrator = opts.integrator; proto.rc.pt_max_depth = max_depth; proto.rc.pt_nee = opts.pt_nee; proto.rc.pt_rr = opts.pt_russian_roulette;
     proto.rc.pt_importance = opts.pt_importance; proto.rc.queue_cap = (int)sc->queue_cap; proto.rc.shadow_cap = (int)sc->shadow_cap;
@@ -587,9 +591,10 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
     };
     if (npipe == 1) run_pipe(0);
     else {
-        std::thread t1([&] { run_pipe(1); });
+        std::vector<std::thread> workers;
+        for (int p = 1; p < npipe; p++) workers.emplace_back([&, p] { run_pipe(p); });
         run_pipe(0);
-        t1.join();
+        for (auto& t : workers) t.join();
     }
     for (int p = 0; p < npipe; p++) if (res[p].err) { for (int q = 0; q < npipe; q++) cudaStreamSynchronize(sc->pipes[q].st); std::rethrow_exception(res[p].err); }
     for (int p = 0; p < npipe; p++) CK(cudaStreamWaitEvent(st, sc->pipes[p].done, 0));
@@ -664,7 +669,7 @@ int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out) {
         sc->device = device;
         CK(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&sc->ev0)); CK(cudaEventCreate(&sc->ev1)); CK(cudaEventCreateWithFlags(&sc->ev_start, cudaEventDisableTiming));
-        if (const char* e = getenv("RT795_PIPES")) sc->single_pipe = atoi(e) == 1;
+        if (const char* e = getenv("RT795_PIPES")) sc->npipes_wanted = std::min(kPipes, std::max(1, atoi(e)));
         {
             const char* tv = getenv("RT795_TRAVERSAL");
             sc->persistent = !(tv && std::string(tv) == "classic");
