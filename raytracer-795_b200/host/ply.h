@@ -18,7 +18,8 @@ struct PlyMesh {
 };
 
 namespace plydetail {
-struct Prop { std::string name; bool is_list = false; std::string type, count_type; };
+enum Ty { T_I8, T_U8, T_I16, T_U16, T_I32, T_U32, T_F32, T_F64, T_BAD };
+struct Prop { std::string name; bool is_list = false; std::string type, count_type; Ty ty = T_BAD, cty = T_BAD; };
 struct Elem { std::string name; size_t count = 0; std::vector<Prop> props; };
 
 inline int TypeSize(const std::string& t) {
@@ -27,6 +28,32 @@ inline int TypeSize(const std::string& t) {
     if (t == "int" || t == "uint" || t == "float" || t == "int32" || t == "uint32" || t == "float32") return 4;
     if (t == "double" || t == "float64") return 8;
     return 0;
+}
+inline Ty TypeOf(const std::string& t) {
+    if (t == "char" || t == "int8") return T_I8;
+    if (t == "uchar" || t == "uint8") return T_U8;
+    if (t == "short" || t == "int16") return T_I16;
+    if (t == "ushort" || t == "uint16") return T_U16;
+    if (t == "int" || t == "int32") return T_I32;
+    if (t == "uint" || t == "uint32") return T_U32;
+    if (t == "float" || t == "float32") return T_F32;
+    if (t == "double" || t == "float64") return T_F64;
+    return T_BAD;
+}
+inline int SizeOf(Ty t) { static const int sz[] = {1, 1, 2, 2, 4, 4, 4, 8, 0}; return sz[t]; }
+// little-endian fast path (the common case): no per-value string compares
+inline double ReadLE(const unsigned char* p, Ty t) {
+    switch (t) {
+        case T_I8: { int8_t v; memcpy(&v, p, 1); return v; }
+        case T_U8: return *p;
+        case T_I16: { int16_t v; memcpy(&v, p, 2); return v; }
+        case T_U16: { uint16_t v; memcpy(&v, p, 2); return v; }
+        case T_I32: { int32_t v; memcpy(&v, p, 4); return v; }
+        case T_U32: { uint32_t v; memcpy(&v, p, 4); return v; }
+        case T_F32: { float v; memcpy(&v, p, 4); return v; }
+        case T_F64: { double v; memcpy(&v, p, 8); return v; }
+        default: return 0;
+    }
 }
 inline double ReadBin(const unsigned char* p, const std::string& t, bool swap) {
     unsigned char b[8];
@@ -78,6 +105,7 @@ inline bool LoadPly(const std::string& path, PlyMesh* out, std::string* err) {
             Prop p; std::string t; is >> t;
             if (t == "list") { p.is_list = true; is >> p.count_type >> p.type >> p.name; }
             else { p.type = t; is >> p.name; }
+            p.ty = TypeOf(p.type); p.cty = TypeOf(p.count_type);
             elems.back().props.push_back(p);
         } else if (tok == "end_header") break;
     }
@@ -107,17 +135,18 @@ inline bool LoadPly(const std::string& path, PlyMesh* out, std::string* err) {
                 if (pr.is_list) {
                     size_t cnt;
                     if (ascii) { double c; if (!(as >> c)) { *err = "PLY truncated"; return false; } cnt = (size_t)c; }
-                    else { int cs = TypeSize(pr.count_type); if (p + cs > end) { *err = "PLY truncated"; return false; } cnt = (size_t)ReadBin(p, pr.count_type, swap); p += cs; }
+                    else { int cs = SizeOf(pr.cty); if (cs == 0 || p + cs > end) { *err = "PLY truncated"; return false; } cnt = (size_t)(swap ? ReadBin(p, pr.count_type, true) : ReadLE(p, pr.cty)); p += cs; }
                     std::vector<int64_t> lst(cnt);
-                    int ts = TypeSize(pr.type);
+                    int ts = SizeOf(pr.ty);
+                    if (!ascii && (ts == 0 || p + (size_t)ts * cnt > end)) { *err = "PLY truncated"; return false; }
                     for (size_t j = 0; j < cnt; j++) {
                         if (ascii) { double v; if (!(as >> v)) { *err = "PLY truncated"; return false; } lst[j] = (int64_t)v; }
-                        else { if (p + ts > end) { *err = "PLY truncated"; return false; } lst[j] = (int64_t)ReadBin(p, pr.type, swap); p += ts; }
+                        else { lst[j] = (int64_t)(swap ? ReadBin(p, pr.type, true) : ReadLE(p, pr.ty)); p += ts; }
                     }
                     if (isf && (pr.name == "vertex_indices" || pr.name == "vertex_index")) out->faces[i] = std::move(lst);
                 } else {
                     if (ascii) { if (!(as >> scal[k])) { *err = "PLY truncated"; return false; } }
-                    else { int ts = TypeSize(pr.type); if (ts == 0 || p + ts > end) { *err = "PLY truncated / bad type"; return false; } scal[k] = ReadBin(p, pr.type, swap); p += ts; }
+                    else { int ts = SizeOf(pr.ty); if (ts == 0 || p + ts > end) { *err = "PLY truncated / bad type"; return false; } scal[k] = swap ? ReadBin(p, pr.type, true) : ReadLE(p, pr.ty); p += ts; }
                 }
             }
             if (isv) {
