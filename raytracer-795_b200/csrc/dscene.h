@@ -29,6 +29,7 @@ struct DImage { const void* pixels; int32_t width, height, format, pad; };
 
 struct DScene {
     // geometry for traversal
+    const uint4* nodes4q;               // BvhNode64Q as 4 x uint4: the same 4-wide tree (same node indices) with 8-bit quantised boxes
     const float4* nodes4;               // BvhNode128 as 8 x float4 (4-wide collapse of `nodes`; used by k_trace_persistent)
     const int32_t* obj_root4;           // per top-level entry: BLAS root in nodes4 (spheres: unused)
     int32_t tlas_root4;

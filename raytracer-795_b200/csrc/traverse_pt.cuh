@@ -44,7 +44,7 @@ RT_D void pt_accum(float* accum, float4 c) {
     }
 }
 
-template <bool ANY_HIT, bool COUNT>
+template <bool ANY_HIT, bool COUNT, bool QNODES = false>
 __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io, DCounters* ctr) {
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
@@ -153,22 +153,44 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
                         unsigned am = __activemask();
                         if ((int)lane == __ffs(am) - 1) { d_exec++; d_alive += __popc(*(volatile unsigned*)&s_alive[threadIdx.x >> 5]); }
                     }
-                    const float4* np = sc.nodes4 + (size_t)node * 8;
-                    // near / far planes are picked by the ray's direction signs through the LOAD ADDRESS (lo and hi of an axis are
-                    // adjacent float4s of the same 128-byte line), so no min/max per axis is needed: 6 FMA + 2 three-input min/max
-                    // + 2 clamps per child instead of 6 FMA + 10 min/max (the ALU pipe is the busiest pipe of this kernel, ncu r01c).
-                    float4 nx4 = ldg4(np + sgx), fx4 = ldg4(np + (1 - sgx)), ny4 = ldg4(np + 2 + sgy), fy4 = ldg4(np + (3 - sgy));
-                    float4 nz4 = ldg4(np + 4 + sgz), fz4 = ldg4(np + (5 - sgz)), cr = ldg4(np + 6);
                     float tn[4]; int rf[4];
+                    if (QNODES) {
+                        // quantised node: 4 loads; plane = origin + byte * scale, so t = byte * (scale * 1/d) + (origin - o) * 1/d.
+                        // byte -> float exactly: the byte is spliced into the mantissa of 2^23 (PRMT), minus 2^23 (FADD on the FMA pipe).
+                        const uint4* qp = sc.nodes4q + (size_t)node * 4;
+                        uint4 a0 = __ldg(qp), a1 = __ldg(qp + 1), a2 = __ldg(qp + 2), a3 = __ldg(qp + 3);
+                        float ax = __uint_as_float(a3.z) * id.x, ay = __uint_as_float(a3.w) * id.y, az = __uint_as_float(a0.w) * id.z;
+                        float bx = __uint_as_float(a0.x) * id.x - ood.x, by = __uint_as_float(a0.y) * id.y - ood.y, bz = __uint_as_float(a0.z) * id.z - ood.z;
+                        unsigned nxw = sgx ? a2.w : a2.x, fxw = sgx ? a2.x : a2.w, nyw = sgy ? a3.x : a2.y, fyw = sgy ? a2.y : a3.x;
+                        unsigned nzw = sgz ? a3.y : a2.z, fzw = sgz ? a2.z : a3.y;
+                        rf[0] = (int)a1.x; rf[1] = (int)a1.y; rf[2] = (int)a1.z; rf[3] = (int)a1.w;
+#define RT_QB(W, K) (__uint_as_float(__byte_perm((W), 0x4B000000u, 0x7650u | (K))) - 8388608.0f)
+#define RT_SLABQ(K)                                                                                                                     \
+                        {                                                                                                               \
+                            float n_ = fmaxf(fmaxf(RT_QB(nxw, K) * ax + bx, RT_QB(nyw, K) * ay + by), fmaxf(RT_QB(nzw, K) * az + bz, 0.f)); \
+                            float f_ = fminf(fminf(RT_QB(fxw, K) * ax + bx, RT_QB(fyw, K) * ay + by), fminf(RT_QB(fzw, K) * az + bz, tmax)); \
+                            tn[K] = (n_ <= f_) ? n_ : 3.0e38f;      /* an absent child has the inverted byte range 255..0 */           \
+                        }
+                        RT_SLABQ(0) RT_SLABQ(1) RT_SLABQ(2) RT_SLABQ(3)
+#undef RT_SLABQ
+#undef RT_QB
+                    } else {
+                    const float4* np = sc.nodes4 + (size_t)node * 8;
+                        // near / far planes are picked by the ray's direction signs through the LOAD ADDRESS (lo and hi of an axis are
+                        // adjacent float4s of the same 128-byte line), so no min/max per axis is needed: 6 FMA + 2 three-input min/max
+                        // + 2 clamps per child instead of 6 FMA + 10 min/max (the ALU pipe is the busiest pipe of this kernel, ncu r01c).
+                        float4 nx4 = ldg4(np + sgx), fx4 = ldg4(np + (1 - sgx)), ny4 = ldg4(np + 2 + sgy), fy4 = ldg4(np + (3 - sgy));
+                        float4 nz4 = ldg4(np + 4 + sgz), fz4 = ldg4(np + (5 - sgz)), cr = ldg4(np + 6);
 #define RT_SLAB(K, C)                                                                                                                   \
-                    {                                                                                                                   \
-                        float n_ = fmaxf(fmaxf(nx4.C * id.x - ood.x, ny4.C * id.y - ood.y), fmaxf(nz4.C * id.z - ood.z, 0.f));             \
-                        float f_ = fminf(fminf(fx4.C * id.x - ood.x, fy4.C * id.y - ood.y), fminf(fz4.C * id.z - ood.z, tmax));            \
-                        rf[K] = __float_as_int(cr.C);                                                                                   \
-                        tn[K] = (n_ <= f_ && rf[K] != kNoChildDev) ? n_ : 3.0e38f;                                                      \
-                    }
-                    RT_SLAB(0, x) RT_SLAB(1, y) RT_SLAB(2, z) RT_SLAB(3, w)
+                        {                                                                                                                   \
+                            float n_ = fmaxf(fmaxf(nx4.C * id.x - ood.x, ny4.C * id.y - ood.y), fmaxf(nz4.C * id.z - ood.z, 0.f));             \
+                            float f_ = fminf(fminf(fx4.C * id.x - ood.x, fy4.C * id.y - ood.y), fminf(fz4.C * id.z - ood.z, tmax));            \
+                            rf[K] = __float_as_int(cr.C);                                                                                   \
+                            tn[K] = (n_ <= f_ && rf[K] != kNoChildDev) ? n_ : 3.0e38f;                                                      \
+                        }
+                        RT_SLAB(0, x) RT_SLAB(1, y) RT_SLAB(2, z) RT_SLAB(3, w)
 #undef RT_SLAB
+                    }
                     if (ANY_HIT) {
                         // occlusion query: visiting order cannot change the answer and stack entries are never culled (t = 0), so
                         // the whole step is straight-line: predicated pushes of all hit children but one, else one pop.

@@ -86,6 +86,29 @@ static void CheckTree(const std::vector<Aabb>& pb, int max_leaf) {
     }
     for (int i = 0; i < n; i++) CHECK(seen4[i] == 1);
     CHECK(worst == b4.max_stack);
+    // 8-bit quantised copy: same refs, decoded boxes contain the fp32 boxes, absent children have an inverted range
+    std::vector<BvhNode64Q> q4;
+    QuantiseBvh4(b4, &q4);
+    CHECK(q4.size() == b4.nodes.size());
+    for (size_t i = 0; i < q4.size(); i++) {
+        const BvhNode64Q& q = q4[i];
+        float origin[3], scale[3];
+        memcpy(&origin[0], &q.w[0], 4); memcpy(&origin[1], &q.w[1], 4); memcpy(&origin[2], &q.w[2], 4);
+        memcpy(&scale[2], &q.w[3], 4); memcpy(&scale[0], &q.w[14], 4); memcpy(&scale[1], &q.w[15], 4);
+        const uint32_t lo_w[3] = {q.w[8], q.w[9], q.w[10]}, hi_w[3] = {q.w[11], q.w[12], q.w[13]};
+        for (int k = 0; k < 4; k++) {
+            int32_t c4, cq; memcpy(&c4, &b4.nodes[i].q[24 + k], 4); memcpy(&cq, &q.w[4 + k], 4);
+            CHECK(c4 == cq);
+            for (int a = 0; a < 3; a++) {
+                unsigned bl = (lo_w[a] >> (8 * k)) & 255u, bh = (hi_w[a] >> (8 * k)) & 255u;
+                if (c4 == kNoChild) { CHECK(bl > bh); continue; }
+                float dl = origin[a] + (float)bl * scale[a], dh = origin[a] + (float)bh * scale[a];
+                Aabb cb = ChildBox4(b4.nodes[i], k);
+                CHECK(dl <= cb.lo[a] && dh >= cb.hi[a]);
+                CHECK(dh - dl <= (cb.hi[a] - cb.lo[a]) + 2.5f * scale[a]);      // and not looser than two grid steps
+            }
+        }
+    }
     CHECK(b4.nodes.size() <= b2.nodes.size());
 }
 
