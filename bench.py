@@ -220,19 +220,25 @@ def run_ours(args, rt):
     cam = hs.camera(0)
     sc = rt.Scene(hs.desc, local)
     integrator = rt.RT_INTEGRATOR_PATH if args.config == "c5" else rt.RT_INTEGRATOR_REFERENCE
-    opts = rt.default_opts(integrator=integrator, tile_rank=rank, tile_count=world)
     npix = cam.nx * cam.ny
-    frame = torch.zeros(npix * 3, dtype=torch.float32, device=dev)
+    # N>1: every rank's resolve kernel stores its tiles into rank 0's framebuffer over NVLink peer memory (multigpu.FrameGather;
+    # RT795_GATHER=nccl selects the SUM-reduce fallback)
+    gather = rt.multigpu.FrameGather(npix * 3, dev)
+    opts = rt.default_opts(integrator=integrator, tile_rank=rank, tile_count=world, resolve_owned_only=gather.resolve_owned_only)
+    frame = gather.frame
     host_frame = torch.empty(npix * 3, dtype=torch.float32).pin_memory()
     cam_host = torch.frombuffer(bytearray(bytes(cam)) + bytearray(bytes(opts)), dtype=torch.uint8).pin_memory()
     cam_dev = torch.empty_like(cam_host, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     stream = torch.cuda.current_stream()
 
-    def render_step(o):
-        sc.render_device(cam, o, frame.data_ptr(), stream.cuda_stream)
-        if world > 1:
-            dist.reduce(frame, dst=0, op=dist.ReduceOp.SUM)   # tiles are disjoint: x + 0 = x, exact gather over NVLink
+    mid_events = []
+
+    def render_step(o, mid=None):
+        sc.render_device(cam, o, gather.out_ptr, stream.cuda_stream)
+        if mid is not None:
+            mid.record(stream)
+        gather.finish()                                       # p2p: device barrier after the peer stores; nccl: SUM reduce to rank 0
 
     host_np = host_frame.numpy().reshape(cam.ny, cam.nx, 3)
 
@@ -260,7 +266,12 @@ def run_ours(args, rt):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
             e0.record(stream)
-            step_fn(opts)
+            if step_fn is render_step:
+                em = torch.cuda.Event(enable_timing=True)
+                step_fn(opts, em)
+                mid_events.append((e0, em, e1))
+            else:
+                step_fn(opts)
             e1.record(stream)
             torch.cuda.synchronize()
             t1 = time.perf_counter()
@@ -286,6 +297,25 @@ def run_ours(args, rt):
     ms_total = timed(render_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     timed_launches = launches
+    # split of the device-timed step: this rank's render (rt_render_device, K8 stores included) vs what completes the gather
+    split = torch.tensor([sum(a.elapsed_time(m) for a, m, _ in mid_events), sum(m.elapsed_time(b) for _, m, b in mid_events)],
+                         dtype=torch.float64, device=dev) / max(1, len(mid_events))
+    if world > 1:
+        dist.all_reduce(split, op=dist.ReduceOp.MAX)
+    ms_render_max, ms_gather_max = [float(x) for x in split.tolist()]
+    gather_check = None
+    if world > 1:
+        # the gathered frame against rank 0 rendering the whole frame alone (float atomics reorder sums: compare to rounding)
+        gathered = frame.clone() if rank == 0 else None
+        barrier()
+        if rank == 0:
+            alone = torch.empty_like(frame)
+            sc.render_device(cam, rt.default_opts(integrator=integrator), alone.data_ptr(), stream.cuda_stream)
+            torch.cuda.synchronize()
+            denom = alone.abs().clamp_min(1e-3)
+            gather_check = {"max_rel_diff_vs_single_gpu_frame": float(((gathered - alone).abs() / denom).max().item()),
+                            "mean_frame": float(gathered.mean().item()), "mean_single": float(alone.mean().item())}
+        barrier()
     ms_e2e = timed(e2e_step, args.steps, wall=True)
 
     rays_local = torch.tensor(traced, dtype=torch.float64, device=dev)
@@ -300,7 +330,8 @@ def run_ours(args, rt):
     e2e_value = rays_frame / (ms_e2e / args.steps * 1e-3) / 1e6
 
     # ---- roofline of the dominant kernel (k_extend): one extra frame with per-stage CUDA events (serialises stages)
-    so = rt.default_opts(integrator=integrator, tile_rank=rank, tile_count=world, collect_counters=1)
+    so = rt.default_opts(integrator=integrator, tile_rank=rank, tile_count=world, collect_counters=1,
+                         resolve_owned_only=gather.resolve_owned_only)
     render_step(so)
     torch.cuda.synchronize()
     st = sc.stats()
@@ -329,10 +360,10 @@ def run_ours(args, rt):
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": rt.scenes.CONFIGS[args.config]["label"] + (" [--small sample]" if args.small else "") + (f" [--spp {args.spp}]" if args.spp else ""),
                            "resolution": [cam.nx, cam.ny], "spp": cam.num_samples, "rays_per_frame": {"primary": rays[0], "secondary": rays[1], "shadow": rays[2]},
-                           "integrator": "path" if integrator else "reference", "parallelism": f"tiles16x16-interleaved-x{world}", "l2": "flushed between steps (256 MB write)",
+                           "integrator": "path" if integrator else "reference", "parallelism": f"tiles16x16-interleaved-x{world}", "gather": {"mode": gather.mode, "fallback_reason": gather.why_not_p2p, "ms_render_max": ms_render_max, "ms_gather_max": ms_gather_max, "check": gather_check}, "l2": "flushed between steps (256 MB write)",
                            "scene_bytes": {"bvh": int(sstats.bvh_bytes), "triangles": int(sstats.tri_bytes)}, "bvh_build_ms": sstats.ms_bvh_build},
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(cam_host.numel()), "d2h_bytes_per_step": int(npix * 12),
-                        "api": "rt_render (host camera/options in, host framebuffer out)" if world == 1 else "rt_render_device + NCCL reduce + D2H on rank 0",
+                        "api": "rt_render (host camera/options in, host framebuffer out)" if world == 1 else ("rt_render_device (K8 stores owned tiles into rank 0's frame over NVLink peer memory) + device barrier" if gather.mode == "p2p" else "rt_render_device + NCCL reduce") + " + D2H on rank 0",
                         "timing": "host clock around the synchronous call, max over ranks"},
                 "gpu_launches": int(lt.item()), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)

@@ -204,6 +204,10 @@ typedef struct RtRenderOpts {
     int32_t queue_capacity;   /* entries per ray-queue level                        */
     int32_t collect_counters; /* bit 0: per-stage CUDA-event timing into RtStats.ms_* (serialises stages);
                                  bit 1: per-ray node-visit / primitive-test counters into RtStats (slower kernels) */
+    int32_t resolve_owned_only; /* tile_count > 1 only.  0: the resolve writes the whole frame (pixels of other ranks' tiles = 0, so
+                                 a SUM reduce gathers exactly).  1: the resolve stores ONLY this rank's tiles and leaves every other
+                                 pixel of `out` untouched - `out` may then be a peer (NVLink) mapping of the root GPU's
+                                 framebuffer and the resolve kernel itself is the gather (rt_render_device only) */
 } RtRenderOpts;
 
 /* Primary-hit record for parity/debug (rt_trace_primary); mirrors what the oracle hit harness dumps. */

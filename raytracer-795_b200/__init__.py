@@ -5,5 +5,5 @@ csrc/, host shell in host/).  This Python package is only the ctypes driver used
 synthetic scene generators.  The directory name carries a hyphen (it mirrors the reference repository's name), so it
 is loaded through __graft_entry__.load_package() under the module name `raytracer_795_b200`.
 """
-from . import binding, scenes, tiling  # noqa: F401
+from . import binding, multigpu, scenes, tiling  # noqa: F401
 from .binding import *  # noqa: F401,F403

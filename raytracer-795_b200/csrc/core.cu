@@ -633,7 +633,15 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
     for (int p = 0; p < npipe; p++) if (res[p].err) { for (int q = 0; q < npipe; q++) cudaStreamSynchronize(sc->pipes[q].st); std::rethrow_exception(res[p].err); }
     for (int p = 0; p < npipe; p++) CK(cudaStreamWaitEvent(st, sc->pipes[p].done, 0));
     double ms_resolve = 0;
-    proto.Timed(&ms_resolve, [&] { k_resolve<<<Blocks((long long)npix3), kBlock, 0, st>>>(sc->accum.p, d_out, (int)npix3, 1.0f / (float)proto.cam.spp); });
+    proto.Timed(&ms_resolve, [&] {
+        float inv_spp = 1.0f / (float)proto.cam.spp;
+        if (opts.resolve_owned_only && proto.tl.count > 1) {
+            long long n = (long long)proto.tl.local_tiles * proto.tl.th * (proto.tl.tw >> 2);
+            if (n > 0) k_resolve_owned<<<Blocks(n), kBlock, 0, st>>>(sc->accum.p, d_out, proto.tl, cam->nx, cam->ny, inv_spp);
+        } else {
+            k_resolve<<<Blocks((long long)npix3), kBlock, 0, st>>>(sc->accum.p, d_out, (int)npix3, inv_spp);
+        }
+    });
     CK(cudaEventRecord(sc->ev1, st));
     CK(cudaEventSynchronize(sc->ev1));
     CK(cudaGetLastError());
@@ -755,6 +763,7 @@ int rt_render(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts, fl
     return Guard("rt_render", [&] {
         CK(cudaSetDevice(sc->device));
         size_t n = (size_t)cam->nx * cam->ny * 3;
+        if (opts && opts->resolve_owned_only) throw Invalid{"resolve_owned_only is for rt_render_device (the host frame of rt_render is written whole)"};
         sc->out_dev.Alloc(n);
         RenderDevice(sc, cam, opts, sc->out_dev.p, nullptr);
         CK(cudaMemcpyAsync(out_rgb, sc->out_dev.p, n * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));

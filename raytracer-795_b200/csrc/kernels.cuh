@@ -395,6 +395,32 @@ __global__ void k_resolve(const float* __restrict__ accum, float* __restrict__ o
     if (i < n3) out[i] = accum[i] * inv_spp;
 }
 
+// K8 restricted to the tiles this rank owns (RtRenderOpts.resolve_owned_only): `out` may be a peer mapping of the root GPU's
+// framebuffer, so the resolve IS the multi-GPU gather - each rank stores its own tiles over NVLink, the other pixels of
+// `out` are never touched.  One thread per (owned tile, row, 4-pixel group): 48 contiguous bytes = three 16-byte stores.
+__global__ void k_resolve_owned(const float* __restrict__ accum, float* __restrict__ out, DTiling tl, int nx, int ny, float inv_spp) {
+    int gx = tl.tw >> 2;                                             // 4-pixel groups per tile row (tile_w is a multiple of 8)
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long n = (long long)tl.local_tiles * tl.th * gx;
+    if (i >= n) return;
+    int g = (int)(i % gx);
+    int row = (int)((i / gx) % tl.th);
+    int lt = (int)(i / ((long long)gx * tl.th));
+    int k = lt * tl.count + tl.rank;
+    int x = (k % tl.tiles_x) * tl.tw + g * 4, y = (k / tl.tiles_x) * tl.th + row;
+    if (y >= ny || x >= nx) return;
+    size_t base = ((size_t)y * nx + x) * 3;
+    if (x + 4 <= nx && (base & 3) == 0 && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(accum)) & 15) == 0) {
+        const float4* a = reinterpret_cast<const float4*>(accum + base);
+        float4* o = reinterpret_cast<float4*>(out + base);
+#pragma unroll
+        for (int j = 0; j < 3; j++) { float4 v = a[j]; o[j] = make_float4(v.x * inv_spp, v.y * inv_spp, v.z * inv_spp, v.w * inv_spp); }
+    } else {
+        int m = min(4, nx - x) * 3;
+        for (int j = 0; j < m; j++) out[base + j] = accum[base + j] * inv_spp;
+    }
+}
+
 // ---- primary-hit dump for rt_trace_primary (parity harness)
 __global__ void k_primary_hits(DScene sc, DRayQueue q, int count, RtHit* out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

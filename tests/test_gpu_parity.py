@@ -190,6 +190,34 @@ def test_tile_partition_is_exact(rt, scene_dir):
     sc.close(); hs.close()
 
 
+def test_owned_tile_resolve_is_the_gather(rt, scene_dir):
+    """RtRenderOpts.resolve_owned_only (the multi-GPU p2p gather, multigpu.FrameGather): every rank's resolve kernel stores
+    only its own tiles into ONE shared framebuffer and touches nothing else.  Ragged resolution (tiles cut by both image
+    edges, rows whose byte offset is not 16-byte aligned) and N = 2, 3, 8."""
+    import torch
+    for res in ((200, 120), (203, 117)):
+        xml = rt.scenes.scene_c3(os.path.join(scene_dir, f"c3own{res[0]}"), res=res, spp=4, n=32)
+        hs, sc = _load(rt, xml)
+        cam = hs.camera(0)
+        full = sc.render(cam)
+        for world in (2, 3, 8):
+            shared = torch.full((cam.ny, cam.nx, 3), float("nan"), dtype=torch.float32, device="cuda:0")
+            for r in range(world):
+                before = shared.clone()
+                sc.render_device(cam, rt.default_opts(tile_rank=r, tile_count=world, resolve_owned_only=1), shared.data_ptr())
+                torch.cuda.synchronize()
+                mask = torch.from_numpy(rt.tiling.tile_mask(cam.nx, cam.ny, r, world)).to("cuda:0")
+                changed = ~((shared == before) | (shared.isnan() & before.isnan())).all(dim=-1)
+                assert not bool((changed & ~mask).any())                 # nothing outside the rank's own tiles is written
+                assert not bool(shared[mask].isnan().any())              # every owned pixel is
+            got = shared.cpu().numpy()
+            assert np.isfinite(got).all()
+            assert np.allclose(got, full, rtol=1e-5, atol=1e-5)
+        with pytest.raises(rt.RtError):
+            sc.render(cam, rt.default_opts(tile_rank=0, tile_count=2, resolve_owned_only=1))   # host-frame call writes whole frames only
+        sc.close(); hs.close()
+
+
 def test_tonemap_runs_and_is_monotone(rt, scene_dir):
     xml = rt.scenes.scene_c1(os.path.join(scene_dir, "c1tm"), res=128)
     hs, sc = _load(rt, xml)
