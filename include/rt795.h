@@ -141,6 +141,11 @@ typedef struct RtLight {
     int32_t image;           /* environment: 0-based index into images[]            */
 } RtLight;
 
+/* Per-mesh acceleration-structure builder.  AUTO: meshes of >= 32768 triangles are built on the GPU (Morton sort + parallel
+ * locally-ordered clustering + SAH leaf collapse, csrc/bvh_device.cu), smaller ones by the host binned-SAH builder.  Both
+ * produce the same node formats; any conservative BVH returns the same closest hit up to ties. */
+enum { RT_BVH_AUTO = 0, RT_BVH_HOST_SAH = 1, RT_BVH_DEVICE_PLOC = 2 };
+
 typedef struct RtSceneDesc {
     int32_t abi_version;     /* RT795_ABI_VERSION                                   */
     /* scene scalars, src/Scene.h:60-67, defaults src/Parser.h:23-25 */
@@ -169,6 +174,8 @@ typedef struct RtSceneDesc {
     int32_t num_textures; const RtTexture* textures;
     int32_t num_images;   const RtImage* images;
     int32_t num_lights;   const RtLight* lights;
+
+    int32_t bvh_builder;     /* RT_BVH_*: who builds the per-mesh BVH (replaces BVH::ConstructionHelper, src/BVH.cpp:64-135) */
 } RtSceneDesc;
 
 /* Camera, the arguments of Camera::Camera (src/Camera.cpp:7-61) after Parser::ParseCameras resolved
@@ -232,7 +239,11 @@ typedef struct RtStats {
     double ms_extend, ms_shade, ms_shadow, ms_raygen, ms_resolve;  /* per-stage sums, CUDA events (only with collect_counters bit 0) */
     uint64_t launches_extend, launches_shade, launches_shadow;     /* launches per stage in the last render */
     uint64_t bvh_nodes, bvh_bytes, tri_bytes;             /* scene footprint in HBM */
-    double ms_bvh_build, ms_upload;                       /* rt_scene_create host build / upload */
+    double ms_bvh_build, ms_upload;                       /* rt_scene_create: BVH build (host + device, wall clock) / upload */
+    double ms_bvh_device;                                 /* device time of the GPU BLAS builds inside ms_bvh_build (CUDA events) */
+    int32_t bvh_device_meshes;                            /* meshes whose BLAS was built on the GPU */
+    int32_t bvh_ploc_iterations;                          /* clustering iterations of the last GPU build */
+    uint64_t bvh2_nodes;                                  /* binary twin of the BVH (rt_trace_primary, RT795_TRAVERSAL=classic) */
 } RtStats;
 
 typedef struct RtScene RtScene;   /* opaque */
@@ -264,6 +275,12 @@ int rt_tonemap(RtScene* scene, const float* in_rgb, int nx, int ny, float key, f
                float gamma, uint8_t* out_rgb8);
 
 int rt_get_stats(RtScene* scene, RtStats* out);
+
+/* Test / diagnostic aid: copies one of the scene's acceleration-structure arrays back to the host so a checker can walk it
+ * (tests/test_gpu_bvh_device.py validates the device-built trees this way).  `out` may be NULL to query the size.  Formats:
+ * csrc/bvh_build.h (BvhNode64, BvhNode128, BvhNode64Q; triangles as 3 x float4 {v0|global tri id, e1, e2}). */
+enum { RT_DEBUG_BVH2 = 0, RT_DEBUG_BVH4 = 1, RT_DEBUG_BVH4Q = 2, RT_DEBUG_TRIS = 3, RT_DEBUG_OBJ_ROOT4 = 4 };
+int rt_debug_read_bvh(RtScene* scene, int what, void* out, uint64_t capacity_bytes, uint64_t* size_bytes, int32_t* tlas_root);
 const char* rt_last_error(void);
 int rt_abi_version(void);
 /* Number of usable CUDA devices (0 if none / driver missing); never fails. */

@@ -21,6 +21,8 @@ ORACLE_REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 RT_OK = 0
 (RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_OOM, RT_ERR_IO, RT_ERR_PARSE, RT_ERR_OVERFLOW) = (-1, -2, -3, -4, -5, -6)
 RT_INTEGRATOR_REFERENCE, RT_INTEGRATOR_PATH = 0, 1
+RT_BVH_AUTO, RT_BVH_HOST_SAH, RT_BVH_DEVICE_PLOC = 0, 1, 2
+RT_DEBUG_BVH2, RT_DEBUG_BVH4, RT_DEBUG_BVH4Q, RT_DEBUG_TRIS, RT_DEBUG_OBJ_ROOT4 = 0, 1, 2, 3, 4
 RT_OBJ_SPHERE, RT_OBJ_MESH = 0, 1
 
 f3 = C.c_float * 3
@@ -74,7 +76,7 @@ class RtSceneDesc(C.Structure):
                 ("num_materials", C.c_int32), ("materials", C.POINTER(RtMaterial)),
                 ("num_textures", C.c_int32), ("textures", C.POINTER(RtTexture)),
                 ("num_images", C.c_int32), ("images", C.POINTER(RtImage)),
-                ("num_lights", C.c_int32), ("lights", C.POINTER(RtLight))]
+                ("num_lights", C.c_int32), ("lights", C.POINTER(RtLight)), ("bvh_builder", C.c_int32)]
 
 
 class RtCameraDesc(C.Structure):
@@ -104,7 +106,8 @@ class RtStats(C.Structure):
                 ("ms_raygen", C.c_double), ("ms_resolve", C.c_double),
                 ("launches_extend", C.c_uint64), ("launches_shade", C.c_uint64), ("launches_shadow", C.c_uint64),
                 ("bvh_nodes", C.c_uint64), ("bvh_bytes", C.c_uint64), ("tri_bytes", C.c_uint64),
-                ("ms_bvh_build", C.c_double), ("ms_upload", C.c_double)]
+                ("ms_bvh_build", C.c_double), ("ms_upload", C.c_double), ("ms_bvh_device", C.c_double),
+                ("bvh_device_meshes", C.c_int32), ("bvh_ploc_iterations", C.c_int32), ("bvh2_nodes", C.c_uint64)]
 
 
 HIT_DTYPE = np.dtype([("full", "<i4"), ("object", "<i4"), ("primitive", "<i4"), ("t", "<f4"),
@@ -112,7 +115,7 @@ HIT_DTYPE = np.dtype([("full", "<i4"), ("object", "<i4"), ("primitive", "<i4"), 
 
 # every symbol include/rt795.h declares (tests/test_abi.py asserts the library exports all of them)
 CORE_SYMBOLS = ["rt_scene_create", "rt_scene_destroy", "rt_render", "rt_render_device", "rt_trace_primary", "rt_tonemap",
-                "rt_get_stats", "rt_last_error", "rt_abi_version", "rt_device_count", "rt_host_load_scene",
+                "rt_get_stats", "rt_debug_read_bvh", "rt_last_error", "rt_abi_version", "rt_device_count", "rt_host_load_scene",
                 "rt_host_free_scene", "rt_host_scene_desc", "rt_host_num_cameras", "rt_host_camera",
                 "rt_host_camera_image_name", "rt_host_save_image", "rt_host_save_f32"]
 
@@ -144,6 +147,7 @@ def load_core() -> C.CDLL:
         lib.rt_trace_primary.argtypes = [C.c_void_p, P(RtCameraDesc), C.c_void_p]
         lib.rt_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
         lib.rt_get_stats.argtypes = [C.c_void_p, P(RtStats)]
+        lib.rt_debug_read_bvh.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, P(C.c_uint64), P(C.c_int32)]
         lib.rt_last_error.restype = C.c_char_p
         lib.rt_host_load_scene.argtypes = [C.c_char_p, P(C.c_void_p)]
         lib.rt_host_free_scene.argtypes = [C.c_void_p]
@@ -232,9 +236,16 @@ class HostScene:
 class Scene:
     """rt_scene_create / rt_render / rt_trace_primary on one CUDA device."""
 
-    def __init__(self, desc, device: int = 0):
+    def __init__(self, desc, device: int = 0, bvh_builder: Optional[int] = None):
         self.lib = load_core()
         self.h = C.c_void_p()
+        if bvh_builder is not None:                               # same scene, another RT_BVH_* builder: shallow copy of the descriptor
+            src = desc.contents if hasattr(desc, "contents") else desc
+            d = RtSceneDesc()
+            C.memmove(C.byref(d), C.byref(src), C.sizeof(RtSceneDesc))
+            d.bvh_builder = bvh_builder
+            self._desc = d
+            desc = C.byref(d)
         _check(self.lib.rt_scene_create(desc, device, C.byref(self.h)))
 
     def render(self, cam: RtCameraDesc, opts: Optional[RtRenderOpts] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
@@ -259,6 +270,15 @@ class Scene:
         out = np.empty((ny, nx, 3), dtype=np.uint8)
         _check(self.lib.rt_tonemap(self.h, rgb.ctypes.data, nx, ny, key, burn, saturation, gamma, out.ctypes.data))
         return out
+
+    def read_bvh(self, what: int):
+        """(array, tlas_root): one acceleration-structure array as float32 (nodes, triangles) / uint32 (quantised nodes) / int32 rows."""
+        size, root = C.c_uint64(0), C.c_int32(0)
+        _check(self.lib.rt_debug_read_bvh(self.h, what, None, 0, C.byref(size), C.byref(root)))
+        buf = np.empty(size.value // 4, dtype=np.uint32)
+        _check(self.lib.rt_debug_read_bvh(self.h, what, buf.ctypes.data, buf.nbytes, C.byref(size), C.byref(root)))
+        row = {RT_DEBUG_BVH2: 16, RT_DEBUG_BVH4: 32, RT_DEBUG_BVH4Q: 16, RT_DEBUG_TRIS: 12, RT_DEBUG_OBJ_ROOT4: 1}[what]
+        return buf.reshape(-1, row), int(root.value)
 
     def stats(self) -> RtStats:
         s = RtStats()

@@ -1,4 +1,5 @@
 #include "bvh_build.h"
+#include "bvh_quant.h"
 
 #include <algorithm>
 #include <cmath>
@@ -261,47 +262,7 @@ void CollapseToBvh4(const BuiltBvh& b2, BuiltBvh4* out) {
 
 void QuantiseBvh4(const BuiltBvh4& b4, std::vector<BvhNode64Q>* out) {
     out->assign(b4.nodes.size(), BvhNode64Q());
-    for (size_t i = 0; i < b4.nodes.size(); i++) {
-        const BvhNode128& n = b4.nodes[i];
-        BvhNode64Q& q = (*out)[i];
-        memset(&q, 0, sizeof q);
-        int32_t ref[4]; bool has[4];
-        float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-        for (int k = 0; k < 4; k++) {
-            memcpy(&ref[k], &n.q[24 + k], 4);
-            has[k] = ref[k] != kNoChild;
-            if (!has[k]) continue;
-            for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], n.q[a * 8 + k]); hi[a] = std::max(hi[a], n.q[a * 8 + 4 + k]); }
-        }
-        float scale[3];
-        uint8_t qlo[3][4], qhi[3][4];
-        for (int a = 0; a < 3; a++) {
-            if (!(hi[a] >= lo[a])) { lo[a] = 0.f; hi[a] = 0.f; }
-            float ext = hi[a] - lo[a];
-            int e;
-            std::frexp(ext > 0.f ? ext / 255.0f : 1e-30f, &e);          // ext/255 = m * 2^e, m in [0.5, 1)  ->  2^e >= ext/255
-            for (;; e++) {                                                 // grow the grid until every plane fits in a byte
-                float sc = std::ldexp(1.0f, e);
-                bool ok = true;
-                for (int k = 0; k < 4 && ok; k++) {
-                    if (!has[k]) { qlo[a][k] = 255; qhi[a][k] = 0; continue; }
-                    float clo = n.q[a * 8 + k], chi = n.q[a * 8 + 4 + k];
-                    int l = (int)std::floor((clo - lo[a]) / sc), h = (int)std::ceil((chi - lo[a]) / sc);
-                    l = std::max(0, std::min(255, l));
-                    while (l > 0 && lo[a] + (float)l * sc > clo) l--;        // decoded in float exactly as the kernel does: stay conservative
-                    while (h < 256 && lo[a] + (float)h * sc < chi) h++;
-                    if (h > 255 || lo[a] + (float)l * sc > clo) { ok = false; break; }
-                    qlo[a][k] = (uint8_t)l; qhi[a][k] = (uint8_t)h;
-                }
-                if (ok) { scale[a] = sc; break; }
-            }
-        }
-        auto pack = [](const uint8_t* b) { return (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24); };
-        memcpy(&q.w[0], &lo[0], 4); memcpy(&q.w[1], &lo[1], 4); memcpy(&q.w[2], &lo[2], 4); memcpy(&q.w[3], &scale[2], 4);
-        for (int k = 0; k < 4; k++) memcpy(&q.w[4 + k], &ref[k], 4);
-        q.w[8] = pack(qlo[0]); q.w[9] = pack(qlo[1]); q.w[10] = pack(qlo[2]); q.w[11] = pack(qhi[0]);
-        q.w[12] = pack(qhi[1]); q.w[13] = pack(qhi[2]); memcpy(&q.w[14], &scale[0], 4); memcpy(&q.w[15], &scale[1], 4);
-    }
+    for (size_t i = 0; i < b4.nodes.size(); i++) QuantiseNode4(b4.nodes[i].q, (*out)[i].w, kNoChild);
 }
 
 }  // namespace rt795

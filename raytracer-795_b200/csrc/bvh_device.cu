@@ -1,0 +1,508 @@
+// D1: device BLAS builder - see bvh_device.h for the pipeline.  sm_100a only.
+#include "bvh_device.h"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "bvh_quant.h"
+
+namespace rt795 {
+namespace {
+
+#define BCK(x)                                                                                                          \
+    do {                                                                                                                \
+        cudaError_t e_ = (x);                                                                                           \
+        if (e_ != cudaSuccess) throw std::runtime_error(std::string("bvh_device: ") + #x + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+constexpr int kPlocRadius = 16;          // nearest-neighbour search window (+-) in the Morton-ordered cluster array (RT795_PLOC_RADIUS overrides, <= kMaxPlocRadius)
+constexpr int kMaxPlocRadius = 64;
+constexpr int kTB = 256;
+constexpr int kMaxPlocIterations = 4096; // a healthy build of 1 M triangles takes ~40; beyond the cap the host builder takes over
+constexpr int kCntMask = 0x3fffffff, kLeafBit = 0x40000000;
+enum { CTR_QOUT = 0, CTR_ALLOC = 1, CTR_STACK = 2, CTR_DEPTH = 3, CTR_N = 4 };
+
+inline int Grid(long long n) { return (int)((n + kTB - 1) / kTB); }
+
+// One cudaMalloc for all temporaries: Reserve() records, Commit() allocates and hands the pointers out.
+class Arena {
+public:
+    template <class T> void Reserve(T** slot, size_t n) {
+        off_ = (off_ + 255) & ~(size_t)255;
+        recs_.push_back({reinterpret_cast<void**>(slot), off_});
+        off_ += (n ? n : 1) * sizeof(T);
+    }
+    void Commit() {
+        BCK(cudaMalloc(&base_, off_ ? off_ : 256));
+        for (auto& r : recs_) *r.slot = static_cast<char*>(base_) + r.off;
+    }
+    ~Arena() { if (base_) cudaFree(base_); }
+private:
+    struct Rec { void** slot; size_t off; };
+    std::vector<Rec> recs_;
+    size_t off_ = 0;
+    void* base_ = nullptr;
+};
+
+__device__ __forceinline__ float3 f3(float4 v) { return make_float3(v.x, v.y, v.z); }
+__device__ __forceinline__ float3 min3(float3 a, float3 b) { return make_float3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
+__device__ __forceinline__ float3 max3(float3 a, float3 b) { return make_float3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
+__device__ __forceinline__ float half_area(float3 lo, float3 hi) {
+    float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+// float min/max atomics on the ordered-integer view of IEEE floats (target initialised to +-3e38)
+__device__ __forceinline__ void atomic_min_f(float* a, float v) {
+    if (v >= 0.f) atomicMin(reinterpret_cast<int*>(a), __float_as_int(v)); else atomicMax(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* a, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(a), __float_as_int(v)); else atomicMin(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+
+// ---- B1: padded triangle boxes + bounds of their centres
+__global__ void __launch_bounds__(kTB) k_prim_bounds(const float* __restrict__ v, const int32_t* __restrict__ ix, int n, float eps,
+                                                     float4* __restrict__ plo, float4* __restrict__ phi, float* cb) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float3 cmin = make_float3(3.0e38f, 3.0e38f, 3.0e38f), cmax = make_float3(-3.0e38f, -3.0e38f, -3.0e38f);
+    if (i < n) {
+        float3 lo = cmin, hi = cmax;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float* p = v + 3 * (size_t)ix[3 * (size_t)i + k];
+            float3 q = make_float3(p[0], p[1], p[2]);
+            lo = min3(lo, q); hi = max3(hi, q);
+        }
+        float ext = fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z));
+        // same rule as the host builder (core.cu BuildAndUpload): the reference accepts beta, gamma >= -eps, i.e. hits up to
+        // eps*edge outside the triangle, so the box is padded to stay conservative
+        float px = 2.0f * eps * ext + 4.0e-7f * fmaxf(fabsf(lo.x), fabsf(hi.x)) + 1e-30f;
+        float py = 2.0f * eps * ext + 4.0e-7f * fmaxf(fabsf(lo.y), fabsf(hi.y)) + 1e-30f;
+        float pz = 2.0f * eps * ext + 4.0e-7f * fmaxf(fabsf(lo.z), fabsf(hi.z)) + 1e-30f;
+        lo = make_float3(lo.x - px, lo.y - py, lo.z - pz);
+        hi = make_float3(hi.x + px, hi.y + py, hi.z + pz);
+        plo[i] = make_float4(lo.x, lo.y, lo.z, 0.f);
+        phi[i] = make_float4(hi.x, hi.y, hi.z, 0.f);
+        cmin = cmax = make_float3(0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z));
+    }
+    const unsigned full = 0xffffffffu;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        cmin.x = fminf(cmin.x, __shfl_xor_sync(full, cmin.x, s)); cmin.y = fminf(cmin.y, __shfl_xor_sync(full, cmin.y, s)); cmin.z = fminf(cmin.z, __shfl_xor_sync(full, cmin.z, s));
+        cmax.x = fmaxf(cmax.x, __shfl_xor_sync(full, cmax.x, s)); cmax.y = fmaxf(cmax.y, __shfl_xor_sync(full, cmax.y, s)); cmax.z = fmaxf(cmax.z, __shfl_xor_sync(full, cmax.z, s));
+    }
+    if ((threadIdx.x & 31) == 0 && cmin.x <= cmax.x) {
+        atomic_min_f(cb + 0, cmin.x); atomic_min_f(cb + 1, cmin.y); atomic_min_f(cb + 2, cmin.z);
+        atomic_max_f(cb + 3, cmax.x); atomic_max_f(cb + 4, cmax.y); atomic_max_f(cb + 5, cmax.z);
+    }
+}
+
+// ---- B2: 63-bit Morton key of the box centre
+__device__ __forceinline__ unsigned long long spread21(unsigned long long x) {
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+__global__ void __launch_bounds__(kTB) k_morton(const float4* __restrict__ plo, const float4* __restrict__ phi, int n, const float* __restrict__ cb,
+                                                unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 lo = plo[i], hi = phi[i];
+    float c[3] = {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
+    unsigned long long q[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        float ext = cb[3 + a] - cb[a];
+        float t = ext > 0.f ? (c[a] - cb[a]) / ext : 0.f;
+        t = fminf(fmaxf(t, 0.f), 1.f);
+        q[a] = (unsigned long long)fminf(t * 2097152.0f, 2097151.0f);
+    }
+    keys[i] = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+    vals[i] = (uint32_t)i;
+}
+
+// ---- B3: PLOC.  Cluster i = (box, node id in lo.w).  Leaves are nodes 0..n-1 in Morton order, inner nodes n..2n-2.
+__global__ void __launch_bounds__(kTB) k_init_clusters(const uint32_t* __restrict__ vals, const float4* __restrict__ plo, const float4* __restrict__ phi, int n,
+                                                       float4* __restrict__ clo, float4* __restrict__ chi, float4* __restrict__ nlo, float4* __restrict__ nhi,
+                                                       int32_t* __restrict__ parent, int32_t* __restrict__ meta, float* __restrict__ cst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t p = vals[i];
+    float4 lo = plo[p], hi = phi[p];
+    lo.w = __int_as_float(i);
+    clo[i] = lo; chi[i] = hi; nlo[i] = lo; nhi[i] = hi;
+    parent[i] = -1; meta[i] = 1 | kLeafBit; cst[i] = 1.0f;
+}
+
+// Nearest neighbour of every cluster inside the window, under the symmetric total order on pairs
+// (merged half-area, not-buddy, min index, max index) - "buddy" = index ^ 1.  Symmetry guarantees that the globally
+// smallest pair is mutual, so every iteration merges at least one pair; the buddy preference makes runs of identical
+// boxes (all distances tie) pair up instead of chaining.
+__global__ void __launch_bounds__(kTB) k_nearest(const float4* __restrict__ clo, const float4* __restrict__ chi, int m, int radius, int32_t* __restrict__ nn) {
+    __shared__ float4 slo[kTB + 2 * kMaxPlocRadius], shi[kTB + 2 * kMaxPlocRadius];
+    int base = blockIdx.x * kTB - radius;
+    for (int t = threadIdx.x; t < kTB + 2 * radius; t += kTB) {
+        int g = base + t;
+        if (g >= 0 && g < m) { slo[t] = clo[g]; shi[t] = chi[g]; }
+    }
+    __syncthreads();
+    int i = blockIdx.x * kTB + threadIdx.x;
+    if (i >= m) return;
+    float3 lo = f3(slo[threadIdx.x + radius]), hi = f3(shi[threadIdx.x + radius]);
+    float best = 3.4e38f;
+    int bestj = -1;
+#pragma unroll 4
+    for (int d = -radius; d <= radius; d++) {
+        int j = i + d;
+        if (d == 0 || j < 0 || j >= m) continue;
+        int t = threadIdx.x + radius + d;
+        float a = half_area(min3(lo, f3(slo[t])), max3(hi, f3(shi[t])));
+        if (a < best || (a == best && j == (i ^ 1))) { best = a; bestj = j; }
+    }
+    nn[i] = bestj;
+}
+
+__global__ void __launch_bounds__(kTB) k_merge_flags(const int32_t* __restrict__ nn, int m, unsigned long long* __restrict__ flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    int j = nn[i];
+    bool mutual = j >= 0 && nn[j] == i;
+    unsigned long long keep = !(mutual && i > j), merge = mutual && i < j;
+    flags[i] = (keep << 32) | merge;                                  // one scan yields the compacted position and the new node id
+}
+
+__global__ void __launch_bounds__(kTB) k_merge_emit(const float4* __restrict__ clo, const float4* __restrict__ chi, const int32_t* __restrict__ nn,
+                                                    const unsigned long long* __restrict__ flags, const unsigned long long* __restrict__ scan, int m, int next_id,
+                                                    float4* __restrict__ clo_out, float4* __restrict__ chi_out, float4* __restrict__ nlo, float4* __restrict__ nhi,
+                                                    int2* __restrict__ child, int32_t* __restrict__ parent, int32_t* __restrict__ meta, float* __restrict__ cst,
+                                                    uint32_t* __restrict__ totals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    unsigned long long f = flags[i], s = scan[i];
+    uint32_t keep = (uint32_t)(f >> 32), merge = (uint32_t)(f & 1u);
+    if (i == m - 1) { totals[0] = (uint32_t)(s >> 32) + keep; totals[1] = (uint32_t)(s & 0xffffffffu) + merge; }
+    if (!keep) return;
+    float4 lo = clo[i], hi = chi[i];
+    if (merge) {
+        int j = nn[i];
+        float4 lo2 = clo[j], hi2 = chi[j];
+        int l = __float_as_int(lo.w), r = __float_as_int(lo2.w);
+        int id = next_id + (int)(s & 0xffffffffu);
+        float3 ulo = min3(f3(lo), f3(lo2)), uhi = max3(f3(hi), f3(hi2));
+        float area = half_area(ulo, uhi), al = half_area(f3(lo), f3(hi)), ar = half_area(f3(lo2), f3(hi2));
+        int c = (meta[l] & kCntMask) + (meta[r] & kCntMask);
+        // SAH, bottom-up: cost(node) = min(#triangles if <= 4, 1 + sum_child area_child / area * cost(child)) - the host builder's
+        // constants (traversal 1, intersection 1, bvh_build.cpp) and leaf rule
+        float split = area > 0.f ? 1.0f + (al * cst[l] + ar * cst[r]) / area : 3.0e38f;
+        split = fminf(split, 3.0e38f);
+        bool leaf = c <= 4 && (float)c <= split;
+        cst[id] = leaf ? (float)c : split;
+        meta[id] = c | (leaf ? kLeafBit : 0);
+        child[id] = make_int2(l, r);
+        parent[l] = id; parent[r] = id; parent[id] = -1;
+        lo = make_float4(ulo.x, ulo.y, ulo.z, __int_as_float(id));
+        hi = make_float4(uhi.x, uhi.y, uhi.z, 0.f);
+        nlo[id] = lo; nhi[id] = hi;
+    }
+    uint32_t pos = (uint32_t)(s >> 32);
+    clo_out[pos] = lo; chi_out[pos] = hi;
+}
+
+// ---- B4: one walk to the root per node: DFS offset of its first triangle, state (0 live inner, 1 leaf of the final tree, 2 buried
+// inside a collapsed leaf), depth
+__global__ void __launch_bounds__(kTB) k_layout(int total, const int32_t* __restrict__ parent, const int2* __restrict__ child, const int32_t* __restrict__ meta,
+                                                int32_t* __restrict__ first, uint8_t* __restrict__ state, int32_t* ctr) {
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    int depth = 0;
+    if (id < total) {
+        int off = 0, cur = id;
+        bool buried = false;
+        for (int p = parent[cur]; p >= 0; p = parent[cur]) {
+            int2 ch = child[p];
+            int mp = meta[p];
+            if (ch.y == cur) off += meta[ch.x] & kCntMask;
+            buried |= (mp & kLeafBit) != 0;
+            cur = p; depth++;
+        }
+        first[id] = off;
+        uint8_t st = buried ? 2 : ((meta[id] & kLeafBit) ? 1 : 0);
+        state[id] = st;
+        if (st == 2) depth = 0;
+    }
+    int wmax = __reduce_max_sync(0xffffffffu, depth);
+    if ((threadIdx.x & 31) == 0 && wmax > 0) atomicMax(&ctr[CTR_DEPTH], wmax);
+}
+
+// ---- B5
+__global__ void __launch_bounds__(kTB) k_emit_tris(int n, const int32_t* __restrict__ first, const uint32_t* __restrict__ vals, const float* __restrict__ v,
+                                                   const int32_t* __restrict__ ix, int first_tri, float4* __restrict__ tris) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t p = vals[i];
+    const int32_t* t = ix + 3 * (size_t)p;
+    const float *a = v + 3 * (size_t)t[0], *b = v + 3 * (size_t)t[1], *c = v + 3 * (size_t)t[2];
+    float4* o = tris + 3 * (size_t)first[i];
+    o[0] = make_float4(a[0], a[1], a[2], __int_as_float(first_tri + (int)p));
+    o[1] = make_float4(b[0] - a[0], b[1] - a[1], b[2] - a[2], 0.f);
+    o[2] = make_float4(c[0] - a[0], c[1] - a[1], c[2] - a[2], 0.f);
+}
+
+__global__ void __launch_bounds__(kTB) k_live_flags(int n, const uint8_t* __restrict__ state, int32_t* __restrict__ live) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n - 1) live[t] = state[n + t] == 0 ? 1 : 0;
+}
+
+__device__ __forceinline__ int32_t encode_leaf(int32_t first, int32_t count) { return ~((first << 3) | (count - 1)); }
+
+// Binary nodes in reverse creation order (the root, created last, becomes node 0; nodes merged in the same PLOC iteration
+// are neighbours on the Morton curve and stay neighbours in memory).
+__global__ void __launch_bounds__(kTB) k_emit_bvh2(int n, int live_total, const int32_t* __restrict__ live, const int32_t* __restrict__ lscan,
+                                                   const int2* __restrict__ child, const uint8_t* __restrict__ state, const int32_t* __restrict__ first,
+                                                   const int32_t* __restrict__ meta, const float4* __restrict__ nlo, const float4* __restrict__ nhi,
+                                                   int node_base, int tri_base, float4* __restrict__ nodes2) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n - 1 || !live[t]) return;
+    int idx = live_total - 1 - lscan[t];
+    int2 ch = child[n + t];
+    int c[2] = {ch.x, ch.y};
+    int32_t ref[2];
+    float4 lo[2], hi[2];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        lo[s] = nlo[c[s]]; hi[s] = nhi[c[s]];
+        ref[s] = state[c[s]] == 1 ? encode_leaf(tri_base + first[c[s]], meta[c[s]] & kCntMask) : node_base + (live_total - 1 - lscan[c[s] - n]);
+    }
+    float4* o = nodes2 + 4 * (size_t)idx;
+    o[0] = make_float4(lo[0].x, hi[0].x, lo[0].y, hi[0].y);
+    o[1] = make_float4(lo[1].x, hi[1].x, lo[1].y, hi[1].y);
+    o[2] = make_float4(lo[0].z, hi[0].z, lo[1].z, hi[1].z);
+    o[3] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), 0.f, 0.f);
+}
+
+// ---- B6: one level of the BVH2 -> BVH4 collapse.  Item = (binary node id, 4-wide node index, stack entries above it).
+__global__ void __launch_bounds__(kTB) k_collapse4(const int4* __restrict__ items, int n_items, int4* __restrict__ items_out, int32_t* ctr,
+                                                   const int2* __restrict__ child, const uint8_t* __restrict__ state, const int32_t* __restrict__ first,
+                                                   const int32_t* __restrict__ meta, const float4* __restrict__ nlo, const float4* __restrict__ nhi,
+                                                   int node4_base, int tri_base, float4* __restrict__ nodes4) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_items) return;
+    int4 it = items[t];
+    int c[4];
+    int nc = 2;
+    { int2 ch = child[it.x]; c[0] = ch.x; c[1] = ch.y; }
+    while (nc < 4) {                                                  // open the largest inner child until four (as CollapseToBvh4)
+        int best = -1;
+        float barea = -1.f;
+        for (int k = 0; k < nc; k++) {
+            if (state[c[k]] != 0) continue;
+            float a = half_area(f3(nlo[c[k]]), f3(nhi[c[k]]));
+            if (a > barea) { barea = a; best = k; }
+        }
+        if (best < 0) break;
+        int2 sub = child[c[best]];
+        for (int k = best; k < nc - 1; k++) c[k] = c[k + 1];
+        c[nc - 1] = sub.x; c[nc] = sub.y;
+        nc++;
+    }
+    int stack_here = it.z + nc - 1;
+    atomicMax(&ctr[CTR_STACK], stack_here);
+    float q[32];
+#pragma unroll
+    for (int k = 0; k < 32; k++) q[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int32_t ref = kNoChild;
+        if (k < nc) {
+            float4 lo = nlo[c[k]], hi = nhi[c[k]];
+            q[0 + k] = lo.x; q[4 + k] = hi.x; q[8 + k] = lo.y; q[12 + k] = hi.y; q[16 + k] = lo.z; q[20 + k] = hi.z;
+            if (state[c[k]] == 1) {
+                ref = encode_leaf(tri_base + first[c[k]], meta[c[k]] & kCntMask);
+            } else {
+                int idx4 = atomicAdd(&ctr[CTR_ALLOC], 1);
+                int slot = atomicAdd(&ctr[CTR_QOUT], 1);
+                items_out[slot] = make_int4(c[k], idx4, stack_here, 0);
+                ref = node4_base + idx4;
+            }
+        }
+        q[24 + k] = __int_as_float(ref);
+    }
+    float4* o = nodes4 + 8 * (size_t)it.y;
+#pragma unroll
+    for (int k = 0; k < 8; k++) o[k] = make_float4(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
+}
+
+// ---- B7
+__global__ void __launch_bounds__(kTB) k_quantise4(const float4* __restrict__ nodes4, int n4, uint4* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float q[32];
+    uint32_t w[16];
+    const float4* in = nodes4 + 8 * (size_t)i;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { float4 v = in[k]; q[4 * k] = v.x; q[4 * k + 1] = v.y; q[4 * k + 2] = v.z; q[4 * k + 3] = v.w; }
+    QuantiseNode4(q, w, kNoChild);
+    uint4* o = out + 4 * (size_t)i;
+#pragma unroll
+    for (int k = 0; k < 4; k++) o[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+}
+
+}  // namespace
+
+void FreeDeviceBlas(DeviceBlas* b) {
+    if (!b) return;
+    if (b->nodes2) cudaFree(b->nodes2);
+    if (b->nodes4) cudaFree(b->nodes4);
+    if (b->nodes4q) cudaFree(b->nodes4q);
+    if (b->tris) cudaFree(b->tris);
+    *b = DeviceBlas();
+}
+
+bool BuildBlasOnDevice(const float* d_vertices, const int32_t* d_tri_idx, int first_tri, int tri_count, float int_test_eps,
+                       int node_base, int node4_base, int tri_base, int max_depth2, int max_stack4, cudaStream_t st, DeviceBlas* out) {
+    *out = DeviceBlas();
+    const int n = tri_count;
+    if (n < 8) throw std::runtime_error("bvh_device: tri_count must be >= 8");
+    const int total = 2 * n - 1;
+    const int32_t* ix = d_tri_idx + 3 * (size_t)first_tri;
+
+    // ---- temporaries
+    float4 *plo, *phi, *clo[2], *chi[2], *nlo, *nhi;
+    unsigned long long *keys[2], *flags, *scan;
+    uint32_t *vals[2], *totals;
+    int32_t *nn, *parent, *meta, *first, *live, *lscan, *ctr;
+    float *cst, *cb;
+    int2* child;
+    uint8_t* state;
+    int4* items[2];
+    void* cub_tmp;
+    size_t sort_bytes = 0, scan64_bytes = 0, scan32_bytes = 0;
+    BCK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, 63, st));
+    BCK(cub::DeviceScan::ExclusiveSum(nullptr, scan64_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, n, st));
+    BCK(cub::DeviceScan::ExclusiveSum(nullptr, scan32_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, n, st));
+    size_t cub_bytes = std::max(sort_bytes, std::max(scan64_bytes, scan32_bytes));
+    Arena ar;
+    ar.Reserve(&plo, n); ar.Reserve(&phi, n);
+    for (int k = 0; k < 2; k++) { ar.Reserve(&clo[k], n); ar.Reserve(&chi[k], n); ar.Reserve(&keys[k], n); ar.Reserve(&vals[k], n); ar.Reserve(&items[k], n); }
+    ar.Reserve(&nlo, total); ar.Reserve(&nhi, total); ar.Reserve(&child, total); ar.Reserve(&parent, total); ar.Reserve(&meta, total);
+    ar.Reserve(&cst, total); ar.Reserve(&first, total); ar.Reserve(&state, total);
+    ar.Reserve(&nn, n); ar.Reserve(&flags, n); ar.Reserve(&scan, n); ar.Reserve(&live, n); ar.Reserve(&lscan, n);
+    ar.Reserve(&totals, 2); ar.Reserve(&ctr, CTR_N); ar.Reserve(&cb, 6);
+    ar.Reserve((char**)&cub_tmp, cub_bytes);
+    ar.Commit();
+
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    struct Ev { cudaEvent_t& a; cudaEvent_t& b; ~Ev() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } ev_guard{e0, e1};
+    BCK(cudaEventCreate(&e0)); BCK(cudaEventCreate(&e1));
+    BCK(cudaEventRecord(e0, st));
+    auto run = [&]() -> bool {                                       // false: refused (caller falls back to the host builder)
+        // B1, B2
+        const float cb_init[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
+        BCK(cudaMemcpyAsync(cb, cb_init, sizeof cb_init, cudaMemcpyHostToDevice, st));
+        k_prim_bounds<<<Grid(n), kTB, 0, st>>>(d_vertices, ix, n, int_test_eps, plo, phi, cb);
+        k_morton<<<Grid(n), kTB, 0, st>>>(plo, phi, n, cb, keys[0], vals[0]);
+        BCK(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, keys[0], keys[1], vals[0], vals[1], n, 0, 63, st));
+        const uint32_t* order = vals[1];
+        k_init_clusters<<<Grid(n), kTB, 0, st>>>(order, plo, phi, n, clo[0], chi[0], nlo, nhi, parent, meta, cst);
+
+        // B3
+        int m = n, next_id = n, cur = 0, iters = 0;
+        int radius = kPlocRadius;
+        if (const char* e = getenv("RT795_PLOC_RADIUS")) radius = std::min(kMaxPlocRadius, std::max(1, atoi(e)));
+        while (m > 1) {
+            if (++iters > kMaxPlocIterations) return false;
+            k_nearest<<<Grid(m), kTB, 0, st>>>(clo[cur], chi[cur], m, radius, nn);
+            k_merge_flags<<<Grid(m), kTB, 0, st>>>(nn, m, flags);
+            BCK(cub::DeviceScan::ExclusiveSum(cub_tmp, scan64_bytes, flags, scan, m, st));
+            k_merge_emit<<<Grid(m), kTB, 0, st>>>(clo[cur], chi[cur], nn, flags, scan, m, next_id, clo[cur ^ 1], chi[cur ^ 1], nlo, nhi, child, parent, meta, cst, totals);
+            uint32_t h_tot[2] = {0, 0};
+            BCK(cudaMemcpyAsync(h_tot, totals, sizeof h_tot, cudaMemcpyDeviceToHost, st));
+            BCK(cudaStreamSynchronize(st));
+            if ((int)h_tot[0] >= m || h_tot[1] == 0) return false;     // no progress (NaN boxes): leave it to the host builder
+            m = (int)h_tot[0]; next_id += (int)h_tot[1]; cur ^= 1;
+        }
+        out->ploc_iterations = iters;
+        if (next_id != total) throw std::runtime_error("bvh_device: node count mismatch after clustering");
+        const int root = total - 1;
+
+        // B4
+        BCK(cudaMemsetAsync(ctr, 0, CTR_N * sizeof(int32_t), st));
+        k_layout<<<Grid(total), kTB, 0, st>>>(total, parent, child, meta, first, state, ctr);
+        // B5
+        BCK(cudaMalloc((void**)&out->tris, (size_t)n * 3 * sizeof(float4)));
+        k_emit_tris<<<Grid(n), kTB, 0, st>>>(n, first, order, d_vertices, ix, first_tri, out->tris);
+        k_live_flags<<<Grid(n - 1), kTB, 0, st>>>(n, state, live);
+        BCK(cub::DeviceScan::ExclusiveSum(cub_tmp, scan32_bytes, live, lscan, n - 1, st));
+        int32_t h_last[2] = {0, 0}, h_ctr[CTR_N];
+        BCK(cudaMemcpyAsync(&h_last[0], live + (n - 2), 4, cudaMemcpyDeviceToHost, st));
+        BCK(cudaMemcpyAsync(&h_last[1], lscan + (n - 2), 4, cudaMemcpyDeviceToHost, st));
+        BCK(cudaMemcpyAsync(h_ctr, ctr, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
+        float h_root[8];
+        BCK(cudaMemcpyAsync(h_root, nlo + root, 16, cudaMemcpyDeviceToHost, st));
+        BCK(cudaMemcpyAsync(h_root + 4, nhi + root, 16, cudaMemcpyDeviceToHost, st));
+        BCK(cudaStreamSynchronize(st));
+        const int live_total = h_last[0] + h_last[1];
+        out->depth2 = h_ctr[CTR_DEPTH];
+        for (int k = 0; k < 3; k++) { out->bounds.lo[k] = h_root[k]; out->bounds.hi[k] = h_root[4 + k]; }
+        if (live_total < 1) throw std::runtime_error("bvh_device: root collapsed into a leaf");
+        if (out->depth2 > max_depth2) return false;
+        out->n2 = live_total;
+        BCK(cudaMalloc((void**)&out->nodes2, (size_t)live_total * 4 * sizeof(float4)));
+        k_emit_bvh2<<<Grid(n - 1), kTB, 0, st>>>(n, live_total, live, lscan, child, state, first, meta, nlo, nhi, node_base, tri_base, out->nodes2);
+
+        // B6: every 4-wide node is a distinct live binary node, so live_total bounds their number
+        BCK(cudaMalloc((void**)&out->nodes4, (size_t)live_total * 8 * sizeof(float4)));
+        {
+            int4 root_item = make_int4(root, 0, 0, 0);
+            BCK(cudaMemcpyAsync(items[0], &root_item, sizeof root_item, cudaMemcpyHostToDevice, st));
+            int32_t init_ctr[CTR_N] = {0, 1, 0, h_ctr[CTR_DEPTH]};
+            BCK(cudaMemcpyAsync(ctr, init_ctr, sizeof init_ctr, cudaMemcpyHostToDevice, st));
+            int n_items = 1, q = 0;
+            while (n_items > 0) {
+                k_collapse4<<<Grid(n_items), kTB, 0, st>>>(items[q], n_items, items[q ^ 1], ctr, child, state, first, meta, nlo, nhi, node4_base, tri_base, out->nodes4);
+                BCK(cudaMemcpyAsync(h_ctr, ctr, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
+                BCK(cudaMemsetAsync(ctr + CTR_QOUT, 0, sizeof(int32_t), st));
+                BCK(cudaStreamSynchronize(st));
+                n_items = h_ctr[CTR_QOUT]; q ^= 1;
+            }
+            out->n4 = h_ctr[CTR_ALLOC];
+            out->max_stack4 = h_ctr[CTR_STACK];
+            if (out->n4 > live_total) throw std::runtime_error("bvh_device: 4-wide node count exceeds its bound");
+            if (out->max_stack4 > max_stack4) return false;
+        }
+        // B7
+        BCK(cudaMalloc((void**)&out->nodes4q, (size_t)out->n4 * 4 * sizeof(uint4)));
+        k_quantise4<<<Grid(out->n4), kTB, 0, st>>>(out->nodes4, out->n4, out->nodes4q);
+        BCK(cudaEventRecord(e1, st));
+        BCK(cudaStreamSynchronize(st));
+        BCK(cudaGetLastError());
+        BCK(cudaEventElapsedTime(&out->ms, e0, e1));
+        out->tri_count = n;
+        return true;
+    };
+    bool ok = false;
+    try {
+        ok = run();
+    } catch (...) {
+        cudaStreamSynchronize(st);
+        FreeDeviceBlas(out);
+        throw;
+    }
+    if (!ok) {
+        cudaStreamSynchronize(st);
+        int iters = out->ploc_iterations, d2 = out->depth2, s4 = out->max_stack4;
+        FreeDeviceBlas(out);
+        out->ploc_iterations = iters; out->depth2 = d2; out->max_stack4 = s4;   // why it was refused, for the caller's log
+    }
+    return ok;
+}
+
+}  // namespace rt795

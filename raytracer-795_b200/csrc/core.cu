@@ -7,6 +7,7 @@
 // There is no CPU rendering path in this library.
 #include "../../include/rt795.h"
 #include "bvh_build.h"
+#include "bvh_device.h"
 #include "kernels.cuh"
 
 #include <algorithm>
@@ -183,92 +184,111 @@ void Validate(const RtSceneDesc* s) {
         if (l.type < RT_LIGHT_POINT || l.type > RT_LIGHT_ENVIRONMENT) bad("unknown light type");
         if (l.type == RT_LIGHT_ENVIRONMENT && (l.image < 0 || l.image >= s->num_images)) bad("environment light image index out of range");
     }
+    if (s->bvh_builder < RT_BVH_AUTO || s->bvh_builder > RT_BVH_DEVICE_PLOC) bad("bvh_builder must be one of RT_BVH_*");
     if (s->env_light_index < -1 || s->env_light_index >= s->num_lights) bad("env_light_index out of range");
     if (s->background_texture < -1 || s->background_texture >= s->num_textures) bad("background_texture out of range");
 }
 
-void BuildAndUpload(RtScene* sc, const RtSceneDesc* s) {
+constexpr int kDeviceBuildMinTris = 32768;   // RT_BVH_AUTO: smaller meshes build faster on the host than the ~40 launch round trips of the device build
+
+// Returns false when device-built BLASes turned out too deep for the traversal stack: the caller retries with allow_device = false.
+bool BuildAndUpload(RtScene* sc, const RtSceneDesc* s, bool allow_device) {
     auto t0 = std::chrono::steady_clock::now();
     cudaStream_t st = sc->stream;
     const float eps = s->int_test_eps;
 
-    // ---- BLAS per mesh
-    std::vector<BvhNode64> nodes;
-    std::vector<BvhNode128> nodes4;
-    std::vector<BvhNode64Q> nodes4q;
-    std::vector<float4> tris;
+    // ---- scene-wide vertex / index arrays first: the device BLAS builder reads them
+    sc->tri_idx.Upload(s->tri_indices, (size_t)s->num_triangles * 3, st);
+    sc->vertices.Upload(s->vertices, (size_t)s->num_vertices * 3, st);
+
+    // ---- BLAS per mesh: large meshes on the device (bvh_device.cu), small ones on the host (bvh_build.cpp).  Every mesh yields
+    // one segment of each scene-wide array (binary nodes, 4-wide nodes, quantised nodes, triangles), child references already
+    // rebased to the segment's position.
+    struct MeshSeg {
+        std::vector<BvhNode64> h2; std::vector<BvhNode128> h4; std::vector<BvhNode64Q> h4q; std::vector<float4> htris;
+        DeviceBlas dev; bool on_device = false;
+        int n2 = 0, n4 = 0, ntris = 0;
+        MeshSeg() = default;
+        MeshSeg(const MeshSeg&) = delete;
+        MeshSeg(MeshSeg&& o) noexcept : h2(std::move(o.h2)), h4(std::move(o.h4)), h4q(std::move(o.h4q)), htris(std::move(o.htris)), dev(o.dev), on_device(o.on_device), n2(o.n2), n4(o.n4), ntris(o.ntris) { o.dev = DeviceBlas(); }
+        ~MeshSeg() { FreeDeviceBlas(&dev); }
+    };
+    std::vector<MeshSeg> segs;
+    segs.reserve(s->num_meshes + 1);
     std::vector<int> mesh_root(s->num_meshes, 0), mesh_depth(s->num_meshes, 0), mesh_root4(s->num_meshes, 0), mesh_stack4(s->num_meshes, 0);
     std::vector<Aabb> mesh_bounds(s->num_meshes);
-    tris.reserve((size_t)s->num_triangles * 3);
+    int n2_total = 0, n4_total = 0, tri_total = 0;
+    int builder = s->bvh_builder;
+    if (const char* e = getenv("RT795_BVH_BUILDER")) builder = !strcmp(e, "host") ? RT_BVH_HOST_SAH : !strcmp(e, "device") ? RT_BVH_DEVICE_PLOC : RT_BVH_AUTO;
+    if (!allow_device) builder = RT_BVH_HOST_SAH;
+    sc->stats.bvh_device_meshes = 0; sc->stats.ms_bvh_device = 0; sc->stats.bvh_ploc_iterations = 0;
     for (int m = 0; m < s->num_meshes; m++) {
         const RtMesh& me = s->meshes[m];
-        std::vector<Aabb> pb(me.tri_count);
-        for (int t = 0; t < me.tri_count; t++) {
-            const int* ix = s->tri_indices + 3 * (size_t)(me.first_tri + t);
-            Aabb b; b.Reset();
-            float ext = 0.f;
-            for (int k = 0; k < 3; k++) b.Grow(s->vertices + 3 * (size_t)ix[k]);
-            for (int k = 0; k < 3; k++) ext = std::max(ext, b.hi[k] - b.lo[k]);
-            // the reference accepts beta, gamma >= -eps: hits up to eps*edge outside the triangle; pad so the box stays conservative
-            for (int k = 0; k < 3; k++) {
-                float mag = std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]));
-                float pad = 2.0f * eps * ext + 4.0e-7f * mag + 1e-30f;
-                b.lo[k] -= pad; b.hi[k] += pad;
+        segs.emplace_back();
+        MeshSeg& sg = segs.back();
+        const int node_base = n2_total, base4 = n4_total, tri_base = tri_total;
+        mesh_root[m] = node_base; mesh_root4[m] = base4;
+        bool want_device = builder == RT_BVH_DEVICE_PLOC ? me.tri_count >= 8 : builder == RT_BVH_AUTO && me.tri_count >= kDeviceBuildMinTris;
+        if (want_device) {
+            // depth limits leave room for a TLAS of the same order as the host's (checked exactly below; a miss rebuilds on the host)
+            sg.on_device = BuildBlasOnDevice(sc->vertices.p, sc->tri_idx.p, me.first_tri, me.tri_count, eps, node_base, base4, tri_base,
+                                             kStackSize - 12, kStackSize - 12, st, &sg.dev);
+            if (sg.on_device) {
+                sg.n2 = sg.dev.n2; sg.n4 = sg.dev.n4; sg.ntris = sg.dev.tri_count;
+                mesh_depth[m] = sg.dev.depth2; mesh_stack4[m] = sg.dev.max_stack4; mesh_bounds[m] = sg.dev.bounds;
+                sc->stats.bvh_device_meshes++; sc->stats.ms_bvh_device += sg.dev.ms; sc->stats.bvh_ploc_iterations = sg.dev.ploc_iterations;
             }
-            pb[t] = b;
         }
-        BuiltBvh bv;
-        BuildSahBvh(pb.data(), me.tri_count, 4, &bv);
-        int node_base = (int)nodes.size(), tri_base = (int)(tris.size() / 3);
-        {
+        if (!sg.on_device) {
+            std::vector<Aabb> pb(me.tri_count);
+            for (int t = 0; t < me.tri_count; t++) {
+                const int* ix = s->tri_indices + 3 * (size_t)(me.first_tri + t);
+                Aabb b; b.Reset();
+                float ext = 0.f;
+                for (int k = 0; k < 3; k++) b.Grow(s->vertices + 3 * (size_t)ix[k]);
+                for (int k = 0; k < 3; k++) ext = std::max(ext, b.hi[k] - b.lo[k]);
+                // the reference accepts beta, gamma >= -eps: hits up to eps*edge outside the triangle; pad so the box stays conservative
+                for (int k = 0; k < 3; k++) {
+                    float mag = std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]));
+                    float pad = 2.0f * eps * ext + 4.0e-7f * mag + 1e-30f;
+                    b.lo[k] -= pad; b.hi[k] += pad;
+                }
+                pb[t] = b;
+            }
+            BuiltBvh bv;
+            BuildSahBvh(pb.data(), me.tri_count, 4, &bv);
             BuiltBvh4 b4;
             CollapseToBvh4(bv, &b4);
-            int base4 = (int)nodes4.size();
-            mesh_root4[m] = base4; mesh_stack4[m] = b4.max_stack;
-            std::vector<BvhNode64Q> q4;
-            QuantiseBvh4(b4, &q4);
-            for (BvhNode64Q nq : q4) {
-                for (int c = 0; c < 4; c++) {
-                    int32_t ch; memcpy(&ch, &nq.w[4 + c], 4);
-                    if (ch == kNoChild) continue;
-                    if (ch >= 0) ch += base4;
-                    else { int payload = ~ch; int first = (payload >> 3) + tri_base; ch = ~((first << 3) | (payload & 7)); }
-                    memcpy(&nq.w[4 + c], &ch, 4);
-                }
-                nodes4q.push_back(nq);
+            mesh_stack4[m] = b4.max_stack;
+            auto rebase = [&](int32_t ch, int inner_base) {
+                if (ch == kNoChild) return ch;
+                if (ch >= 0) return ch + inner_base;
+                int payload = ~ch; int first = (payload >> 3) + tri_base;
+                return (int32_t)~((first << 3) | (payload & 7));
+            };
+            QuantiseBvh4(b4, &sg.h4q);
+            for (BvhNode64Q& nq : sg.h4q)
+                for (int c = 0; c < 4; c++) { int32_t ch; memcpy(&ch, &nq.w[4 + c], 4); ch = rebase(ch, base4); memcpy(&nq.w[4 + c], &ch, 4); }
+            sg.h4 = std::move(b4.nodes);
+            for (BvhNode128& nd : sg.h4)
+                for (int c = 0; c < 4; c++) { int32_t ch; memcpy(&ch, &nd.q[24 + c], 4); ch = rebase(ch, base4); memcpy(&nd.q[24 + c], &ch, 4); }
+            mesh_depth[m] = bv.max_depth;
+            mesh_bounds[m] = bv.bounds;
+            sg.h2 = std::move(bv.nodes);
+            for (BvhNode64& nd : sg.h2)
+                for (int c = 0; c < 2; c++) { int32_t ch; memcpy(&ch, &nd.q[12 + c], 4); ch = rebase(ch, node_base); memcpy(&nd.q[12 + c], &ch, 4); }
+            sg.htris.reserve((size_t)me.tri_count * 3);
+            for (int k = 0; k < me.tri_count; k++) {
+                int gtri = me.first_tri + bv.order[k];
+                const int* ix = s->tri_indices + 3 * (size_t)gtri;
+                const float *a = s->vertices + 3 * (size_t)ix[0], *b = s->vertices + 3 * (size_t)ix[1], *c = s->vertices + 3 * (size_t)ix[2];
+                sg.htris.push_back(make_float4(a[0], a[1], a[2], BitsToFloat(gtri)));
+                sg.htris.push_back(make_float4(b[0] - a[0], b[1] - a[1], b[2] - a[2], 0.f));
+                sg.htris.push_back(make_float4(c[0] - a[0], c[1] - a[1], c[2] - a[2], 0.f));
             }
-            for (BvhNode128 nd : b4.nodes) {
-                for (int c = 0; c < 4; c++) {
-                    int32_t ch; memcpy(&ch, &nd.q[24 + c], 4);
-                    if (ch == kNoChild) continue;
-                    if (ch >= 0) ch += base4;
-                    else { int payload = ~ch; int first = (payload >> 3) + tri_base; ch = ~((first << 3) | (payload & 7)); }
-                    memcpy(&nd.q[24 + c], &ch, 4);
-                }
-                nodes4.push_back(nd);
-            }
+            sg.n2 = (int)sg.h2.size(); sg.n4 = (int)sg.h4.size(); sg.ntris = me.tri_count;
         }
-        mesh_root[m] = node_base;
-        mesh_depth[m] = bv.max_depth;
-        mesh_bounds[m] = bv.bounds;
-        for (BvhNode64 nd : bv.nodes) {
-            for (int c = 0; c < 2; c++) {
-                int32_t ch; memcpy(&ch, &nd.q[12 + c], 4);
-                if (ch == kNoChild) continue;
-                if (ch >= 0) ch += node_base;
-                else { int payload = ~ch; int first = (payload >> 3) + tri_base; ch = ~((first << 3) | (payload & 7)); }
-                memcpy(&nd.q[12 + c], &ch, 4);
-            }
-            nodes.push_back(nd);
-        }
-        for (int k = 0; k < me.tri_count; k++) {
-            int gtri = me.first_tri + bv.order[k];
-            const int* ix = s->tri_indices + 3 * (size_t)gtri;
-            const float *a = s->vertices + 3 * (size_t)ix[0], *b = s->vertices + 3 * (size_t)ix[1], *c = s->vertices + 3 * (size_t)ix[2];
-            tris.push_back(make_float4(a[0], a[1], a[2], BitsToFloat(gtri)));
-            tris.push_back(make_float4(b[0] - a[0], b[1] - a[1], b[2] - a[2], 0.f));
-            tris.push_back(make_float4(c[0] - a[0], c[1] - a[1], c[2] - a[2], 0.f));
-        }
+        n2_total += sg.n2; n4_total += sg.n4; tri_total += sg.ntris;
     }
 
     // ---- top-level entries + TLAS
@@ -331,64 +351,65 @@ void BuildAndUpload(RtScene* sc, const RtSceneDesc* s) {
     }
     BuiltBvh tl;
     BuildSahBvh(obounds.data(), s->num_objects, 1, &tl);
-    int tlas_base = (int)nodes.size();
-    for (BvhNode64 nd : tl.nodes) {
-        for (int c = 0; c < 2; c++) {
-            int32_t ch; memcpy(&ch, &nd.q[12 + c], 4);
-            if (ch == kNoChild) continue;
-            if (ch >= 0) ch += tlas_base;
-            else { int payload = ~ch; int obj = tl.order[payload >> 3]; ch = ~(obj << 3); }   // TLAS leaves hold exactly one entry
-            memcpy(&nd.q[12 + c], &ch, 4);
-        }
-        nodes.push_back(nd);
-    }
-    int tlas_base4 = (int)nodes4.size();
+    const int tlas_base = n2_total, tlas_base4 = n4_total;
+    BuiltBvh4 t4;
+    CollapseToBvh4(tl, &t4);
     {
-        BuiltBvh4 t4;
-        CollapseToBvh4(tl, &t4);
-        std::vector<BvhNode64Q> q4;
-        QuantiseBvh4(t4, &q4);
-        for (BvhNode64Q nq : q4) {
-            for (int c = 0; c < 4; c++) {
-                int32_t ch; memcpy(&ch, &nq.w[4 + c], 4);
-                if (ch == kNoChild) continue;
-                if (ch >= 0) ch += tlas_base4;
-                else { int payload = ~ch; int obj = tl.order[payload >> 3]; ch = ~(obj << 3); }
-                memcpy(&nq.w[4 + c], &ch, 4);
-            }
-            nodes4q.push_back(nq);
-        }
-        for (BvhNode128 nd : t4.nodes) {
-            for (int c = 0; c < 4; c++) {
-                int32_t ch; memcpy(&ch, &nd.q[24 + c], 4);
-                if (ch == kNoChild) continue;
-                if (ch >= 0) ch += tlas_base4;
-                else { int payload = ~ch; int obj = tl.order[payload >> 3]; ch = ~(obj << 3); }
-                memcpy(&nd.q[24 + c], &ch, 4);
-            }
-            nodes4.push_back(nd);
-        }
         int need4 = t4.max_stack + max_blas_stack4 + 4;
-        if (need4 > kStackSize) throw Invalid{"4-wide BVH needs a deeper traversal stack (" + std::to_string(need4) + " > " + std::to_string(kStackSize) + ")"};
+        int need2 = tl.max_depth + max_blas_depth + 3;
+        if (need4 > kStackSize || need2 > kStackSize) {
+            if (sc->stats.bvh_device_meshes > 0) return false;           // device-built trees ran deeper than the estimate: rebuild on the host
+            if (need4 > kStackSize) throw Invalid{"4-wide BVH needs a deeper traversal stack (" + std::to_string(need4) + " > " + std::to_string(kStackSize) + ")"};
+            throw Invalid{"BVH too deep for the traversal stack (" + std::to_string(need2) + " > " + std::to_string(kStackSize) + ")"};
+        }
+        sc->bvh_depth = need2;
     }
-    sc->bvh_depth = tl.max_depth + max_blas_depth + 3;
-    if (sc->bvh_depth > kStackSize) throw Invalid{"BVH too deep for the traversal stack (" + std::to_string(sc->bvh_depth) + " > " + std::to_string(kStackSize) + ")"};
+    std::vector<BvhNode64Q> tq;
+    QuantiseBvh4(t4, &tq);
+    auto tlas_ref = [&](int32_t ch, int inner_base) {
+        if (ch == kNoChild) return ch;
+        if (ch >= 0) return ch + inner_base;
+        int payload = ~ch; int obj = tl.order[payload >> 3];
+        return (int32_t)~(obj << 3);                                     // TLAS leaves hold exactly one entry
+    };
+    for (BvhNode64& nd : tl.nodes)
+        for (int c = 0; c < 2; c++) { int32_t ch; memcpy(&ch, &nd.q[12 + c], 4); ch = tlas_ref(ch, tlas_base); memcpy(&nd.q[12 + c], &ch, 4); }
+    for (BvhNode64Q& nq : tq)
+        for (int c = 0; c < 4; c++) { int32_t ch; memcpy(&ch, &nq.w[4 + c], 4); ch = tlas_ref(ch, tlas_base4); memcpy(&nq.w[4 + c], &ch, 4); }
+    for (BvhNode128& nd : t4.nodes)
+        for (int c = 0; c < 4; c++) { int32_t ch; memcpy(&ch, &nd.q[24 + c], 4); ch = tlas_ref(ch, tlas_base4); memcpy(&nd.q[24 + c], &ch, 4); }
+    n2_total += (int)tl.nodes.size(); n4_total += (int)t4.nodes.size();
     auto t1 = std::chrono::steady_clock::now();
 
-    // ---- upload
+    // ---- upload / gather the segments into the scene-wide arrays
     static_assert(sizeof(BvhNode64) == 64, "node size");
     static_assert(sizeof(BvhNode128) == 128, "node4 size");
-    sc->nodes.Upload((const float4*)nodes.data(), nodes.size() * 4, st);
-    sc->nodes4.Upload((const float4*)nodes4.data(), nodes4.size() * 8, st);
     static_assert(sizeof(BvhNode64Q) == 64, "quantised node size");
-    sc->nodes4q.Upload((const uint4*)nodes4q.data(), nodes4q.size() * 4, st);
+    sc->nodes.Alloc((size_t)n2_total * 4);
+    sc->nodes4.Alloc((size_t)n4_total * 8);
+    sc->nodes4q.Alloc((size_t)n4_total * 4);
+    sc->tris.Alloc((size_t)tri_total * 3);
+    {
+        size_t o2 = 0, o4 = 0, ot = 0;
+        auto put = [&](void* dst, const void* src, size_t bytes, bool dev) {
+            if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        };
+        for (MeshSeg& sg : segs) {
+            bool d = sg.on_device;
+            put(sc->nodes.p + o2 * 4, d ? (const void*)sg.dev.nodes2 : (const void*)sg.h2.data(), (size_t)sg.n2 * 64, d);
+            put(sc->nodes4.p + o4 * 8, d ? (const void*)sg.dev.nodes4 : (const void*)sg.h4.data(), (size_t)sg.n4 * 128, d);
+            put(sc->nodes4q.p + o4 * 4, d ? (const void*)sg.dev.nodes4q : (const void*)sg.h4q.data(), (size_t)sg.n4 * 64, d);
+            put(sc->tris.p + ot * 3, d ? (const void*)sg.dev.tris : (const void*)sg.htris.data(), (size_t)sg.ntris * 48, d);
+            o2 += sg.n2; o4 += sg.n4; ot += sg.ntris;
+        }
+        put(sc->nodes.p + o2 * 4, tl.nodes.data(), tl.nodes.size() * 64, false);
+        put(sc->nodes4.p + o4 * 8, t4.nodes.data(), t4.nodes.size() * 128, false);
+        put(sc->nodes4q.p + o4 * 4, tq.data(), tq.size() * 64, false);
+    }
     sc->obj_root4.Upload(root4.data(), root4.size(), st);
-    sc->tris.Upload(tris.data(), tris.size(), st);
     sc->spheres.Upload(spheres.data(), spheres.size(), st);
     sc->obj_xf.Upload(oxf.data(), oxf.size(), st);
     sc->obj_sh.Upload(osh.data(), osh.size(), st);
-    sc->tri_idx.Upload(s->tri_indices, (size_t)s->num_triangles * 3, st);
-    sc->vertices.Upload(s->vertices, (size_t)s->num_vertices * 3, st);
     if (s->vertex_normals) sc->normals.Upload(s->vertex_normals, (size_t)s->num_vertices * 3, st); else sc->normals.Alloc(1);
     if (s->texcoords) sc->texcoords.Upload(s->texcoords, (size_t)s->num_texcoords * 2, st); else sc->texcoords.Alloc(1);
     sc->materials.Upload(s->materials, s->num_materials, st);
@@ -419,9 +440,11 @@ void BuildAndUpload(RtScene* sc, const RtSceneDesc* s) {
     d.env_light = s->env_light_index; d.background_texture = s->background_texture;
     for (int i = 0; i < s->num_materials; i++) if (s->materials[i].type == RT_MAT_DIELECTRIC) sc->has_dielectric = true;
 
-    sc->stats.bvh_nodes = nodes4.size(); sc->stats.bvh_bytes = nodes4.size() * 128; sc->stats.tri_bytes = tris.size() * 16;   // the 4-wide BVH is the one the render kernels walk sc->stats.tri_bytes = tris.size() * 16;
+    sc->stats.bvh2_nodes = (uint64_t)n2_total;
+    sc->stats.bvh_nodes = (uint64_t)n4_total; sc->stats.bvh_bytes = (uint64_t)n4_total * 128; sc->stats.tri_bytes = (uint64_t)tri_total * 48;   // the 4-wide BVH is the one the render kernels walk
     sc->stats.ms_bvh_build = std::chrono::duration<double, std::milli>(t1 - t0).count();
     sc->stats.ms_upload = std::chrono::duration<double, std::milli>(t2 - t1).count();
+    return true;
 }
 
 inline int Blocks(long long n) { return (int)((n + kBlock - 1) / kBlock); }
@@ -726,7 +749,7 @@ int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out) {
             sc->grid_extend = prop.multiProcessorCount * std::max(1, be);
             sc->grid_shadow = prop.multiProcessorCount * std::max(1, bs);
         }
-        BuildAndUpload(sc, desc);
+        if (!BuildAndUpload(sc, desc, true)) BuildAndUpload(sc, desc, false);
     });
     if (rcode != RT_OK) { if (sc) rt_scene_destroy(sc); return rcode; }
     *out = sc;
@@ -849,6 +872,28 @@ int rt_get_stats(RtScene* sc, RtStats* out) {
     if (!sc || !out) { SetLastError("rt_get_stats: null argument"); return RT_ERR_INVALID; }
     *out = sc->stats;
     return RT_OK;
+}
+
+int rt_debug_read_bvh(RtScene* sc, int what, void* out, uint64_t capacity_bytes, uint64_t* size_bytes, int32_t* tlas_root) {
+    if (!sc || !size_bytes) { SetLastError("rt_debug_read_bvh: null argument"); return RT_ERR_INVALID; }
+    return Guard("rt_debug_read_bvh", [&] {
+        CK(cudaSetDevice(sc->device));
+        const void* src = nullptr; uint64_t bytes = 0; int32_t root = 0;
+        switch (what) {
+            case RT_DEBUG_BVH2: src = sc->nodes.p; bytes = (uint64_t)(sc->stats.bvh2_nodes) * 64; root = sc->d.tlas_root; break;
+            case RT_DEBUG_BVH4: src = sc->nodes4.p; bytes = sc->stats.bvh_nodes * 128; root = sc->d.tlas_root4; break;
+            case RT_DEBUG_BVH4Q: src = sc->nodes4q.p; bytes = sc->stats.bvh_nodes * 64; root = sc->d.tlas_root4; break;
+            case RT_DEBUG_TRIS: src = sc->tris.p; bytes = sc->stats.tri_bytes; break;
+            case RT_DEBUG_OBJ_ROOT4: src = sc->obj_root4.p; bytes = (uint64_t)std::max(1, sc->d.num_objects) * 4; break;
+            default: throw Invalid{"rt_debug_read_bvh: unknown array"};
+        }
+        *size_bytes = bytes;
+        if (tlas_root) *tlas_root = root;
+        if (!out) return;
+        if (capacity_bytes < bytes) throw Invalid{"rt_debug_read_bvh: buffer too small"};
+        CK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, sc->stream));
+        CK(cudaStreamSynchronize(sc->stream));
+    });
 }
 
 }  // extern "C"

@@ -1,7 +1,7 @@
 // CLI with the reference's contract (src/main.cpp:7-14): `raytracer scene.xml` renders every camera of the scene
 // and writes each camera's <ImageName> (P3 PPM for "*.png*" names, half-float EXR otherwise, src/Image.cpp:26-34).
 // Extra, optional knobs after the scene path:  --f32 (also dump <ImageName>.f32 raw floats)  --device N
-// --integrator path|reference  --seed S  --tonemap KEY BURN SAT GAMMA (writes <ImageName>.tm.ppm)
+// --integrator path|reference  --bvh auto|host|device (per-mesh BVH builder)  --seed S  --tonemap KEY BURN SAT GAMMA (writes <ImageName>.tm.ppm)
 #include "../../include/rt795.h"
 #include <cstdio>
 #include <cstdlib>
@@ -10,9 +10,9 @@
 #include <vector>
 
 int main(int argc, char* argv[]) {
-    if (argc < 2) { fprintf(stderr, "usage: %s scene.xml [--f32] [--device N] [--integrator path|reference] [--seed S] [--tonemap key burn sat gamma]\n", argv[0]); return 2; }
+    if (argc < 2) { fprintf(stderr, "usage: %s scene.xml [--f32] [--device N] [--integrator path|reference] [--bvh auto|host|device] [--seed S] [--tonemap key burn sat gamma]\n", argv[0]); return 2; }
     bool f32 = false, tonemap = false;
-    int device = 0;
+    int device = 0, bvh = RT_BVH_AUTO;
     float tm[4] = {0.18f, 1.0f, 1.0f, 2.2f};
     RtRenderOpts opts;
     memset(&opts, 0, sizeof opts);
@@ -22,13 +22,16 @@ int main(int argc, char* argv[]) {
         else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--seed") && i + 1 < argc) opts.seed = strtoull(argv[++i], nullptr, 10);
         else if (!strcmp(argv[i], "--integrator") && i + 1 < argc) opts.integrator = !strcmp(argv[++i], "path") ? RT_INTEGRATOR_PATH : RT_INTEGRATOR_REFERENCE;
+        else if (!strcmp(argv[i], "--bvh") && i + 1 < argc) { const char* b = argv[++i]; bvh = !strcmp(b, "host") ? RT_BVH_HOST_SAH : !strcmp(b, "device") ? RT_BVH_DEVICE_PLOC : RT_BVH_AUTO; }
         else if (!strcmp(argv[i], "--tonemap") && i + 4 < argc) { tonemap = true; for (int k = 0; k < 4; k++) tm[k] = (float)atof(argv[++i]); }
         else { fprintf(stderr, "unknown option %s\n", argv[i]); return 2; }
     }
     RtHostScene* hs = nullptr;
     if (rt_host_load_scene(argv[1], &hs) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }
     RtScene* sc = nullptr;
-    if (rt_scene_create(rt_host_scene_desc(hs), device, &sc) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }
+    RtSceneDesc desc = *rt_host_scene_desc(hs);
+    desc.bvh_builder = bvh;
+    if (rt_scene_create(&desc, device, &sc) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }
     printf("BVH construction complete.\n");
     for (int c = 0; c < rt_host_num_cameras(hs); c++) {
         const RtCameraDesc* cam = rt_host_camera(hs, c);
