@@ -218,7 +218,10 @@ def run_ours(args, rt):
     xml = make_scene(rt, args.config, full_kw, tag)
     hs = rt.HostScene(xml)
     cam = hs.camera(0)
-    sc = rt.Scene(hs.desc, local)
+    # the scene is built once and rendered steps+warmup times: ask for the builder that gives the best tree (host binned SAH); the
+    # library default (AUTO) builds big meshes on the GPU ~40x faster for a ~2.5 % slower frame (profiles/bench/r01_bvh_builders_c4.json)
+    builder = {"host": rt.RT_BVH_HOST_SAH, "device": rt.RT_BVH_DEVICE_PLOC, "auto": rt.RT_BVH_AUTO}[args.bvh]
+    sc = rt.Scene(hs.desc, local, bvh_builder=builder)
     integrator = rt.RT_INTEGRATOR_PATH if args.config == "c5" else rt.RT_INTEGRATOR_REFERENCE
     npix = cam.nx * cam.ny
     # N>1: every rank's resolve kernel stores its tiles into rank 0's framebuffer over NVLink peer memory (multigpu.FrameGather;
@@ -361,7 +364,8 @@ def run_ours(args, rt):
                 "config": {"workload": rt.scenes.CONFIGS[args.config]["label"] + (" [--small sample]" if args.small else "") + (f" [--spp {args.spp}]" if args.spp else ""),
                            "resolution": [cam.nx, cam.ny], "spp": cam.num_samples, "rays_per_frame": {"primary": rays[0], "secondary": rays[1], "shadow": rays[2]},
                            "integrator": "path" if integrator else "reference", "parallelism": f"tiles16x16-interleaved-x{world}", "gather": {"mode": gather.mode, "fallback_reason": gather.why_not_p2p, "ms_render_max": ms_render_max, "ms_gather_max": ms_gather_max, "check": gather_check}, "l2": "flushed between steps (256 MB write)",
-                           "scene_bytes": {"bvh": int(sstats.bvh_bytes), "triangles": int(sstats.tri_bytes)}, "bvh_build_ms": sstats.ms_bvh_build},
+                           "scene_bytes": {"bvh": int(sstats.bvh_bytes), "triangles": int(sstats.tri_bytes)}, "bvh_build_ms": sstats.ms_bvh_build,
+                           "bvh_builder": args.bvh, "bvh_device_meshes": int(sstats.bvh_device_meshes)},
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(cam_host.numel()), "d2h_bytes_per_step": int(npix * 12),
                         "api": "rt_render (host camera/options in, host framebuffer out)" if world == 1 else ("rt_render_device (K8 stores owned tiles into rank 0's frame over NVLink peer memory) + device barrier" if gather.mode == "p2p" else "rt_render_device + NCCL reduce") + " + D2H on rank 0",
                         "timing": "host clock around the synchronous call, max over ranks"},
@@ -382,6 +386,7 @@ def main():
     ap.add_argument("--config", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--small", action="store_true", help="use the bounded sample configuration (smoke runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bvh", default="host", choices=["host", "device", "auto"], help="per-mesh BVH builder (RtSceneDesc.bvh_builder)")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel of the workload (exploration; the headline run uses the configuration's own)")
     args = ap.parse_args()
     rt = ge.load_package()

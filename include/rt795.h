@@ -294,6 +294,15 @@ typedef struct RtHostScene RtHostScene;   /* opaque; owns the arrays behind the 
  * normals, and flattens to an RtSceneDesc.  Pure host code (no CUDA). */
 int rt_host_load_scene(const char* xml_path, RtHostScene** out);
 void rt_host_free_scene(RtHostScene* hs);
+/* Scene blob: the prepared scene (everything rt_host_load_scene produces, cameras and image names included) as one binary
+ * file, so later runs skip the text parsing the reference does on every start (src/Parser.h:684-727, 1109-1143).  The blob
+ * remembers size + mtime of the XML and of every PLY / image it was read from.
+ *   rt_host_load_scene_blob: check_sources != 0 rejects (RT_ERR_PARSE, "stale") a blob whose sources changed or vanished.
+ *   rt_host_load_scene_cached: loads `blob_path` (NULL -> "<xml_path>.rt795blob") when it is a fresh blob of xml_path, else
+ *   parses xml_path and (best effort) writes the blob; *cache_hit (may be NULL) says which happened. */
+int rt_host_save_scene_blob(const RtHostScene* hs, const char* blob_path);
+int rt_host_load_scene_blob(const char* blob_path, int check_sources, RtHostScene** out);
+int rt_host_load_scene_cached(const char* xml_path, const char* blob_path, RtHostScene** out, int* cache_hit);
 const RtSceneDesc* rt_host_scene_desc(const RtHostScene* hs);
 int rt_host_num_cameras(const RtHostScene* hs);
 const RtCameraDesc* rt_host_camera(const RtHostScene* hs, int i);

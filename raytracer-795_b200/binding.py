@@ -24,6 +24,7 @@ RT_INTEGRATOR_REFERENCE, RT_INTEGRATOR_PATH = 0, 1
 RT_BVH_AUTO, RT_BVH_HOST_SAH, RT_BVH_DEVICE_PLOC = 0, 1, 2
 RT_DEBUG_BVH2, RT_DEBUG_BVH4, RT_DEBUG_BVH4Q, RT_DEBUG_TRIS, RT_DEBUG_OBJ_ROOT4 = 0, 1, 2, 3, 4
 RT_OBJ_SPHERE, RT_OBJ_MESH = 0, 1
+RT_IMG_RGBA8, RT_IMG_RGBA32F = 0, 1
 
 f3 = C.c_float * 3
 
@@ -116,6 +117,7 @@ HIT_DTYPE = np.dtype([("full", "<i4"), ("object", "<i4"), ("primitive", "<i4"), 
 # every symbol include/rt795.h declares (tests/test_abi.py asserts the library exports all of them)
 CORE_SYMBOLS = ["rt_scene_create", "rt_scene_destroy", "rt_render", "rt_render_device", "rt_trace_primary", "rt_tonemap",
                 "rt_get_stats", "rt_debug_read_bvh", "rt_last_error", "rt_abi_version", "rt_device_count", "rt_host_load_scene",
+                "rt_host_save_scene_blob", "rt_host_load_scene_blob", "rt_host_load_scene_cached",
                 "rt_host_free_scene", "rt_host_scene_desc", "rt_host_num_cameras", "rt_host_camera",
                 "rt_host_camera_image_name", "rt_host_save_image", "rt_host_save_f32"]
 
@@ -150,6 +152,9 @@ def load_core() -> C.CDLL:
         lib.rt_debug_read_bvh.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, P(C.c_uint64), P(C.c_int32)]
         lib.rt_last_error.restype = C.c_char_p
         lib.rt_host_load_scene.argtypes = [C.c_char_p, P(C.c_void_p)]
+        lib.rt_host_save_scene_blob.argtypes = [C.c_void_p, C.c_char_p]
+        lib.rt_host_load_scene_blob.argtypes = [C.c_char_p, C.c_int, P(C.c_void_p)]
+        lib.rt_host_load_scene_cached.argtypes = [C.c_char_p, C.c_char_p, P(C.c_void_p), P(C.c_int)]
         lib.rt_host_free_scene.argtypes = [C.c_void_p]
         lib.rt_host_free_scene.restype = None
         lib.rt_host_scene_desc.argtypes = [C.c_void_p]
@@ -205,11 +210,24 @@ def default_opts(**kw) -> RtRenderOpts:
 class HostScene:
     """rt_host_load_scene: XML (+PLY/PNG/EXR) -> RtSceneDesc, the reference's Scene ctor + renderScene prologue."""
 
-    def __init__(self, xml_path: str):
+    def __init__(self, xml_path: Optional[str] = None, *, blob: Optional[str] = None, check_sources: bool = True, cached: bool = False):
+        """HostScene(xml): parse.  HostScene(blob=path): rt_host_load_scene_blob.  HostScene(xml, cached=True[, blob=path]):
+        rt_host_load_scene_cached (self.cache_hit tells whether the blob was used)."""
         self.lib = load_core()
         self.h = C.c_void_p()
-        _check(self.lib.rt_host_load_scene(os.fsencode(xml_path), C.byref(self.h)))
+        self.cache_hit = False
+        if cached:
+            hit = C.c_int(0)
+            _check(self.lib.rt_host_load_scene_cached(os.fsencode(xml_path), os.fsencode(blob) if blob else None, C.byref(self.h), C.byref(hit)))
+            self.cache_hit = bool(hit.value)
+        elif blob is not None:
+            _check(self.lib.rt_host_load_scene_blob(os.fsencode(blob), 1 if check_sources else 0, C.byref(self.h)))
+        else:
+            _check(self.lib.rt_host_load_scene(os.fsencode(xml_path), C.byref(self.h)))
         self.desc = self.lib.rt_host_scene_desc(self.h)
+
+    def save_blob(self, path: str) -> None:
+        _check(self.lib.rt_host_save_scene_blob(self.h, os.fsencode(path)))
 
     @property
     def num_cameras(self) -> int:

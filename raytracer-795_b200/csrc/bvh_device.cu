@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -23,6 +24,7 @@ namespace {
 
 constexpr int kPlocRadius = 16;          // nearest-neighbour search window (+-) in the Morton-ordered cluster array (RT795_PLOC_RADIUS overrides, <= kMaxPlocRadius)
 constexpr int kMaxPlocRadius = 64;
+constexpr int kTopClusters = 4096;       // clustering stops here; the levels above are built with binned SAH (RT795_PLOC_TOP overrides; 1 = pure PLOC)
 constexpr int kTB = 256;
 constexpr int kMaxPlocIterations = 4096; // a healthy build of 1 M triangles takes ~40; beyond the cap the host builder takes over
 constexpr int kCntMask = 0x3fffffff, kLeafBit = 0x40000000;
@@ -215,6 +217,25 @@ __global__ void __launch_bounds__(kTB) k_merge_emit(const float4* __restrict__ c
     }
     uint32_t pos = (uint32_t)(s >> 32);
     clo_out[pos] = lo; chi_out[pos] = hi;
+}
+
+// ---- B3b: top of the tree.  Once the clusters are few (kTopClusters) their Morton neighbourhoods say little about which
+// should merge; the last levels - the ones every ray walks - are built by the host's binned-SAH builder over the cluster
+// boxes (a few thousand "primitives", < 1 ms) and spliced in as ordinary inner nodes.
+__global__ void __launch_bounds__(kTB) k_gather_clusters(const float4* __restrict__ clo, int m, const int32_t* __restrict__ meta, const float* __restrict__ cst,
+                                                         int32_t* __restrict__ out_meta, float* __restrict__ out_cst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    int id = __float_as_int(clo[i].w);
+    out_meta[i] = meta[id]; out_cst[i] = cst[id];
+}
+__global__ void __launch_bounds__(kTB) k_set_parents(int first_id, int count, const int2* __restrict__ child, int32_t* __restrict__ parent, int root) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    int id = first_id + t;
+    int2 ch = child[id];
+    parent[ch.x] = id; parent[ch.y] = id;
+    if (id == root) parent[id] = -1;
 }
 
 // ---- B4: one walk to the root per node: DFS offset of its first triangle, state (0 live inner, 1 leaf of the final tree, 2 buried
@@ -414,10 +435,12 @@ bool BuildBlasOnDevice(const float* d_vertices, const int32_t* d_tri_idx, int fi
         k_init_clusters<<<Grid(n), kTB, 0, st>>>(order, plo, phi, n, clo[0], chi[0], nlo, nhi, parent, meta, cst);
 
         // B3
+        int top = kTopClusters;
+        if (const char* e = getenv("RT795_PLOC_TOP")) top = std::max(1, atoi(e));
         int m = n, next_id = n, cur = 0, iters = 0;
         int radius = kPlocRadius;
         if (const char* e = getenv("RT795_PLOC_RADIUS")) radius = std::min(kMaxPlocRadius, std::max(1, atoi(e)));
-        while (m > 1) {
+        while (m > top) {
             if (++iters > kMaxPlocIterations) return false;
             k_nearest<<<Grid(m), kTB, 0, st>>>(clo[cur], chi[cur], m, radius, nn);
             k_merge_flags<<<Grid(m), kTB, 0, st>>>(nn, m, flags);
@@ -430,6 +453,64 @@ bool BuildBlasOnDevice(const float* d_vertices, const int32_t* d_tri_idx, int fi
             m = (int)h_tot[0]; next_id += (int)h_tot[1]; cur ^= 1;
         }
         out->ploc_iterations = iters;
+        if (m > 1) {
+            // B3b: binned SAH over the remaining clusters on the host; node ids [next_id, total) = reversed flatten order (root last)
+            std::vector<float4> hlo(m), hhi(m);
+            std::vector<int32_t> hmeta(m);
+            std::vector<float> hcst(m);
+            int32_t* g_meta = live;                                      // scratch not in use yet
+            float* g_cst = reinterpret_cast<float*>(lscan);
+            k_gather_clusters<<<Grid(m), kTB, 0, st>>>(clo[cur], m, meta, cst, g_meta, g_cst);
+            BCK(cudaMemcpyAsync(hlo.data(), clo[cur], (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, st));
+            BCK(cudaMemcpyAsync(hhi.data(), chi[cur], (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, st));
+            BCK(cudaMemcpyAsync(hmeta.data(), g_meta, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+            BCK(cudaMemcpyAsync(hcst.data(), g_cst, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+            BCK(cudaStreamSynchronize(st));
+            std::vector<Aabb> pb(m);
+            for (int i = 0; i < m; i++) { pb[i].lo[0] = hlo[i].x; pb[i].lo[1] = hlo[i].y; pb[i].lo[2] = hlo[i].z; pb[i].hi[0] = hhi[i].x; pb[i].hi[1] = hhi[i].y; pb[i].hi[2] = hhi[i].z; }
+            BuiltBvh tb;
+            BuildSahBvh(pb.data(), m, 1, &tb);
+            const int inner = (int)tb.nodes.size();
+            if (inner != m - 1) throw std::runtime_error("bvh_device: top tree is not a full binary tree over the clusters");
+            std::vector<float4> tlo(inner), thi(inner);
+            std::vector<int2> tch(inner);
+            std::vector<int32_t> tmeta(inner);
+            std::vector<float> tcst(inner);
+            auto slot_of = [&](int i) { return inner - 1 - i; };          // flatten index -> slot in [next_id, total): root (0) -> last
+            for (int i = inner - 1; i >= 0; i--) {                        // children come after their parent in the flatten order
+                const BvhNode64& nd = tb.nodes[i];
+                int ids[2], cnt[2]; float cs[2], area[2];
+                float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+                for (int c = 0; c < 2; c++) {
+                    int32_t ref; memcpy(&ref, &nd.q[12 + c], 4);
+                    float blo[3] = {nd.q[c * 4 + 0], nd.q[c * 4 + 2], nd.q[8 + c * 2 + 0]}, bhi[3] = {nd.q[c * 4 + 1], nd.q[c * 4 + 3], nd.q[8 + c * 2 + 1]};
+                    for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], blo[k]); hi[k] = std::max(hi[k], bhi[k]); }
+                    float dx = bhi[0] - blo[0], dy = bhi[1] - blo[1], dz = bhi[2] - blo[2];
+                    area[c] = dx * dy + dy * dz + dz * dx;
+                    if (ref >= 0) { int sl = slot_of(ref); ids[c] = next_id + sl; cnt[c] = tmeta[sl] & kCntMask; cs[c] = tcst[sl]; }
+                    else { int ci = tb.order[(~ref) >> 3]; int32_t nid; memcpy(&nid, &hlo[ci].w, 4); ids[c] = nid; cnt[c] = hmeta[ci] & kCntMask; cs[c] = hcst[ci]; }
+                }
+                float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+                float a = dx * dy + dy * dz + dz * dx;
+                int c = cnt[0] + cnt[1];
+                float split = a > 0.f ? 1.0f + (area[0] * cs[0] + area[1] * cs[1]) / a : 3.0e38f;
+                if (!(split <= 3.0e38f)) split = 3.0e38f;
+                bool leaf = c <= 4 && (float)c <= split;
+                int sl = slot_of(i);
+                int32_t idbits = next_id + sl; float idf; memcpy(&idf, &idbits, 4);
+                tlo[sl] = make_float4(lo[0], lo[1], lo[2], idf); thi[sl] = make_float4(hi[0], hi[1], hi[2], 0.f);
+                tch[sl] = make_int2(ids[0], ids[1]);
+                tmeta[sl] = c | (leaf ? kLeafBit : 0); tcst[sl] = leaf ? (float)c : split;
+            }
+            BCK(cudaMemcpyAsync(nlo + next_id, tlo.data(), (size_t)inner * sizeof(float4), cudaMemcpyHostToDevice, st));
+            BCK(cudaMemcpyAsync(nhi + next_id, thi.data(), (size_t)inner * sizeof(float4), cudaMemcpyHostToDevice, st));
+            BCK(cudaMemcpyAsync(child + next_id, tch.data(), (size_t)inner * sizeof(int2), cudaMemcpyHostToDevice, st));
+            BCK(cudaMemcpyAsync(meta + next_id, tmeta.data(), (size_t)inner * 4, cudaMemcpyHostToDevice, st));
+            BCK(cudaMemcpyAsync(cst + next_id, tcst.data(), (size_t)inner * 4, cudaMemcpyHostToDevice, st));
+            k_set_parents<<<Grid(inner), kTB, 0, st>>>(next_id, inner, child, parent, next_id + inner - 1);
+            BCK(cudaStreamSynchronize(st));                               // the host vectors above go out of scope
+            next_id += inner;
+        }
         if (next_id != total) throw std::runtime_error("bvh_device: node count mismatch after clustering");
         const int root = total - 1;
 

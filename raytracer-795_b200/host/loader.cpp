@@ -11,7 +11,10 @@
 #include "ply.h"
 #include "xml.h"
 
+#include <sys/stat.h>
+
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -117,9 +120,30 @@ struct RtHostScene {
     std::vector<RtLight> lights;
     std::vector<RtCameraDesc> cameras;
     std::vector<std::string> image_names;
+    std::vector<std::string> deps;        // every file the scene was read from (XML first): the blob cache's staleness check
 };
 
 namespace {
+
+// Points the descriptor's array fields at the vectors the host scene owns (after a parse or a blob load).
+void BindDesc(RtHostScene* hs) {
+    hs->images.clear();
+    for (auto& li : hs->image_store) {
+        RtImage im; im.width = li.width; im.height = li.height; im.format = li.format; im.pixels = li.bytes.data();
+        hs->images.push_back(im);
+    }
+    RtSceneDesc& d = hs->desc;
+    d.num_vertices = (int)hs->vertices.size() / 3; d.vertices = hs->vertices.data(); d.vertex_normals = hs->normals.data();
+    d.num_texcoords = (int)hs->texcoords.size() / 2; d.texcoords = hs->texcoords.data();
+    d.num_triangles = (int)hs->tris.size() / 3; d.tri_indices = hs->tris.data();
+    d.num_meshes = (int)hs->meshes.size(); d.meshes = hs->meshes.data();
+    d.num_spheres = (int)hs->spheres.size(); d.spheres = hs->spheres.data();
+    d.num_objects = (int)hs->objects.size(); d.objects = hs->objects.data();
+    d.num_materials = (int)hs->materials.size(); d.materials = hs->materials.data();
+    d.num_textures = (int)hs->textures.size(); d.textures = hs->textures.data();
+    d.num_images = (int)hs->images.size(); d.images = hs->images.data();
+    d.num_lights = (int)hs->lights.size(); d.lights = hs->lights.data();
+}
 
 class Loader {
 public:
@@ -132,6 +156,7 @@ public:
             fclose(probe);
         }
         if (!doc.LoadFile(path_.c_str(), err)) return false;
+        hs_->deps.push_back(path_);
         root_ = doc.root();
         // directory prefix exactly as src/Parser.h:488-498: everything up to and including the last '/',
         // and, when there is no '/', the FIRST CHARACTER of the path (lastIndex defaults to 0) - SURVEY A.11.
@@ -338,6 +363,7 @@ private:
         for (size_t i = 0; i < loaded_paths_.size(); i++) if (loaded_paths_[i] == p) return (int)i;
         LoadedImage li;
         if (!LoadImageFile(p, &li, err)) { io_error_ = true; return -1; }
+        hs_->deps.push_back(p);
         hs_->image_store.push_back(std::move(li));
         loaded_paths_.push_back(p);
         return (int)loaded_paths_.size() - 1;
@@ -472,6 +498,7 @@ private:
             if (auto ply = fe->FindAttributePrefix("plyFile")) {
                 PlyMesh pm;
                 if (!LoadPly(base_ + ply->value, &pm, err)) { io_error_ = true; return false; }
+                hs_->deps.push_back(base_ + ply->value);
                 int texture_offset = (int)hs_->texcoords.size() / 2 + 1;          // Parser.h:1051
                 hs_->texcoords.insert(hs_->texcoords.end(), pm.uv.begin(), pm.uv.end());
                 int vertex_count = (int)hs_->vertices.size() / 3 + 1;             // Parser.h:1065
@@ -658,10 +685,6 @@ private:
                 if (uvi < 0 || uvi >= ntc) return Fail(err, "textured mesh lacks texture coordinates for some vertex (SURVEY A.9)");
             }
         }
-        for (auto& li : hs_->image_store) {
-            RtImage im; im.width = li.width; im.height = li.height; im.format = li.format; im.pixels = li.bytes.data();
-            hs_->images.push_back(im);
-        }
         RtSceneDesc& d = hs_->desc;
         memset(&d, 0, sizeof d);
         d.abi_version = RT795_ABI_VERSION;
@@ -670,21 +693,55 @@ private:
         d.env_light_index = env_light_;
         d.background_texture = -1;
         for (size_t i = 0; i < hs_->textures.size(); i++) if (hs_->textures[i].decal_mode == RT_DM_REPLACE_BACKGROUND) d.background_texture = (int)i;   // last wins, Scene.cpp:494-500
-        d.num_vertices = (int)hs_->vertices.size() / 3; d.vertices = hs_->vertices.data(); d.vertex_normals = hs_->normals.data();
-        d.num_texcoords = ntc; d.texcoords = hs_->texcoords.data();
-        d.num_triangles = (int)hs_->tris.size() / 3; d.tri_indices = hs_->tris.data();
-        d.num_meshes = (int)hs_->meshes.size(); d.meshes = hs_->meshes.data();
-        d.num_spheres = (int)hs_->spheres.size(); d.spheres = hs_->spheres.data();
-        d.num_objects = (int)hs_->objects.size(); d.objects = hs_->objects.data();
-        d.num_materials = (int)hs_->materials.size(); d.materials = hs_->materials.data();
-        d.num_textures = (int)hs_->textures.size(); d.textures = hs_->textures.data();
-        d.num_images = (int)hs_->images.size(); d.images = hs_->images.data();
-        d.num_lights = (int)hs_->lights.size(); d.lights = hs_->lights.data();
+        BindDesc(hs_);
         return true;
     }
 };
 
 }  // namespace
+
+// ---- scene blob (scene ingest).  The prepared, flattened scene written as one little-endian file so the
+// next run skips XML / PLY / PNG / EXR parsing, transform composition and smooth-normal computation (reference:
+// src/Parser.h:684-727, 1109-1143 text parsing with atof, src/Scene.cpp:303-318).  The blob records size + mtime of every
+// source file it came from; a changed source makes it stale.
+namespace {
+
+const char kBlobMagic[8] = {'R', 'T', '7', '9', '5', 'S', 'B', '2'};
+
+struct BlobWriter {
+    FILE* f; bool ok = true;
+    void Raw(const void* p, size_t n) { if (ok && n && fwrite(p, 1, n, f) != n) ok = false; }
+    void U64(uint64_t v) { Raw(&v, 8); }
+    void Str(const std::string& s) { U64(s.size()); Raw(s.data(), s.size()); }
+    template <class T> void Vec(const std::vector<T>& v) { U64(v.size()); Raw(v.data(), v.size() * sizeof(T)); }
+};
+struct BlobReader {
+    FILE* f; bool ok = true; uint64_t limit;
+    void Raw(void* p, size_t n) { if (ok && n && fread(p, 1, n, f) != n) ok = false; }
+    uint64_t U64() { uint64_t v = 0; Raw(&v, 8); return v; }
+    bool Str(std::string* s) { uint64_t n = U64(); if (!ok || n > limit) return ok = false; s->resize(n); Raw(&(*s)[0], n); return ok; }
+    template <class T> bool Vec(std::vector<T>* v) { uint64_t n = U64(); if (!ok || n > limit / sizeof(T)) return ok = false; v->resize(n); Raw(v->data(), n * sizeof(T)); return ok; }
+};
+
+// layout fingerprint: a blob written by a library with different struct layouts must not be read
+uint64_t LayoutStamp() {
+    const uint64_t sz[] = {sizeof(RtSceneDesc), sizeof(RtObject), sizeof(RtMaterial), sizeof(RtTexture), sizeof(RtLight), sizeof(RtCameraDesc),
+                           sizeof(RtMesh), sizeof(RtSphere), (uint64_t)RT795_ABI_VERSION};
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t v : sz) { h ^= v; h *= 1099511628211ull; }
+    return h;
+}
+
+bool StatFile(const std::string& path, uint64_t* size, int64_t* mtime_ns) {
+    struct stat sb;
+    if (stat(path.c_str(), &sb) != 0) return false;
+    *size = (uint64_t)sb.st_size;
+    *mtime_ns = (int64_t)sb.st_mtim.tv_sec * 1000000000ll + (int64_t)sb.st_mtim.tv_nsec;
+    return true;
+}
+
+}  // namespace
+
 
 extern "C" {
 
@@ -703,6 +760,100 @@ int rt_host_load_scene(const char* xml_path, RtHostScene** out) {
     return RT_OK;
 }
 void rt_host_free_scene(RtHostScene* hs) { delete hs; }
+int rt_host_save_scene_blob(const RtHostScene* hs, const char* blob_path) {
+    if (!hs || !blob_path) { SetLastError("rt_host_save_scene_blob: null argument"); return RT_ERR_INVALID; }
+    std::string tmp = std::string(blob_path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) { SetLastError(std::string("rt_host_save_scene_blob: cannot write ") + tmp); return RT_ERR_IO; }
+    BlobWriter w{f};
+    w.Raw(kBlobMagic, 8); w.U64(LayoutStamp());
+    w.U64(hs->deps.size());
+    for (const std::string& d : hs->deps) {
+        uint64_t size = 0; int64_t mt = 0;
+        StatFile(d, &size, &mt);
+        w.Str(d); w.U64(size); w.U64((uint64_t)mt);
+    }
+    w.Raw(&hs->desc, sizeof(RtSceneDesc));                               // scalars; the pointer fields are rebound on load
+    w.Vec(hs->vertices); w.Vec(hs->normals); w.Vec(hs->texcoords); w.Vec(hs->tris);
+    w.Vec(hs->meshes); w.Vec(hs->spheres); w.Vec(hs->objects); w.Vec(hs->materials); w.Vec(hs->textures); w.Vec(hs->lights); w.Vec(hs->cameras);
+    w.U64(hs->image_names.size());
+    for (const std::string& n : hs->image_names) w.Str(n);
+    w.U64(hs->image_store.size());
+    for (const LoadedImage& li : hs->image_store) { w.U64((uint64_t)li.width); w.U64((uint64_t)li.height); w.U64((uint64_t)li.format); w.Vec(li.bytes); }
+    w.Raw(kBlobMagic, 8);                                                // trailer: a truncated file is rejected
+    bool ok = w.ok;
+    if (fclose(f) != 0) ok = false;
+    if (!ok || rename(tmp.c_str(), blob_path) != 0) { remove(tmp.c_str()); SetLastError(std::string("rt_host_save_scene_blob: write failed for ") + blob_path); return RT_ERR_IO; }
+    return RT_OK;
+}
+
+int rt_host_load_scene_blob(const char* blob_path, int check_sources, RtHostScene** out) {
+    if (!blob_path || !out) { SetLastError("rt_host_load_scene_blob: null argument"); return RT_ERR_INVALID; }
+    *out = nullptr;
+    FILE* f = fopen(blob_path, "rb");
+    if (!f) { SetLastError(std::string("rt_host_load_scene_blob: cannot open ") + blob_path); return RT_ERR_IO; }
+    uint64_t fsize = 0; int64_t fmt = 0;
+    StatFile(blob_path, &fsize, &fmt);
+    BlobReader r{f, true, fsize};
+    RtHostScene* hs = new RtHostScene();
+    auto fail = [&](const std::string& why) { fclose(f); delete hs; SetLastError(std::string("rt_host_load_scene_blob: ") + blob_path + ": " + why); return RT_ERR_PARSE; };
+    char magic[8];
+    r.Raw(magic, 8);
+    if (!r.ok || memcmp(magic, kBlobMagic, 8) != 0) return fail("not a scene blob");
+    if (r.U64() != LayoutStamp()) return fail("written by an incompatible library version");
+    uint64_t ndeps = r.U64();
+    if (!r.ok || ndeps > 1u << 20) return fail("corrupt header");
+    for (uint64_t i = 0; i < ndeps; i++) {
+        std::string path;
+        if (!r.Str(&path)) return fail("corrupt header");
+        uint64_t size = r.U64(); int64_t mt = (int64_t)r.U64();
+        hs->deps.push_back(path);
+        if (check_sources) {
+            uint64_t now_size = 0; int64_t now_mt = 0;
+            if (!StatFile(path, &now_size, &now_mt) || now_size != size || now_mt != mt) return fail("stale: " + path + " changed since the blob was written");
+        }
+    }
+    r.Raw(&hs->desc, sizeof(RtSceneDesc));
+    r.Vec(&hs->vertices); r.Vec(&hs->normals); r.Vec(&hs->texcoords); r.Vec(&hs->tris);
+    r.Vec(&hs->meshes); r.Vec(&hs->spheres); r.Vec(&hs->objects); r.Vec(&hs->materials); r.Vec(&hs->textures); r.Vec(&hs->lights); r.Vec(&hs->cameras);
+    uint64_t nn = r.U64();
+    if (!r.ok || nn > 1u << 20) return fail("corrupt body");
+    hs->image_names.resize(nn);
+    for (auto& n : hs->image_names) if (!r.Str(&n)) return fail("corrupt body");
+    uint64_t ni = r.U64();
+    if (!r.ok || ni > 1u << 20) return fail("corrupt body");
+    hs->image_store.resize(ni);
+    for (auto& li : hs->image_store) {
+        li.width = (int)r.U64(); li.height = (int)r.U64(); li.format = (int)r.U64();
+        if (!r.Vec(&li.bytes)) return fail("corrupt body");
+        size_t px = li.format == RT_IMG_RGBA8 ? 4 : 16;
+        if (li.width < 1 || li.height < 1 || li.bytes.size() != (size_t)li.width * li.height * px) return fail("corrupt image");
+    }
+    r.Raw(magic, 8);
+    if (!r.ok || memcmp(magic, kBlobMagic, 8) != 0) return fail("truncated");
+    fclose(f);
+    if (hs->cameras.size() != hs->image_names.size() || hs->vertices.size() % 3 || hs->tris.size() % 3 || hs->texcoords.size() % 2 ||
+        (!hs->normals.empty() && hs->normals.size() != hs->vertices.size())) { delete hs; SetLastError(std::string("rt_host_load_scene_blob: ") + blob_path + ": inconsistent arrays"); return RT_ERR_PARSE; }
+    hs->desc.abi_version = RT795_ABI_VERSION;
+    BindDesc(hs);                                                         // rt_scene_create validates every index range again
+    *out = hs;
+    return RT_OK;
+}
+
+int rt_host_load_scene_cached(const char* xml_path, const char* blob_path, RtHostScene** out, int* cache_hit) {
+    if (!xml_path || !out) { SetLastError("rt_host_load_scene_cached: null argument"); return RT_ERR_INVALID; }
+    std::string blob = blob_path ? std::string(blob_path) : std::string(xml_path) + ".rt795blob";
+    if (cache_hit) *cache_hit = 0;
+    if (rt_host_load_scene_blob(blob.c_str(), 1, out) == RT_OK) {
+        if (!(*out)->deps.empty() && (*out)->deps[0] == xml_path) { if (cache_hit) *cache_hit = 1; return RT_OK; }
+        rt_host_free_scene(*out); *out = nullptr;                         // a blob of some other scene
+    }
+    int rc = rt_host_load_scene(xml_path, out);
+    if (rc != RT_OK) return rc;
+    rt_host_save_scene_blob(*out, blob.c_str());                          // best effort: a read-only directory just means no cache
+    return RT_OK;
+}
+
 const RtSceneDesc* rt_host_scene_desc(const RtHostScene* hs) { return hs ? &hs->desc : nullptr; }
 int rt_host_num_cameras(const RtHostScene* hs) { return hs ? (int)hs->cameras.size() : 0; }
 const RtCameraDesc* rt_host_camera(const RtHostScene* hs, int i) { return (hs && i >= 0 && i < (int)hs->cameras.size()) ? &hs->cameras[i] : nullptr; }

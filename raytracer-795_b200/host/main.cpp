@@ -1,6 +1,7 @@
 // CLI with the reference's contract (src/main.cpp:7-14): `raytracer scene.xml` renders every camera of the scene
 // and writes each camera's <ImageName> (P3 PPM for "*.png*" names, half-float EXR otherwise, src/Image.cpp:26-34).
 // Extra, optional knobs after the scene path:  --f32 (also dump <ImageName>.f32 raw floats)  --device N
+// --cache (keep / reuse <scene.xml>.rt795blob, the prepared scene, while its sources are unchanged)
 // --integrator path|reference  --bvh auto|host|device (per-mesh BVH builder)  --seed S  --tonemap KEY BURN SAT GAMMA (writes <ImageName>.tm.ppm)
 #include "../../include/rt795.h"
 #include <cstdio>
@@ -10,8 +11,8 @@
 #include <vector>
 
 int main(int argc, char* argv[]) {
-    if (argc < 2) { fprintf(stderr, "usage: %s scene.xml [--f32] [--device N] [--integrator path|reference] [--bvh auto|host|device] [--seed S] [--tonemap key burn sat gamma]\n", argv[0]); return 2; }
-    bool f32 = false, tonemap = false;
+    if (argc < 2) { fprintf(stderr, "usage: %s scene.xml [--f32] [--cache] [--device N] [--integrator path|reference] [--bvh auto|host|device] [--seed S] [--tonemap key burn sat gamma]\n", argv[0]); return 2; }
+    bool f32 = false, tonemap = false, cache = false;
     int device = 0, bvh = RT_BVH_AUTO;
     float tm[4] = {0.18f, 1.0f, 1.0f, 2.2f};
     RtRenderOpts opts;
@@ -19,6 +20,7 @@ int main(int argc, char* argv[]) {
     opts.seed = 795; opts.pt_nee = 1; opts.pt_russian_roulette = 1; opts.pt_importance = 1;
     for (int i = 2; i < argc; i++) {
         if (!strcmp(argv[i], "--f32")) f32 = true;
+        else if (!strcmp(argv[i], "--cache")) cache = true;
         else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--seed") && i + 1 < argc) opts.seed = strtoull(argv[++i], nullptr, 10);
         else if (!strcmp(argv[i], "--integrator") && i + 1 < argc) opts.integrator = !strcmp(argv[++i], "path") ? RT_INTEGRATOR_PATH : RT_INTEGRATOR_REFERENCE;
@@ -27,7 +29,8 @@ int main(int argc, char* argv[]) {
         else { fprintf(stderr, "unknown option %s\n", argv[i]); return 2; }
     }
     RtHostScene* hs = nullptr;
-    if (rt_host_load_scene(argv[1], &hs) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }
+    int hit = 0;
+    if ((cache ? rt_host_load_scene_cached(argv[1], nullptr, &hs, &hit) : rt_host_load_scene(argv[1], &hs)) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }
     RtScene* sc = nullptr;
     RtSceneDesc desc = *rt_host_scene_desc(hs);
     desc.bvh_builder = bvh;

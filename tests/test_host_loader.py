@@ -237,3 +237,73 @@ def test_malformed_inputs_are_errors_not_crashes(rt, tmp_path):
     p = write_scene(str(tmp_path / "c"), textures=tex, objects='<Mesh id="1"><Material>1</Material><Textures>1</Textures><Faces>1 2 3</Faces></Mesh>')
     with pytest.raises(rt.RtError):
         rt.HostScene(p)
+
+
+# ---- scene blob (scene ingest)
+def _desc_bytes(rt, hs):
+    """Every array + scalar the core sees, as comparable python values."""
+    import ctypes as C
+    d = hs.desc.contents
+    out = {"scalars": (d.max_recursion_depth, d.shadow_ray_eps, d.int_test_eps, tuple(d.background_color), tuple(d.ambient_light), d.env_light_index,
+                       d.background_texture, d.num_vertices, d.num_texcoords, d.num_triangles, d.num_meshes, d.num_spheres, d.num_objects,
+                       d.num_materials, d.num_textures, d.num_images, d.num_lights)}
+    def raw(ptr, n, elem):
+        return C.string_at(ptr, n * elem) if n and ptr else b""
+    out["vertices"] = raw(d.vertices, d.num_vertices * 3, 4)
+    out["normals"] = raw(d.vertex_normals, d.num_vertices * 3, 4) if d.vertex_normals else b""
+    out["texcoords"] = raw(d.texcoords, d.num_texcoords * 2, 4)
+    out["tris"] = raw(d.tri_indices, d.num_triangles * 3, 4)
+    for name, n in (("meshes", d.num_meshes), ("spheres", d.num_spheres), ("objects", d.num_objects), ("materials", d.num_materials),
+                    ("textures", d.num_textures), ("lights", d.num_lights)):
+        arr = getattr(d, name)
+        out[name] = raw(arr, n, C.sizeof(arr._type_)) if n else b""
+    out["images"] = [(d.images[i].width, d.images[i].height, d.images[i].format,
+                      C.string_at(d.images[i].pixels, d.images[i].width * d.images[i].height * (4 if d.images[i].format == rt.RT_IMG_RGBA8 else 16)))
+                     for i in range(d.num_images)]
+    out["cameras"] = [(bytes(hs.camera(i)), hs.image_name(i)) for i in range(hs.num_cameras)]
+    return out
+
+
+def test_scene_blob_round_trip_staleness_and_corruption(rt, tmp_path):
+    d = str(tmp_path / "blob")
+    xml = rt.scenes.scene_c4(d, res=(64, 36), spp=4, n=24, deterministic=True)      # PLY mesh + instances + EXR image + Perlin textures
+    a = rt.HostScene(xml)
+    blob = os.path.join(d, "scene.blob")
+    a.save_blob(blob)
+    b = rt.HostScene(blob=blob)
+    assert _desc_bytes(rt, a) == _desc_bytes(rt, b)                                   # bit-identical prepared scene
+    b.close()
+
+    # cached loader: miss (writes <xml>.rt795blob), then hit
+    c1 = rt.HostScene(xml, cached=True)
+    assert not c1.cache_hit and os.path.exists(xml + ".rt795blob")
+    c2 = rt.HostScene(xml, cached=True)
+    assert c2.cache_hit and _desc_bytes(rt, a) == _desc_bytes(rt, c2)
+    c1.close(); c2.close()
+
+    # a changed source file makes the blob stale: explicit load refuses, the cached loader re-parses and rewrites
+    ply = os.path.join(d, "c4_mesh.ply")
+    st = os.stat(ply)
+    os.utime(ply, ns=(st.st_atime_ns, st.st_mtime_ns + 5_000_000_000))
+    with pytest.raises(rt.RtError, match="stale"):
+        rt.HostScene(blob=blob)
+    rt.HostScene(blob=blob, check_sources=False).close()                              # the caller may vouch for the sources
+    c3 = rt.HostScene(xml, cached=True)
+    assert not c3.cache_hit
+    c3.close()
+    c4 = rt.HostScene(xml, cached=True)
+    assert c4.cache_hit
+    c4.close()
+
+    # corruption: wrong magic, truncation, absurd counts - errors, never crashes
+    data = open(blob, "rb").read()
+    bad = os.path.join(d, "bad.blob")
+    for mutate in (lambda x: b"NOTABLOB" + x[8:], lambda x: x[: len(x) // 2], lambda x: x[:-3],
+                   lambda x: x[:16] + struct.pack("<Q", 1 << 60) + x[24:], lambda x: b""):
+        with open(bad, "wb") as f:
+            f.write(mutate(data))
+        with pytest.raises(rt.RtError):
+            rt.HostScene(blob=bad, check_sources=False)
+    with pytest.raises(rt.RtError):
+        rt.HostScene(blob=os.path.join(d, "missing.blob"))
+    a.close()
