@@ -139,7 +139,7 @@ def load_core() -> C.CDLL:
         if not os.path.exists(CORE_SO):
             raise RuntimeError(f"{CORE_SO} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(make -C raytracer-795_b200). There is no CPU fallback.")
-        lib = C.CDLL(CORE_SO)
+        lib = C.CDLL(os.environ.get("RT795_CORE_SO", CORE_SO))      # RT795_CORE_SO: A/B builds of the same library (profiles/ab_*.sh)
         P = C.POINTER
         lib.rt_scene_create.argtypes = [P(RtSceneDesc), C.c_int, P(C.c_void_p)]
         lib.rt_scene_destroy.argtypes = [C.c_void_p]

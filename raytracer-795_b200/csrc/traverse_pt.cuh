@@ -13,6 +13,9 @@
 // the full warp, blocked lanes idling inside the phase) raises the leaf-phase batch from 3.0 to 10.8 lanes (occlusion) and
 // 12.9 to 18.9 (closest hit) but drops the node-step batch from 15.9 to 11.8 and 24.2 to 20.0 lanes because leaf holders
 // wait for the slowest searcher: C4 frame 68.7 -> 77.0 ms.  The loose votes over __activemask() below are faster.
+// Second dead end: 2 / 4 pending-leaf slots per lane instead of one (sibling leaves of a 4-wide node arrive in groups).  Leaf
+// phases drop 64.6 M -> 23.5 M (occlusion, 4 slots) and their batch rises 2.5 -> 4.3 lanes, but the extra speculative node
+// visits (8.28 -> 8.92 per ray) cost as much: occlusion stage +1.0 ms, closest hit -0.5 ms, frame +1 ms.
 #pragma once
 #include "shade.cuh"
 #include "traverse.cuh"
@@ -54,7 +57,13 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
     // Traversal stack: (node, t_entry) packed into 64 bits (one LDL.64 / STL.64 per entry) with the TOP entry cached in
     // registers, so a pop hands out the cached entry and the reload of the next one overlaps the work on the popped node
     // (ncu r01b: 26 % of the samples sat in the pop loop waiting on two dependent local loads with ~7 lanes active).
-    unsigned long long stack[kStackSize];
+    // Occlusion queries never cull stack entries (every t_entry is 0), so their stack holds bare 32-bit node refs: half the
+    // local-memory wavefronts per push / pop (the L1 wavefront rate is that kernel's busiest unit, ncu r01e).  C4: occlusion
+    // stage 35.3 -> 33.5 ms.  (Keeping the first 8..40 entries of each lane's stack in shared memory, [entry][thread] so that
+    // divergent depths stay conflict-free, measured SLOWER: occlusion 33.5 -> 37.5 ms, closest hit 17.5 -> 17.8 ms - the
+    // shared/local select per access and the L1 capacity given up to the carve-out cost more than the wavefronts saved.)
+    unsigned long long stack[ANY_HIT ? 1 : kStackSize];
+    int stack32[ANY_HIT ? kStackSize : 1];
     int sp = 0;
     int top_n = kSentinel; float top_t = 0.f;
     int sgx = 0, sgy = 0, sgz = 0;   // 1 where the current (world or object space) direction component is negative
@@ -79,19 +88,20 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
     } while (0)
 #define RT_PUSH(N, T)                                                                                  \
     do {                                                                                               \
-        stack[sp++] = ((unsigned long long)__float_as_uint(top_t) << 32) | (unsigned)top_n;            \
-        top_n = (N); top_t = (T);                                                                      \
+        if (ANY_HIT) { stack32[sp++] = top_n; top_n = (N); }                                           \
+        else {                                                                                         \
+            stack[sp++] = ((unsigned long long)__float_as_uint(top_t) << 32) | (unsigned)top_n;        \
+            top_n = (N); top_t = (T);                                                                  \
+        }                                                                                              \
     } while (0)
 #define RT_POP1()                                                                                      \
     do {                                                                                               \
         node = top_n;                                                                                  \
-        if (node != kSentinel) {                                                                       \
-            unsigned long long e_ = stack[--sp];                                                       \
-            top_n = (int)(unsigned)e_; top_t = __uint_as_float((unsigned)(e_ >> 32));                  \
-        }                                                                                              \
+        if (node != kSentinel) top_n = stack32[--sp];                                                  \
     } while (0)
 #define RT_POP()                                                                                       \
-    do { for (;;) {                                                                                    \
+    do { if (ANY_HIT) { RT_POP1(); break; }                                                            \
+      for (;;) {                                                                                       \
         node = top_n;                                                                                  \
         if (node == kSentinel) break;                                                                  \
         float tt_ = top_t;                                                                             \
