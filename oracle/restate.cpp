@@ -614,12 +614,16 @@ V3 LightShading(const Ctx& cx, int li, const Ray& ray, const Hit& ret, const RtM
         case RT_LIGHT_ENVIRONMENT: {                                                             // src/Light.cpp:551-660
             V3 u = OrthonormalU(n), w = cross(n, u);
             V3 dir = n;
-            for (int it = 0; it < 64; it++) {     // rejection sampling in the unit ball, upper hemisphere (:634-648); bounded here
-                Rng4 r = philox(cx.seed, pixel, sample, node, DIM_LIGHT0 + li * DIM_LIGHT_STRIDE + it);
-                float x = r.u[0] * 2 - 1.0f, y = r.u[1] * 2 - 1.0f, z = r.u[2] * 2 - 1.0f;
-                V3 smp = p + u * x + n * y + w * z;
-                V3 d = smp - p;
-                if (dot(d, n) > 0 && norm(d) <= 1) { dir = normalized(d); break; }
+            {
+                // The reference rejection-samples the unit ball and keeps the upper half (:634-648); the normalised direction is
+                // uniform over the hemisphere about n.  Restated as the direct draw of that same distribution (cos(theta) uniform
+                // in [0,1], phi uniform) because the product kernel does so (csrc/shade.cuh); the reference's RNG is
+                // unseeded, so only the distribution can be pinned - tests/test_oracle_pin.py checks it against the reference binary.
+                Rng4 r = philox(cx.seed, pixel, sample, node, DIM_LIGHT0 + li * DIM_LIGHT_STRIDE);
+                float c = r.u[0], sn = std::sqrt(std::max(0.f, 1.f - c * c));
+                float ph = 2.0f * 3.14159265358979323846f * r.u[1];
+                float sp_ = std::sin(ph), cp_ = std::cos(ph);
+                dir = normalized(u * (sn * cp_) + n * c + w * (sn * sp_));
             }
             Ray sr{origin, dir, ray.time};
             if (FindIntersection(cx, sr).full) return V3(0, 0, 0);

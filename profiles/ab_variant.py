@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One line per library variant (RT795_CORE_SO): frame time, per-stage times, SIMT diagnostics of the traversal kernels.
-usage: RT795_CORE_SO=... python profiles/ab_variant.py [config] [frames]"""
+usage: RT795_CORE_SO=... python profiles/ab_variant.py [config] [frames] [spp]"""
 import os
 import sys
 
@@ -12,7 +12,9 @@ import bench  # noqa: E402
 rt = ge.load_package()
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c4"
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-xml = bench.make_scene(rt, cfg, bench.WORKLOADS[cfg][0], "full")
+spp = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+kw = bench.WORKLOADS[cfg][0]
+xml = bench.make_scene(rt, cfg, dict(kw, spp=spp) if spp else kw, f"full_spp{spp}" if spp else "full")
 hs = rt.HostScene(xml)
 sc = rt.Scene(hs.desc, 0, bvh_builder=rt.RT_BVH_HOST_SAH)
 cam = hs.camera(0)
