@@ -1,0 +1,73 @@
+"""Two real GPUs (skipped on a one-GPU box): the p2p frame gather - every rank's resolve kernel storing its own tiles into
+rank 0's framebuffer over NVLink peer memory (multigpu.FrameGather, RtRenderOpts.resolve_owned_only) - against the
+single-GPU frame, and against the NCCL reduce fallback."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, xml, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    rt = ge.load_package()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    hs = rt.HostScene(xml)
+    cam = hs.camera(0)
+    sc = rt.Scene(hs.desc, rank)
+    stream = torch.cuda.current_stream()
+    for mode in ("p2p", "nccl"):
+        g = rt.multigpu.FrameGather(cam.nx * cam.ny * 3, dev, mode=mode)
+        if rank == 0:
+            g.frame.fill_(float("nan"))                                   # every pixel must be written by exactly one rank
+        dist.barrier(); torch.cuda.synchronize()
+        if g.mode == "nccl":
+            g.frame.zero_()
+        o = rt.default_opts(tile_rank=rank, tile_count=world, resolve_owned_only=g.resolve_owned_only)
+        sc.render_device(cam, o, g.out_ptr, stream.cuda_stream)
+        g.finish()
+        torch.cuda.synchronize(); dist.barrier()
+        if rank == 0:
+            np.save(os.path.join(out_dir, f"{mode}_{g.mode}.npy"), g.frame.cpu().numpy().reshape(cam.ny, cam.nx, 3))
+    if rank == 0:
+        alone = torch.empty(cam.nx * cam.ny * 3, dtype=torch.float32, device=dev)
+        sc.render_device(cam, rt.default_opts(), alone.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        np.save(os.path.join(out_dir, "alone.npy"), alone.cpu().numpy().reshape(cam.ny, cam.nx, 3))
+    dist.barrier()
+    sc.close(); hs.close()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_p2p_gather_matches_single_gpu(rt, scene_dir, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    xml = rt.scenes.scene_c3(os.path.join(scene_dir, "c3p2p"), res=(203, 117), spp=4, n=48)
+    mp.start_processes(_worker, args=(2, _free_port(), xml, str(tmp_path)), nprocs=2, join=True, start_method="spawn")
+    alone = np.load(tmp_path / "alone.npy")
+    files = sorted(f for f in os.listdir(tmp_path) if f.endswith(".npy") and f != "alone.npy")
+    assert any(f.startswith("p2p_") for f in files) and "nccl_nccl.npy" in files
+    for f in files:
+        got = np.load(tmp_path / f)
+        assert np.isfinite(got).all(), f
+        assert np.allclose(got, alone, rtol=1e-5, atol=1e-5), f

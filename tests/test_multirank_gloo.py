@@ -32,8 +32,12 @@ def _worker(rank, world, port, xml, out_path):
     mask = rt.tiling.tile_mask(cam.nx, cam.ny, rank, world)
     assert mask.sum() > 0
     part = np.where(mask[..., None], full, 0.0).astype(np.float32)
-    t = torch.from_numpy(part)
-    dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+    # the same helper bench.py uses at N>1, on its reduce path (gloo has no peer memory): frame buffer + finish()
+    gather = rt.multigpu.FrameGather(part.size, torch.device("cpu"), mode="nccl")
+    assert gather.mode == "nccl" and gather.resolve_owned_only == 0 and gather.out_ptr == gather.frame.data_ptr()
+    gather.frame.copy_(torch.from_numpy(part).reshape(-1))
+    gather.finish()
+    t = gather.frame.reshape(part.shape)
     cover = torch.from_numpy(mask.astype(np.int32))
     dist.reduce(cover, dst=0, op=dist.ReduceOp.SUM)
     if rank == 0:
