@@ -231,8 +231,15 @@ bool BuildAndUpload(RtScene* sc, const RtSceneDesc* s, bool allow_device) {
         bool want_device = builder == RT_BVH_DEVICE_PLOC ? me.tri_count >= 8 : builder == RT_BVH_AUTO && me.tri_count >= kDeviceBuildMinTris;
         if (want_device) {
             // depth limits leave room for a TLAS of the same order as the host's (checked exactly below; a miss rebuilds on the host)
-            sg.on_device = BuildBlasOnDevice(sc->vertices.p, sc->tri_idx.p, me.first_tri, me.tri_count, eps, node_base, base4, tri_base,
-                                             kStackSize - 12, kStackSize - 12, st, &sg.dev);
+            try {
+                sg.on_device = BuildBlasOnDevice(sc->vertices.p, sc->tri_idx.p, me.first_tri, me.tri_count, eps, node_base, base4, tri_base,
+                                                 kStackSize - 12, kStackSize - 12, st, &sg.dev);
+            } catch (const std::exception&) {
+                // e.g. not enough free HBM for the builder's temporaries: the host builder needs none.  A sticky CUDA error
+                // resurfaces at the next CK() below with its own message.
+                cudaGetLastError();
+                sg.on_device = false;
+            }
             if (sg.on_device) {
                 sg.n2 = sg.dev.n2; sg.n4 = sg.dev.n4; sg.ntris = sg.dev.tri_count;
                 mesh_depth[m] = sg.dev.depth2; mesh_stack4[m] = sg.dev.max_stack4; mesh_bounds[m] = sg.dev.bounds;

@@ -4,6 +4,7 @@
 // --cache (keep / reuse <scene.xml>.rt795blob, the prepared scene, while its sources are unchanged)
 // --integrator path|reference  --bvh auto|host|device (per-mesh BVH builder)  --seed S  --tonemap KEY BURN SAT GAMMA (writes <ImageName>.tm.ppm)
 #include "../../include/rt795.h"
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -28,18 +29,37 @@ int main(int argc, char* argv[]) {
         else if (!strcmp(argv[i], "--tonemap") && i + 4 < argc) { tonemap = true; for (int k = 0; k < 4; k++) tm[k] = (float)atof(argv[++i]); }
         else { fprintf(stderr, "unknown option %s\n", argv[i]); return 2; }
     }
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    // One process renders on one GPU: hide the others before the CUDA runtime starts, so its initialisation touches a single
+    // device (on an 8-GPU box the start-up of the runtime is the largest part of a one-frame run).
+    if (!getenv("CUDA_VISIBLE_DEVICES")) { setenv("CUDA_VISIBLE_DEVICES", std::to_string(device).c_str(), 1); device = 0; }
+    auto t0 = now();
     RtHostScene* hs = nullptr;
     int hit = 0;
     if ((cache ? rt_host_load_scene_cached(argv[1], nullptr, &hs, &hit) : rt_host_load_scene(argv[1], &hs)) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }
+    auto t1 = now();
+    int ndev = rt_device_count();                                        // first CUDA call: runtime + driver initialisation
+    auto t1b = now();
+    if (ndev <= 0) { fprintf(stderr, "no CUDA device: %s\n", rt_last_error()); return 1; }
     RtScene* sc = nullptr;
     RtSceneDesc desc = *rt_host_scene_desc(hs);
     desc.bvh_builder = bvh;
     if (rt_scene_create(&desc, device, &sc) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }
+    auto t2 = now();
     printf("BVH construction complete.\n");
+    {
+        RtStats st;
+        rt_get_stats(sc, &st);
+        fprintf(stderr, "scene: load %.1f ms%s, CUDA start-up %.1f ms, create %.1f ms (BVH build %.1f ms, %d mesh(es) on the GPU; upload %.1f ms)\n", ms(t0, t1),
+                cache ? (hit ? " (blob)" : " (parsed, blob written)") : "", ms(t1, t1b), ms(t1b, t2), st.ms_bvh_build, st.bvh_device_meshes, st.ms_upload);
+    }
     for (int c = 0; c < rt_host_num_cameras(hs); c++) {
         const RtCameraDesc* cam = rt_host_camera(hs, c);
         std::vector<float> img((size_t)cam->nx * cam->ny * 3);
+        auto r0 = now();
         if (rt_render(sc, cam, &opts, img.data()) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }
+        auto r1 = now();
         RtStats st;
         rt_get_stats(sc, &st);
         double rays = (double)(st.rays_primary + st.rays_secondary + st.rays_shadow);
@@ -54,7 +74,9 @@ int main(int argc, char* argv[]) {
             FILE* f = fopen(p.c_str(), "wb");
             if (f) { fprintf(f, "P6\n%d %d\n255\n", cam->nx, cam->ny); fwrite(ldr.data(), 1, ldr.size(), f); fclose(f); }
         }
+        auto w0 = now();
         if (rt_host_save_image(name, img.data(), cam->nx, cam->ny) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }
+        fprintf(stderr, "camera %d: rt_render call %.1f ms (first call allocates the ray queues), image write %.1f ms\n", c, ms(r0, r1), ms(w0, now()));
     }
     rt_scene_destroy(sc);
     rt_host_free_scene(hs);
