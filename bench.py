@@ -218,9 +218,8 @@ def run_ours(args, rt):
     xml = make_scene(rt, args.config, full_kw, tag)
     hs = rt.HostScene(xml)
     cam = hs.camera(0)
-    # the scene is built once and rendered steps+warmup times: ask for the builder that gives the best tree (host binned SAH); the
-    # library default (AUTO) builds big meshes on the GPU ~40x faster for a ~2.5 % slower frame (profiles/bench/r01_bvh_builders_c4.json)
-    builder = {"host": rt.RT_BVH_HOST_SAH, "device": rt.RT_BVH_DEVICE_PLOC, "auto": rt.RT_BVH_AUTO}[args.bvh]
+    # library default (AUTO): big meshes get the host builder's binned-SAH tree, built on the GPU (profiles/bench/r01_bvh_builders_c4.json)
+    builder = {"host": rt.RT_BVH_HOST_SAH, "ploc": rt.RT_BVH_DEVICE_PLOC, "sah": rt.RT_BVH_DEVICE_SAH, "auto": rt.RT_BVH_AUTO}[args.bvh]
     sc = rt.Scene(hs.desc, local, bvh_builder=builder)
     integrator = rt.RT_INTEGRATOR_PATH if args.config == "c5" else rt.RT_INTEGRATOR_REFERENCE
     npix = cam.nx * cam.ny
@@ -388,7 +387,7 @@ def main():
     ap.add_argument("--config", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--small", action="store_true", help="use the bounded sample configuration (smoke runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--bvh", default="host", choices=["host", "device", "auto"], help="per-mesh BVH builder (RtSceneDesc.bvh_builder)")
+    ap.add_argument("--bvh", default="auto", choices=["host", "ploc", "sah", "auto"], help="per-mesh BVH builder (RtSceneDesc.bvh_builder)")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel of the workload (exploration; the headline run uses the configuration's own)")
     args = ap.parse_args()
     rt = ge.load_package()

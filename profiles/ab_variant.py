@@ -16,7 +16,7 @@ spp = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 kw = bench.WORKLOADS[cfg][0]
 xml = bench.make_scene(rt, cfg, dict(kw, spp=spp) if spp else kw, f"full_spp{spp}" if spp else "full")
 hs = rt.HostScene(xml)
-sc = rt.Scene(hs.desc, 0, bvh_builder=rt.RT_BVH_HOST_SAH)
+sc = rt.Scene(hs.desc, 0)
 cam = hs.camera(0)
 integ = rt.RT_INTEGRATOR_PATH if cfg == "c5" else rt.RT_INTEGRATOR_REFERENCE
 best = 1e9

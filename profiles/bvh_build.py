@@ -22,7 +22,7 @@ cam = hs.camera(0)
 integ = rt.RT_INTEGRATOR_PATH if cfg == "c5" else rt.RT_INTEGRATOR_REFERENCE
 rt.Scene(hs.desc, 0, bvh_builder=rt.RT_BVH_HOST_SAH).close()          # CUDA context + first-use costs out of the way
 out = {"config": cfg, "ms_host_load_scene": t_load, "builders": {}}
-for name, b in (("host_sah", rt.RT_BVH_HOST_SAH), ("device_ploc", rt.RT_BVH_DEVICE_PLOC)):
+for name, b in (("host_sah", rt.RT_BVH_HOST_SAH), ("device_ploc", rt.RT_BVH_DEVICE_PLOC), ("device_sah", rt.RT_BVH_DEVICE_SAH)):
     t0 = time.perf_counter()
     sc = rt.Scene(hs.desc, 0, bvh_builder=b)
     t_create = (time.perf_counter() - t0) * 1e3

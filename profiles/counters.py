@@ -16,7 +16,7 @@ full_kw, sample_kw = bench.WORKLOADS[cfg]
 kw = sample_kw if "--small" in sys.argv else full_kw
 xml = bench.make_scene(rt, cfg, kw, "small" if "--small" in sys.argv else "full")
 hs = rt.HostScene(xml)
-sc = rt.Scene(hs.desc, 0, bvh_builder=rt.RT_BVH_HOST_SAH)   # the builder bench.py uses
+sc = rt.Scene(hs.desc, 0)
 cam = hs.camera(0)
 integ = rt.RT_INTEGRATOR_PATH if cfg == "c5" else rt.RT_INTEGRATOR_REFERENCE
 sc.render(cam, rt.default_opts(integrator=integ))

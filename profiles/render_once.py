@@ -17,7 +17,7 @@ full_kw, sample_kw = bench.WORKLOADS[cfg]
 small = "--small" in sys.argv
 xml = bench.make_scene(rt, cfg, sample_kw if small else full_kw, "small" if small else "full")
 hs = rt.HostScene(xml)
-sc = rt.Scene(hs.desc, 0, bvh_builder=rt.RT_BVH_HOST_SAH)   # the builder bench.py uses
+sc = rt.Scene(hs.desc, 0)
 cam = hs.camera(0)
 integ = rt.RT_INTEGRATOR_PATH if cfg == "c5" else rt.RT_INTEGRATOR_REFERENCE
 for _ in range(frames):

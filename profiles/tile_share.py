@@ -17,7 +17,7 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 frames = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 6
 xml = bench.make_scene(rt, cfg, bench.WORKLOADS[cfg][0], "full")
 hs = rt.HostScene(xml)
-sc = rt.Scene(hs.desc, 0, bvh_builder=rt.RT_BVH_HOST_SAH)   # the builder bench.py uses
+sc = rt.Scene(hs.desc, 0)
 cam = hs.camera(0)
 integ = rt.RT_INTEGRATOR_PATH if cfg == "c5" else rt.RT_INTEGRATOR_REFERENCE
 if "--ranks" in sys.argv:                                   # per-rank device time: the load balance of the interleaved partition

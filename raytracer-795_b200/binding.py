@@ -21,7 +21,7 @@ ORACLE_REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 RT_OK = 0
 (RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_OOM, RT_ERR_IO, RT_ERR_PARSE, RT_ERR_OVERFLOW) = (-1, -2, -3, -4, -5, -6)
 RT_INTEGRATOR_REFERENCE, RT_INTEGRATOR_PATH = 0, 1
-RT_BVH_AUTO, RT_BVH_HOST_SAH, RT_BVH_DEVICE_PLOC = 0, 1, 2
+RT_BVH_AUTO, RT_BVH_HOST_SAH, RT_BVH_DEVICE_PLOC, RT_BVH_DEVICE_SAH = 0, 1, 2, 3
 RT_DEBUG_BVH2, RT_DEBUG_BVH4, RT_DEBUG_BVH4Q, RT_DEBUG_TRIS, RT_DEBUG_OBJ_ROOT4 = 0, 1, 2, 3, 4
 RT_OBJ_SPHERE, RT_OBJ_MESH = 0, 1
 RT_IMG_RGBA8, RT_IMG_RGBA32F = 0, 1

@@ -67,6 +67,10 @@ __device__ __forceinline__ void atomic_max_f(float* a, float v) {
     if (v >= 0.f) atomicMax(reinterpret_cast<int*>(a), __float_as_int(v)); else atomicMin(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
 }
 
+// Monotone float <-> int maps, so __reduce_min_sync / __reduce_max_sync (integer only) can reduce floats inside a lane group.
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
 // ---- B1: padded triangle boxes + bounds of their centres
 __global__ void __launch_bounds__(kTB) k_prim_bounds(const float* __restrict__ v, const int32_t* __restrict__ ix, int n, float eps,
                                                      float4* __restrict__ plo, float4* __restrict__ phi, float* cb) {
@@ -83,9 +87,11 @@ __global__ void __launch_bounds__(kTB) k_prim_bounds(const float* __restrict__ v
         float ext = fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z));
         // same rule as the host builder (core.cu BuildAndUpload): the reference accepts beta, gamma >= -eps, i.e. hits up to
         // eps*edge outside the triangle, so the box is padded to stay conservative
-        float px = 2.0f * eps * ext + 4.0e-7f * fmaxf(fabsf(lo.x), fabsf(hi.x)) + 1e-30f;
-        float py = 2.0f * eps * ext + 4.0e-7f * fmaxf(fabsf(lo.y), fabsf(hi.y)) + 1e-30f;
-        float pz = 2.0f * eps * ext + 4.0e-7f * fmaxf(fabsf(lo.z), fabsf(hi.z)) + 1e-30f;
+        // (explicit roundings, no FMA contraction: bit-identical to the host's boxes, so the device SAH sees the host's input)
+        float pe = __fmul_rn(__fmul_rn(2.0f, eps), ext);
+        float px = __fadd_rn(__fadd_rn(pe, __fmul_rn(4.0e-7f, fmaxf(fabsf(lo.x), fabsf(hi.x)))), 1e-30f);
+        float py = __fadd_rn(__fadd_rn(pe, __fmul_rn(4.0e-7f, fmaxf(fabsf(lo.y), fabsf(hi.y)))), 1e-30f);
+        float pz = __fadd_rn(__fadd_rn(pe, __fmul_rn(4.0e-7f, fmaxf(fabsf(lo.z), fabsf(hi.z)))), 1e-30f);
         lo = make_float3(lo.x - px, lo.y - py, lo.z - pz);
         hi = make_float3(hi.x + px, hi.y + py, hi.z + pz);
         plo[i] = make_float4(lo.x, lo.y, lo.z, 0.f);
@@ -277,36 +283,306 @@ __global__ void __launch_bounds__(kTB) k_emit_tris(int n, const int32_t* __restr
     o[2] = make_float4(c[0] - a[0], c[1] - a[1], c[2] - a[2], 0.f);
 }
 
-__global__ void __launch_bounds__(kTB) k_live_flags(int n, const uint8_t* __restrict__ state, int32_t* __restrict__ live) {
+// The finished binary tree lives in an "id space": ids [id_base, id_base + id_count) may be inner nodes (state 0), leaves of the
+// final tree (state 1: triangles [first, first + count) of the leaf-ordered array) or unused (state 2).  PLOC: id_base = n
+// (triangle leaves are ids 0..n-1), root = last id, numbered in reverse creation order.  Device SAH: id_base = 0, root = 0.
+__global__ void __launch_bounds__(kTB) k_live_flags(int id_base, int id_count, const uint8_t* __restrict__ state, int32_t* __restrict__ live) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n - 1) live[t] = state[n + t] == 0 ? 1 : 0;
+    if (t < id_count) live[t] = state[id_base + t] == 0 ? 1 : 0;
 }
 
 __device__ __forceinline__ int32_t encode_leaf(int32_t first, int32_t count) { return ~((first << 3) | (count - 1)); }
 
-// Binary nodes in reverse creation order (the root, created last, becomes node 0; nodes merged in the same PLOC iteration
-// are neighbours on the Morton curve and stay neighbours in memory).
-__global__ void __launch_bounds__(kTB) k_emit_bvh2(int n, int live_total, const int32_t* __restrict__ live, const int32_t* __restrict__ lscan,
-                                                   const int2* __restrict__ child, const uint8_t* __restrict__ state, const int32_t* __restrict__ first,
-                                                   const int32_t* __restrict__ meta, const float4* __restrict__ nlo, const float4* __restrict__ nhi,
-                                                   int node_base, int tri_base, float4* __restrict__ nodes2) {
+// Binary nodes, numbered by the scan of the live flags (PLOC: reversed, so the root - created last - becomes node 0 and nodes
+// merged in the same iteration, neighbours on the Morton curve, stay neighbours in memory).
+__global__ void __launch_bounds__(kTB) k_emit_bvh2(int id_base, int id_count, int reverse, int live_total, const int32_t* __restrict__ live,
+                                                   const int32_t* __restrict__ lscan, const int2* __restrict__ child, const uint8_t* __restrict__ state,
+                                                   const int32_t* __restrict__ first, const int32_t* __restrict__ meta, const float4* __restrict__ nlo,
+                                                   const float4* __restrict__ nhi, int node_base, int tri_base, float4* __restrict__ nodes2) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n - 1 || !live[t]) return;
-    int idx = live_total - 1 - lscan[t];
-    int2 ch = child[n + t];
+    if (t >= id_count || !live[t]) return;
+    int idx = reverse ? live_total - 1 - lscan[t] : lscan[t];
+    int2 ch = child[id_base + t];
     int c[2] = {ch.x, ch.y};
     int32_t ref[2];
     float4 lo[2], hi[2];
 #pragma unroll
     for (int s = 0; s < 2; s++) {
         lo[s] = nlo[c[s]]; hi[s] = nhi[c[s]];
-        ref[s] = state[c[s]] == 1 ? encode_leaf(tri_base + first[c[s]], meta[c[s]] & kCntMask) : node_base + (live_total - 1 - lscan[c[s] - n]);
+        if (state[c[s]] == 1) ref[s] = encode_leaf(tri_base + first[c[s]], meta[c[s]] & kCntMask);
+        else { int ls = lscan[c[s] - id_base]; ref[s] = node_base + (reverse ? live_total - 1 - ls : ls); }
     }
     float4* o = nodes2 + 4 * (size_t)idx;
     o[0] = make_float4(lo[0].x, hi[0].x, lo[0].y, hi[0].y);
     o[1] = make_float4(lo[1].x, hi[1].x, lo[1].y, hi[1].y);
     o[2] = make_float4(lo[0].z, hi[0].z, lo[1].z, hi[1].z);
     o[3] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), 0.f, 0.f);
+}
+
+// =====================================================================================================================
+// Device binned SAH (RT_BVH_DEVICE_SAH): the host builder's algorithm (bvh_build.cpp: 16 bins x 3 axes over the centroid
+// bounds, same costs, same leaf rule) run level-synchronously over ALL nodes of a level at once.  The primitive array is
+// never partitioned: each primitive carries the index of the node it currently belongs to (`pnode`) and is re-assigned
+// after its node's split is known; leaf ranges are made contiguous at the end by one stable sort on the leaf's DFS offset.
+// Per level: S1 centroid bounds per node (float atomics), S2 binning (atomics into the node's 3 x 16 bins), S3 split
+// selection per node (the host's sweep, same operation order), scan, S4 child creation, S5 re-assignment.
+constexpr int kSahBins = 16;
+constexpr int kSahMaxLeaf = 4;
+constexpr int kSahMaxDepth = 36;         // deeper levels fall back to Morton-position midpoint splits (the host falls back to medians)
+constexpr int kBinWords = 8;             // lo.xyz, hi.xyz, count, pad
+
+struct SahNodes {                        // build nodes, SoA; index = creation order, root = 0, children of a node are adjacent
+    float4 *lo, *hi;                     // primitive bounds
+    float4 *clo, *chi;                   // centroid bounds (S1)
+    int2* child;                         // (left, left + 1), or (-1, -1)
+    int32_t *parent, *meta;              // meta: count | kLeafBit
+    int32_t *pos_min, *pos_max;          // range of Morton positions of its primitives (fallback split)
+    int32_t *split;                      // S3 decision: -1 leaf, else axis | bin << 2 | fallback << 8
+    int32_t *pos_mid;
+};
+
+__global__ void __launch_bounds__(kTB) k_sah_init_nodes(SahNodes nd, int begin, int end) {
+    int b = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= end) return;
+    nd.clo[b] = make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f); nd.chi[b] = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, 0.f);
+    nd.pos_min[b] = 0x7fffffff; nd.pos_max[b] = -1;
+    nd.child[b] = make_int2(-1, -1);
+}
+
+__global__ void __launch_bounds__(kTB) k_sah_root(SahNodes nd, int n, const float4* __restrict__ plo, const float4* __restrict__ phi, int32_t* __restrict__ pnode) {
+    // root bounds: warp-reduced float atomics into node 0 (lo/hi initialised by the caller)
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float3 lo = make_float3(3.0e38f, 3.0e38f, 3.0e38f), hi = make_float3(-3.0e38f, -3.0e38f, -3.0e38f);
+    if (i < n) { lo = f3(plo[i]); hi = f3(phi[i]); pnode[i] = 0; }
+    const unsigned full = 0xffffffffu;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(full, lo.x, s)); lo.y = fminf(lo.y, __shfl_xor_sync(full, lo.y, s)); lo.z = fminf(lo.z, __shfl_xor_sync(full, lo.z, s));
+        hi.x = fmaxf(hi.x, __shfl_xor_sync(full, hi.x, s)); hi.y = fmaxf(hi.y, __shfl_xor_sync(full, hi.y, s)); hi.z = fmaxf(hi.z, __shfl_xor_sync(full, hi.z, s));
+    }
+    if ((threadIdx.x & 31) == 0 && lo.x <= hi.x) {
+        float* l = reinterpret_cast<float*>(nd.lo), *h = reinterpret_cast<float*>(nd.hi);
+        atomic_min_f(l + 0, lo.x); atomic_min_f(l + 1, lo.y); atomic_min_f(l + 2, lo.z);
+        atomic_max_f(h + 0, hi.x); atomic_max_f(h + 1, hi.y); atomic_max_f(h + 2, hi.z);
+    }
+}
+
+__device__ __forceinline__ float3 centre_of(float4 lo, float4 hi) { return make_float3(0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)); }
+
+// S1.  i = Morton position; order[i] = primitive.  Primitives whose node is older than this level sit in finished leaves.
+// Lanes of a warp that share a node (neighbours on the Morton curve: all of them near the top of the tree) reduce among
+// themselves first and issue one set of atomics per group instead of one per primitive.
+__global__ void __launch_bounds__(kTB) k_sah_cbounds(SahNodes nd, int n, int lvl_begin, const uint32_t* __restrict__ order, const float4* __restrict__ plo,
+                                                     const float4* __restrict__ phi, const int32_t* __restrict__ pnode) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = i < n ? pnode[i] : -1;
+    bool act = b >= lvl_begin;
+    unsigned am = __ballot_sync(0xffffffffu, act);
+    if (!act) return;
+    uint32_t p = order[i];
+    float3 c = centre_of(plo[p], phi[p]);
+    unsigned g = __match_any_sync(am, b);
+    int lx = __reduce_min_sync(g, f2ord(c.x)), ly = __reduce_min_sync(g, f2ord(c.y)), lz = __reduce_min_sync(g, f2ord(c.z));
+    int hx = __reduce_max_sync(g, f2ord(c.x)), hy = __reduce_max_sync(g, f2ord(c.y)), hz = __reduce_max_sync(g, f2ord(c.z));
+    int pmin = __reduce_min_sync(g, i), pmax = __reduce_max_sync(g, i);
+    if ((int)(threadIdx.x & 31) != __ffs(g) - 1) return;
+    float* l = reinterpret_cast<float*>(nd.clo + b), *h = reinterpret_cast<float*>(nd.chi + b);
+    atomic_min_f(l + 0, ord2f(lx)); atomic_min_f(l + 1, ord2f(ly)); atomic_min_f(l + 2, ord2f(lz));
+    atomic_max_f(h + 0, ord2f(hx)); atomic_max_f(h + 1, ord2f(hy)); atomic_max_f(h + 2, ord2f(hz));
+    atomicMin(nd.pos_min + b, pmin); atomicMax(nd.pos_max + b, pmax);
+}
+
+__global__ void __launch_bounds__(kTB) k_sah_init_bins(float* bins, long long nbins) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nbins) return;
+    float* w = bins + t * kBinWords;
+    w[0] = w[1] = w[2] = 3.0e38f; w[3] = w[4] = w[5] = -3.0e38f; w[6] = 0.f; w[7] = 0.f;   // w[6] holds the count as an int (bit pattern 0)
+}
+
+__device__ __forceinline__ int sah_bin(float c, float lo, float ext) {
+    float scale = (float)kSahBins / ext;                                 // as bvh_build.cpp Split(): scale = kBins / ext
+    int b = (int)((c - lo) * scale);
+    return b < 0 ? 0 : (b > kSahBins - 1 ? kSahBins - 1 : b);
+}
+
+// S2.  Same grouping as S1, per axis, on (node, bin).
+__global__ void __launch_bounds__(kTB) k_sah_bin(SahNodes nd, int n, int chunk_begin, int chunk_end, const uint32_t* __restrict__ order, const float4* __restrict__ plo,
+                                                 const float4* __restrict__ phi, const int32_t* __restrict__ pnode, float* bins) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = i < n ? pnode[i] : -1;
+    bool act = b >= chunk_begin && b < chunk_end;
+    if (act && (nd.meta[b] & kCntMask) <= 1) act = false;               // single-primitive node: a leaf, no split to evaluate
+    unsigned am = __ballot_sync(0xffffffffu, act);
+    if (!act) return;
+    uint32_t p = order[i];
+    float4 lo = plo[p], hi = phi[p];
+    float3 c = centre_of(lo, hi);
+    float4 cl = nd.clo[b], chh = nd.chi[b];
+    float cc[3] = {c.x, c.y, c.z}, cmin[3] = {cl.x, cl.y, cl.z}, cmax[3] = {chh.x, chh.y, chh.z};
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        float ext = cmax[a] - cmin[a];
+        bool ok = ext > 0.f;                                             // uniform over the lanes of a node
+        unsigned oka = __ballot_sync(am, ok);
+        if (!ok) continue;
+        int k = sah_bin(cc[a], cmin[a], ext);
+        unsigned g = __match_any_sync(oka, (b - chunk_begin) * kSahBins + k);
+        int lx = __reduce_min_sync(g, f2ord(lo.x)), ly = __reduce_min_sync(g, f2ord(lo.y)), lz = __reduce_min_sync(g, f2ord(lo.z));
+        int hx = __reduce_max_sync(g, f2ord(hi.x)), hy = __reduce_max_sync(g, f2ord(hi.y)), hz = __reduce_max_sync(g, f2ord(hi.z));
+        if (lane != __ffs(g) - 1) continue;
+        float* w = bins + (((long long)(b - chunk_begin) * 3 + a) * kSahBins + k) * kBinWords;
+        atomic_min_f(w + 0, ord2f(lx)); atomic_min_f(w + 1, ord2f(ly)); atomic_min_f(w + 2, ord2f(lz));
+        atomic_max_f(w + 3, ord2f(hx)); atomic_max_f(w + 4, ord2f(hy)); atomic_max_f(w + 5, ord2f(hz));
+        atomicAdd(reinterpret_cast<int*>(w + 6), __popc(g));
+    }
+}
+
+struct Box3 { float lo[3], hi[3]; };
+__device__ __forceinline__ void box_reset(Box3& b) { for (int k = 0; k < 3; k++) { b.lo[k] = 3.0e38f; b.hi[k] = -3.0e38f; } }
+__device__ __forceinline__ void box_grow(Box3& b, const float* w) { for (int k = 0; k < 3; k++) { if (w[k] < b.lo[k]) b.lo[k] = w[k]; if (w[3 + k] > b.hi[k]) b.hi[k] = w[3 + k]; } }
+__device__ __forceinline__ float box_half_area(const Box3& b) {          // Aabb::HalfArea, without FMA contraction: the host's rounding
+    float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
+    if (dx < 0 || dy < 0 || dz < 0) return 0.f;
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dy), __fmul_rn(dy, dz)), __fmul_rn(dz, dx));
+}
+
+// S3: the host's Split() on the bins of one node.  Writes the decision and the split flag (scanned into child positions).
+struct SahLevelTmp { float4 *llo, *lhi, *rlo, *rhi; int32_t *lc, *rc; };   // per node of the level: the chosen split's children
+__global__ void __launch_bounds__(128) k_sah_split(SahNodes nd, int lvl_begin, int chunk_begin, int chunk_end, int depth, const float* __restrict__ bins,
+                                                   int32_t* __restrict__ flag, SahLevelTmp tmp) {
+    int b = chunk_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= chunk_end) return;
+    int count = nd.meta[b] & kCntMask;
+    int decision = -1;
+    if (count > 1) {
+        float best_cost = 3.402823466e38f;
+        int best_axis = -1, best_split = -1;
+        if (depth < kSahMaxDepth) {
+            float4 cl = nd.clo[b], chh = nd.chi[b];
+            float cmin[3] = {cl.x, cl.y, cl.z}, cmax[3] = {chh.x, chh.y, chh.z};
+            for (int a = 0; a < 3; a++) {
+                if (!(cmax[a] - cmin[a] > 0.f)) continue;
+                const float* w = bins + ((long long)(b - chunk_begin) * 3 + a) * kSahBins * kBinWords;
+                float ra[kSahBins]; int rc[kSahBins];
+                Box3 acc; box_reset(acc); int c = 0;
+                for (int k = kSahBins - 1; k >= 1; k--) { box_grow(acc, w + k * kBinWords); c += __float_as_int(w[k * kBinWords + 6]); ra[k] = box_half_area(acc); rc[k] = c; }
+                box_reset(acc); c = 0;
+                for (int k = 0; k < kSahBins - 1; k++) {
+                    box_grow(acc, w + k * kBinWords); c += __float_as_int(w[k * kBinWords + 6]);
+                    if (c == 0 || rc[k + 1] == 0) continue;
+                    float cost = __fadd_rn(__fmul_rn(box_half_area(acc), (float)c), __fmul_rn(ra[k + 1], (float)rc[k + 1]));
+                    if (cost < best_cost) { best_cost = cost; best_axis = a; best_split = k; }
+                }
+            }
+        }
+        float4 l = nd.lo[b], h = nd.hi[b];
+        Box3 nb; nb.lo[0] = l.x; nb.lo[1] = l.y; nb.lo[2] = l.z; nb.hi[0] = h.x; nb.hi[1] = h.y; nb.hi[2] = h.z;
+        float area = box_half_area(nb);
+        float leaf_cost = (float)count;                                  // kIntersectCost * count
+        float split_cost = best_axis >= 0 && area > 0 ? __fadd_rn(1.0f, __fdiv_rn(best_cost, area)) : 3.402823466e38f;
+        if (count <= kSahMaxLeaf && leaf_cost <= split_cost) decision = -1;
+        else if (best_axis >= 0) decision = best_axis | (best_split << 2);
+        else if (count <= kSahMaxLeaf) decision = -1;
+        else {                                                           // centroids coincide or depth cap: split the Morton range in the middle
+            int lo_p = nd.pos_min[b], hi_p = nd.pos_max[b];
+            nd.pos_mid[b] = lo_p + (hi_p - lo_p) / 2;
+            decision = 1 << 8;
+        }
+    }
+    nd.split[b] = decision;
+    flag[b - lvl_begin] = decision >= 0 ? 1 : 0;
+    if (decision < 0) nd.meta[b] = count | kLeafBit;
+    if (decision >= 0 && !(decision & (1 << 8))) {
+        int axis = decision & 3, split = decision >> 2;
+        const float* w = bins + ((long long)(b - chunk_begin) * 3 + axis) * kSahBins * kBinWords;
+        Box3 lb, rb; box_reset(lb); box_reset(rb);
+        int lc = 0, rc = 0;
+        for (int k = 0; k < kSahBins; k++) {
+            int c = __float_as_int(w[k * kBinWords + 6]);
+            if (c == 0) continue;
+            if (k <= split) { box_grow(lb, w + k * kBinWords); lc += c; } else { box_grow(rb, w + k * kBinWords); rc += c; }
+        }
+        int t = b - lvl_begin;
+        tmp.llo[t] = make_float4(lb.lo[0], lb.lo[1], lb.lo[2], 0.f); tmp.lhi[t] = make_float4(lb.hi[0], lb.hi[1], lb.hi[2], 0.f);
+        tmp.rlo[t] = make_float4(rb.lo[0], rb.lo[1], rb.lo[2], 0.f); tmp.rhi[t] = make_float4(rb.hi[0], rb.hi[1], rb.hi[2], 0.f);
+        tmp.lc[t] = lc; tmp.rc[t] = rc;
+    }
+}
+
+// S4: children of the nodes that split, at next_begin + 2 * scan.  A fallback split keeps the parent's box for both children
+// (conservative); their counts come from S5's atomics.
+__global__ void __launch_bounds__(kTB) k_sah_children(SahNodes nd, int lvl_begin, int lvl_end, int next_begin, const int32_t* __restrict__ flag,
+                                                      const int32_t* __restrict__ scan, SahLevelTmp tmp) {
+    int b = lvl_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= lvl_end || !flag[b - lvl_begin]) return;
+    int t = b - lvl_begin;
+    int left = next_begin + 2 * scan[t];
+    int d = nd.split[b];
+    nd.child[b] = make_int2(left, left + 1);
+    nd.parent[left] = b; nd.parent[left + 1] = b;
+    if (d & (1 << 8)) {
+        nd.lo[left] = nd.lo[b]; nd.hi[left] = nd.hi[b]; nd.lo[left + 1] = nd.lo[b]; nd.hi[left + 1] = nd.hi[b];
+        nd.meta[left] = 0; nd.meta[left + 1] = 0;
+        return;
+    }
+    nd.lo[left] = tmp.llo[t]; nd.hi[left] = tmp.lhi[t]; nd.lo[left + 1] = tmp.rlo[t]; nd.hi[left + 1] = tmp.rhi[t];
+    nd.meta[left] = tmp.lc[t]; nd.meta[left + 1] = tmp.rc[t];
+}
+
+// S5
+__global__ void __launch_bounds__(kTB) k_sah_assign(SahNodes nd, int n, int lvl_begin, const uint32_t* __restrict__ order, const float4* __restrict__ plo,
+                                                    const float4* __restrict__ phi, int32_t* __restrict__ pnode) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int b = pnode[i];
+    if (b < lvl_begin) return;
+    int d = nd.split[b];
+    if (d < 0) return;                                                   // its node became a leaf: the primitive stays
+    int left = nd.child[b].x;
+    int side;
+    if (d & (1 << 8)) {
+        side = i <= nd.pos_mid[b] ? 0 : 1;
+        atomicAdd(nd.meta + left + side, 1);
+    } else {
+        int axis = d & 3, split = d >> 2;
+        uint32_t p = order[i];
+        float3 c = centre_of(plo[p], phi[p]);
+        float4 cl = nd.clo[b], chh = nd.chi[b];
+        float cc = axis == 0 ? c.x : (axis == 1 ? c.y : c.z), cmin = axis == 0 ? cl.x : (axis == 1 ? cl.y : cl.z), cmax = axis == 0 ? chh.x : (axis == 1 ? chh.y : chh.z);
+        side = sah_bin(cc, cmin, cmax - cmin) <= split ? 0 : 1;
+    }
+    pnode[i] = left + side;
+}
+
+// DFS offset of every build node (one walk to the root), state for the emission stage, key of every primitive for the final sort
+__global__ void __launch_bounds__(kTB) k_sah_layout(SahNodes nd, int nb, int32_t* __restrict__ first, uint8_t* __restrict__ state) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    int off = 0, cur = b;
+    for (int p = nd.parent[cur]; p >= 0; p = nd.parent[cur]) {
+        int left = nd.child[p].x;
+        if (cur != left) off += nd.meta[left] & kCntMask;
+        cur = p;
+    }
+    first[b] = off;
+    state[b] = (nd.meta[b] & kLeafBit) ? 1 : 0;
+}
+__global__ void __launch_bounds__(kTB) k_sah_keys(int n, const int32_t* __restrict__ pnode, const int32_t* __restrict__ first, uint32_t* __restrict__ keys) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = (uint32_t)first[pnode[i]];
+}
+__global__ void __launch_bounds__(kTB) k_emit_tris_ordered(int n, const uint32_t* __restrict__ prims, const float* __restrict__ v, const int32_t* __restrict__ ix,
+                                                           int first_tri, float4* __restrict__ tris) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t p = prims[k];
+    const int32_t* t = ix + 3 * (size_t)p;
+    const float *a = v + 3 * (size_t)t[0], *b = v + 3 * (size_t)t[1], *c = v + 3 * (size_t)t[2];
+    float4* o = tris + 3 * (size_t)k;
+    o[0] = make_float4(a[0], a[1], a[2], __int_as_float(first_tri + (int)p));
+    o[1] = make_float4(b[0] - a[0], b[1] - a[1], b[2] - a[2], 0.f);
+    o[2] = make_float4(c[0] - a[0], c[1] - a[1], c[2] - a[2], 0.f);
 }
 
 // ---- B6: one level of the BVH2 -> BVH4 collapse.  Item = (binary node id, 4-wide node index, stack entries above it).
@@ -387,44 +663,59 @@ void FreeDeviceBlas(DeviceBlas* b) {
     *b = DeviceBlas();
 }
 
-bool BuildBlasOnDevice(const float* d_vertices, const int32_t* d_tri_idx, int first_tri, int tri_count, float int_test_eps,
+bool BuildBlasOnDevice(const float* d_vertices, const int32_t* d_tri_idx, int first_tri, int tri_count, float int_test_eps, int algorithm,
                        int node_base, int node4_base, int tri_base, int max_depth2, int max_stack4, cudaStream_t st, DeviceBlas* out) {
     *out = DeviceBlas();
     const int n = tri_count;
     if (n < 8) throw std::runtime_error("bvh_device: tri_count must be >= 8");
-    const int total = 2 * n - 1;
+    const bool sah = algorithm == kDeviceAlgoSah;
+    const int total = 2 * n - 1;                                         // PLOC id space; the SAH build uses at most 2n build nodes
+    const int ids = 2 * n;
     const int32_t* ix = d_tri_idx + 3 * (size_t)first_tri;
 
     // ---- temporaries
     float4 *plo, *phi, *clo[2], *chi[2], *nlo, *nhi;
     unsigned long long *keys[2], *flags, *scan;
-    uint32_t *vals[2], *totals;
-    int32_t *nn, *parent, *meta, *first, *live, *lscan, *ctr;
-    float *cst, *cb;
+    uint32_t *vals[2], *totals, *skeys[2], *sprims;
+    int32_t *nn, *parent, *meta, *first, *live, *lscan, *ctr, *pnode;
+    float *cst, *cb, *bins;
     int2* child;
     uint8_t* state;
     int4* items[2];
+    SahNodes nd{};
+    SahLevelTmp lt{};
     void* cub_tmp;
-    size_t sort_bytes = 0, scan64_bytes = 0, scan32_bytes = 0;
+    const int bin_chunk = std::min(n, 1 << 17);                          // nodes binned per pass of a level (1536 B of bins each)
+    size_t sort_bytes = 0, sort32_bytes = 0, scan64_bytes = 0, scan32_bytes = 0;
     BCK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, 63, st));
+    BCK(cub::DeviceRadixSort::SortPairs(nullptr, sort32_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, 32, st));
     BCK(cub::DeviceScan::ExclusiveSum(nullptr, scan64_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, n, st));
-    BCK(cub::DeviceScan::ExclusiveSum(nullptr, scan32_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, n, st));
-    size_t cub_bytes = std::max(sort_bytes, std::max(scan64_bytes, scan32_bytes));
+    BCK(cub::DeviceScan::ExclusiveSum(nullptr, scan32_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, ids, st));
+    size_t cub_bytes = std::max(std::max(sort_bytes, sort32_bytes), std::max(scan64_bytes, scan32_bytes));
     Arena ar;
     ar.Reserve(&plo, n); ar.Reserve(&phi, n);
-    for (int k = 0; k < 2; k++) { ar.Reserve(&clo[k], n); ar.Reserve(&chi[k], n); ar.Reserve(&keys[k], n); ar.Reserve(&vals[k], n); ar.Reserve(&items[k], n); }
-    ar.Reserve(&nlo, total); ar.Reserve(&nhi, total); ar.Reserve(&child, total); ar.Reserve(&parent, total); ar.Reserve(&meta, total);
-    ar.Reserve(&cst, total); ar.Reserve(&first, total); ar.Reserve(&state, total);
-    ar.Reserve(&nn, n); ar.Reserve(&flags, n); ar.Reserve(&scan, n); ar.Reserve(&live, n); ar.Reserve(&lscan, n);
-    ar.Reserve(&totals, 2); ar.Reserve(&ctr, CTR_N); ar.Reserve(&cb, 6);
+    for (int k = 0; k < 2; k++) { ar.Reserve(&keys[k], n); ar.Reserve(&vals[k], n); ar.Reserve(&items[k], n); }
+    ar.Reserve(&nlo, ids); ar.Reserve(&nhi, ids); ar.Reserve(&child, ids); ar.Reserve(&parent, ids); ar.Reserve(&meta, ids);
+    ar.Reserve(&first, ids); ar.Reserve(&state, ids); ar.Reserve(&live, ids); ar.Reserve(&lscan, ids);
+    ar.Reserve(&ctr, CTR_N); ar.Reserve(&cb, 6); ar.Reserve(&totals, 2);
+    if (sah) {
+        ar.Reserve(&nd.clo, ids); ar.Reserve(&nd.chi, ids); ar.Reserve(&nd.pos_min, ids); ar.Reserve(&nd.pos_max, ids); ar.Reserve(&nd.split, ids); ar.Reserve(&nd.pos_mid, ids);
+        ar.Reserve(&lt.llo, n); ar.Reserve(&lt.lhi, n); ar.Reserve(&lt.rlo, n); ar.Reserve(&lt.rhi, n); ar.Reserve(&lt.lc, n); ar.Reserve(&lt.rc, n);
+        ar.Reserve(&pnode, n); ar.Reserve(&skeys[0], n); ar.Reserve(&skeys[1], n); ar.Reserve(&sprims, n);
+        ar.Reserve(&bins, (size_t)bin_chunk * 3 * kSahBins * kBinWords);
+    } else {
+        for (int k = 0; k < 2; k++) { ar.Reserve(&clo[k], n); ar.Reserve(&chi[k], n); }
+        ar.Reserve(&cst, ids); ar.Reserve(&nn, n); ar.Reserve(&flags, n); ar.Reserve(&scan, n);
+    }
     ar.Reserve((char**)&cub_tmp, cub_bytes);
     ar.Commit();
+    nd.lo = nlo; nd.hi = nhi; nd.child = child; nd.parent = parent; nd.meta = meta;
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     struct Ev { cudaEvent_t& a; cudaEvent_t& b; ~Ev() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } ev_guard{e0, e1};
     BCK(cudaEventCreate(&e0)); BCK(cudaEventCreate(&e1));
     BCK(cudaEventRecord(e0, st));
-    auto run = [&]() -> bool {                                       // false: refused (caller falls back to the host builder)
+    auto run = [&]() -> bool {                                           // false: refused (caller falls back to the host builder)
         // B1, B2
         const float cb_init[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
         BCK(cudaMemcpyAsync(cb, cb_init, sizeof cb_init, cudaMemcpyHostToDevice, st));
@@ -432,119 +723,166 @@ bool BuildBlasOnDevice(const float* d_vertices, const int32_t* d_tri_idx, int fi
         k_morton<<<Grid(n), kTB, 0, st>>>(plo, phi, n, cb, keys[0], vals[0]);
         BCK(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, keys[0], keys[1], vals[0], vals[1], n, 0, 63, st));
         const uint32_t* order = vals[1];
-        k_init_clusters<<<Grid(n), kTB, 0, st>>>(order, plo, phi, n, clo[0], chi[0], nlo, nhi, parent, meta, cst);
 
-        // B3
-        int top = kTopClusters;
-        if (const char* e = getenv("RT795_PLOC_TOP")) top = std::max(1, atoi(e));
-        int m = n, next_id = n, cur = 0, iters = 0;
-        int radius = kPlocRadius;
-        if (const char* e = getenv("RT795_PLOC_RADIUS")) radius = std::min(kMaxPlocRadius, std::max(1, atoi(e)));
-        while (m > top) {
-            if (++iters > kMaxPlocIterations) return false;
-            k_nearest<<<Grid(m), kTB, 0, st>>>(clo[cur], chi[cur], m, radius, nn);
-            k_merge_flags<<<Grid(m), kTB, 0, st>>>(nn, m, flags);
-            BCK(cub::DeviceScan::ExclusiveSum(cub_tmp, scan64_bytes, flags, scan, m, st));
-            k_merge_emit<<<Grid(m), kTB, 0, st>>>(clo[cur], chi[cur], nn, flags, scan, m, next_id, clo[cur ^ 1], chi[cur ^ 1], nlo, nhi, child, parent, meta, cst, totals);
-            uint32_t h_tot[2] = {0, 0};
-            BCK(cudaMemcpyAsync(h_tot, totals, sizeof h_tot, cudaMemcpyDeviceToHost, st));
-            BCK(cudaStreamSynchronize(st));
-            if ((int)h_tot[0] >= m || h_tot[1] == 0) return false;     // no progress (NaN boxes): leave it to the host builder
-            m = (int)h_tot[0]; next_id += (int)h_tot[1]; cur ^= 1;
-        }
-        out->ploc_iterations = iters;
-        if (m > 1) {
-            // B3b: binned SAH over the remaining clusters on the host; node ids [next_id, total) = reversed flatten order (root last)
-            std::vector<float4> hlo(m), hhi(m);
-            std::vector<int32_t> hmeta(m);
-            std::vector<float> hcst(m);
-            int32_t* g_meta = live;                                      // scratch not in use yet
-            float* g_cst = reinterpret_cast<float*>(lscan);
-            k_gather_clusters<<<Grid(m), kTB, 0, st>>>(clo[cur], m, meta, cst, g_meta, g_cst);
-            BCK(cudaMemcpyAsync(hlo.data(), clo[cur], (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, st));
-            BCK(cudaMemcpyAsync(hhi.data(), chi[cur], (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, st));
-            BCK(cudaMemcpyAsync(hmeta.data(), g_meta, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-            BCK(cudaMemcpyAsync(hcst.data(), g_cst, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-            BCK(cudaStreamSynchronize(st));
-            std::vector<Aabb> pb(m);
-            for (int i = 0; i < m; i++) { pb[i].lo[0] = hlo[i].x; pb[i].lo[1] = hlo[i].y; pb[i].lo[2] = hlo[i].z; pb[i].hi[0] = hhi[i].x; pb[i].hi[1] = hhi[i].y; pb[i].hi[2] = hhi[i].z; }
-            BuiltBvh tb;
-            BuildSahBvh(pb.data(), m, 1, &tb);
-            const int inner = (int)tb.nodes.size();
-            if (inner != m - 1) throw std::runtime_error("bvh_device: top tree is not a full binary tree over the clusters");
-            std::vector<float4> tlo(inner), thi(inner);
-            std::vector<int2> tch(inner);
-            std::vector<int32_t> tmeta(inner);
-            std::vector<float> tcst(inner);
-            auto slot_of = [&](int i) { return inner - 1 - i; };          // flatten index -> slot in [next_id, total): root (0) -> last
-            for (int i = inner - 1; i >= 0; i--) {                        // children come after their parent in the flatten order
-                const BvhNode64& nd = tb.nodes[i];
-                int ids[2], cnt[2]; float cs[2], area[2];
-                float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-                for (int c = 0; c < 2; c++) {
-                    int32_t ref; memcpy(&ref, &nd.q[12 + c], 4);
-                    float blo[3] = {nd.q[c * 4 + 0], nd.q[c * 4 + 2], nd.q[8 + c * 2 + 0]}, bhi[3] = {nd.q[c * 4 + 1], nd.q[c * 4 + 3], nd.q[8 + c * 2 + 1]};
-                    for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], blo[k]); hi[k] = std::max(hi[k], bhi[k]); }
-                    float dx = bhi[0] - blo[0], dy = bhi[1] - blo[1], dz = bhi[2] - blo[2];
-                    area[c] = dx * dy + dy * dz + dz * dx;
-                    if (ref >= 0) { int sl = slot_of(ref); ids[c] = next_id + sl; cnt[c] = tmeta[sl] & kCntMask; cs[c] = tcst[sl]; }
-                    else { int ci = tb.order[(~ref) >> 3]; int32_t nid; memcpy(&nid, &hlo[ci].w, 4); ids[c] = nid; cnt[c] = hmeta[ci] & kCntMask; cs[c] = hcst[ci]; }
-                }
-                float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
-                float a = dx * dy + dy * dz + dz * dx;
-                int c = cnt[0] + cnt[1];
-                float split = a > 0.f ? 1.0f + (area[0] * cs[0] + area[1] * cs[1]) / a : 3.0e38f;
-                if (!(split <= 3.0e38f)) split = 3.0e38f;
-                bool leaf = c <= 4 && (float)c <= split;
-                int sl = slot_of(i);
-                int32_t idbits = next_id + sl; float idf; memcpy(&idf, &idbits, 4);
-                tlo[sl] = make_float4(lo[0], lo[1], lo[2], idf); thi[sl] = make_float4(hi[0], hi[1], hi[2], 0.f);
-                tch[sl] = make_int2(ids[0], ids[1]);
-                tmeta[sl] = c | (leaf ? kLeafBit : 0); tcst[sl] = leaf ? (float)c : split;
-            }
-            BCK(cudaMemcpyAsync(nlo + next_id, tlo.data(), (size_t)inner * sizeof(float4), cudaMemcpyHostToDevice, st));
-            BCK(cudaMemcpyAsync(nhi + next_id, thi.data(), (size_t)inner * sizeof(float4), cudaMemcpyHostToDevice, st));
-            BCK(cudaMemcpyAsync(child + next_id, tch.data(), (size_t)inner * sizeof(int2), cudaMemcpyHostToDevice, st));
-            BCK(cudaMemcpyAsync(meta + next_id, tmeta.data(), (size_t)inner * 4, cudaMemcpyHostToDevice, st));
-            BCK(cudaMemcpyAsync(cst + next_id, tcst.data(), (size_t)inner * 4, cudaMemcpyHostToDevice, st));
-            k_set_parents<<<Grid(inner), kTB, 0, st>>>(next_id, inner, child, parent, next_id + inner - 1);
-            BCK(cudaStreamSynchronize(st));                               // the host vectors above go out of scope
-            next_id += inner;
-        }
-        if (next_id != total) throw std::runtime_error("bvh_device: node count mismatch after clustering");
-        const int root = total - 1;
-
-        // B4
+        // the finished binary tree, as the emission stage sees it
+        int id_base = 0, id_count = 0, reverse = 0, root = 0;
         BCK(cudaMemsetAsync(ctr, 0, CTR_N * sizeof(int32_t), st));
-        k_layout<<<Grid(total), kTB, 0, st>>>(total, parent, child, meta, first, state, ctr);
-        // B5
         BCK(cudaMalloc((void**)&out->tris, (size_t)n * 3 * sizeof(float4)));
-        k_emit_tris<<<Grid(n), kTB, 0, st>>>(n, first, order, d_vertices, ix, first_tri, out->tris);
-        k_live_flags<<<Grid(n - 1), kTB, 0, st>>>(n, state, live);
-        BCK(cub::DeviceScan::ExclusiveSum(cub_tmp, scan32_bytes, live, lscan, n - 1, st));
+
+        if (sah) {
+            // ---- S: level-synchronous binned SAH
+            const float4 root_lo = make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f), root_hi = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, 0.f);
+            const int32_t root_meta = n, root_parent = -1;
+            BCK(cudaMemcpyAsync(nd.lo, &root_lo, 16, cudaMemcpyHostToDevice, st));
+            BCK(cudaMemcpyAsync(nd.hi, &root_hi, 16, cudaMemcpyHostToDevice, st));
+            BCK(cudaMemcpyAsync(nd.meta, &root_meta, 4, cudaMemcpyHostToDevice, st));
+            BCK(cudaMemcpyAsync(nd.parent, &root_parent, 4, cudaMemcpyHostToDevice, st));
+            k_sah_root<<<Grid(n), kTB, 0, st>>>(nd, n, plo, phi, pnode);
+            int lvl_begin = 0, lvl_end = 1, depth = 0;
+            while (lvl_end > lvl_begin) {
+                if (depth > kSahMaxDepth + 40) return false;
+                const int width = lvl_end - lvl_begin;
+                k_sah_init_nodes<<<Grid(width), kTB, 0, st>>>(nd, lvl_begin, lvl_end);
+                k_sah_cbounds<<<Grid(n), kTB, 0, st>>>(nd, n, lvl_begin, order, plo, phi, pnode);
+                for (int cb0 = lvl_begin; cb0 < lvl_end; cb0 += bin_chunk) {
+                    int cb1 = std::min(lvl_end, cb0 + bin_chunk);
+                    long long nbins = (long long)(cb1 - cb0) * 3 * kSahBins;
+                    k_sah_init_bins<<<Grid(nbins), kTB, 0, st>>>(bins, nbins);
+                    k_sah_bin<<<Grid(n), kTB, 0, st>>>(nd, n, cb0, cb1, order, plo, phi, pnode, bins);
+                    k_sah_split<<<(cb1 - cb0 + 127) / 128, 128, 0, st>>>(nd, lvl_begin, cb0, cb1, depth, bins, live, lt);
+                }
+                BCK(cub::DeviceScan::ExclusiveSum(cub_tmp, scan32_bytes, live, lscan, width, st));
+                k_sah_children<<<Grid(width), kTB, 0, st>>>(nd, lvl_begin, lvl_end, lvl_end, live, lscan, lt);
+                int32_t h_last[2] = {0, 0};
+                BCK(cudaMemcpyAsync(&h_last[0], live + (width - 1), 4, cudaMemcpyDeviceToHost, st));
+                BCK(cudaMemcpyAsync(&h_last[1], lscan + (width - 1), 4, cudaMemcpyDeviceToHost, st));
+                k_sah_assign<<<Grid(n), kTB, 0, st>>>(nd, n, lvl_begin, order, plo, phi, pnode);
+                BCK(cudaStreamSynchronize(st));
+                const int splits = h_last[0] + h_last[1];
+                if (lvl_end + 2 * splits > ids) throw std::runtime_error("bvh_device: SAH build node overflow");
+                lvl_begin = lvl_end; lvl_end += 2 * splits;
+                if (splits) depth++;
+            }
+            const int nb = lvl_end;
+            out->ploc_iterations = depth;
+            out->depth2 = depth;
+            k_sah_layout<<<Grid(nb), kTB, 0, st>>>(nd, nb, first, state);
+            k_sah_keys<<<Grid(n), kTB, 0, st>>>(n, pnode, first, skeys[0]);
+            BCK(cub::DeviceRadixSort::SortPairs(cub_tmp, sort32_bytes, skeys[0], skeys[1], order, sprims, n, 0, 32, st));   // stable: Morton order inside a leaf
+            k_emit_tris_ordered<<<Grid(n), kTB, 0, st>>>(n, sprims, d_vertices, ix, first_tri, out->tris);
+            id_base = 0; id_count = nb; reverse = 0; root = 0;
+        } else {
+            k_init_clusters<<<Grid(n), kTB, 0, st>>>(order, plo, phi, n, clo[0], chi[0], nlo, nhi, parent, meta, cst);
+            // ---- B3
+            int top = kTopClusters;
+            if (const char* e = getenv("RT795_PLOC_TOP")) top = std::max(1, atoi(e));
+            int m = n, next_id = n, cur = 0, iters = 0;
+            int radius = kPlocRadius;
+            if (const char* e = getenv("RT795_PLOC_RADIUS")) radius = std::min(kMaxPlocRadius, std::max(1, atoi(e)));
+            while (m > top) {
+                if (++iters > kMaxPlocIterations) return false;
+                k_nearest<<<Grid(m), kTB, 0, st>>>(clo[cur], chi[cur], m, radius, nn);
+                k_merge_flags<<<Grid(m), kTB, 0, st>>>(nn, m, flags);
+                BCK(cub::DeviceScan::ExclusiveSum(cub_tmp, scan64_bytes, flags, scan, m, st));
+                k_merge_emit<<<Grid(m), kTB, 0, st>>>(clo[cur], chi[cur], nn, flags, scan, m, next_id, clo[cur ^ 1], chi[cur ^ 1], nlo, nhi, child, parent, meta, cst, totals);
+                uint32_t h_tot[2] = {0, 0};
+                BCK(cudaMemcpyAsync(h_tot, totals, sizeof h_tot, cudaMemcpyDeviceToHost, st));
+                BCK(cudaStreamSynchronize(st));
+                if ((int)h_tot[0] >= m || h_tot[1] == 0) return false;     // no progress (NaN boxes): leave it to the host builder
+                m = (int)h_tot[0]; next_id += (int)h_tot[1]; cur ^= 1;
+            }
+            out->ploc_iterations = iters;
+            if (m > 1) {
+                // B3b: binned SAH over the remaining clusters on the host; node ids [next_id, total) = reversed flatten order (root last)
+                std::vector<float4> hlo(m), hhi(m);
+                std::vector<int32_t> hmeta(m);
+                std::vector<float> hcst(m);
+                int32_t* g_meta = live;                                      // scratch not in use yet
+                float* g_cst = reinterpret_cast<float*>(lscan);
+                k_gather_clusters<<<Grid(m), kTB, 0, st>>>(clo[cur], m, meta, cst, g_meta, g_cst);
+                BCK(cudaMemcpyAsync(hlo.data(), clo[cur], (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, st));
+                BCK(cudaMemcpyAsync(hhi.data(), chi[cur], (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, st));
+                BCK(cudaMemcpyAsync(hmeta.data(), g_meta, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+                BCK(cudaMemcpyAsync(hcst.data(), g_cst, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+                BCK(cudaStreamSynchronize(st));
+                std::vector<Aabb> pb(m);
+                for (int i = 0; i < m; i++) { pb[i].lo[0] = hlo[i].x; pb[i].lo[1] = hlo[i].y; pb[i].lo[2] = hlo[i].z; pb[i].hi[0] = hhi[i].x; pb[i].hi[1] = hhi[i].y; pb[i].hi[2] = hhi[i].z; }
+                BuiltBvh tb;
+                BuildSahBvh(pb.data(), m, 1, &tb);
+                const int inner = (int)tb.nodes.size();
+                if (inner != m - 1) throw std::runtime_error("bvh_device: top tree is not a full binary tree over the clusters");
+                std::vector<float4> tlo(inner), thi(inner);
+                std::vector<int2> tch(inner);
+                std::vector<int32_t> tmeta(inner);
+                std::vector<float> tcst(inner);
+                auto slot_of = [&](int i) { return inner - 1 - i; };          // flatten index -> slot in [next_id, total): root (0) -> last
+                for (int i = inner - 1; i >= 0; i--) {                        // children come after their parent in the flatten order
+                    const BvhNode64& nd = tb.nodes[i];
+                    int ids[2], cnt[2]; float cs[2], area[2];
+                    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+                    for (int c = 0; c < 2; c++) {
+                        int32_t ref; memcpy(&ref, &nd.q[12 + c], 4);
+                        float blo[3] = {nd.q[c * 4 + 0], nd.q[c * 4 + 2], nd.q[8 + c * 2 + 0]}, bhi[3] = {nd.q[c * 4 + 1], nd.q[c * 4 + 3], nd.q[8 + c * 2 + 1]};
+                        for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], blo[k]); hi[k] = std::max(hi[k], bhi[k]); }
+                        float dx = bhi[0] - blo[0], dy = bhi[1] - blo[1], dz = bhi[2] - blo[2];
+                        area[c] = dx * dy + dy * dz + dz * dx;
+                        if (ref >= 0) { int sl = slot_of(ref); ids[c] = next_id + sl; cnt[c] = tmeta[sl] & kCntMask; cs[c] = tcst[sl]; }
+                        else { int ci = tb.order[(~ref) >> 3]; int32_t nid; memcpy(&nid, &hlo[ci].w, 4); ids[c] = nid; cnt[c] = hmeta[ci] & kCntMask; cs[c] = hcst[ci]; }
+                    }
+                    float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+                    float a = dx * dy + dy * dz + dz * dx;
+                    int c = cnt[0] + cnt[1];
+                    float split = a > 0.f ? 1.0f + (area[0] * cs[0] + area[1] * cs[1]) / a : 3.0e38f;
+                    if (!(split <= 3.0e38f)) split = 3.0e38f;
+                    bool leaf = c <= 4 && (float)c <= split;
+                    int sl = slot_of(i);
+                    int32_t idbits = next_id + sl; float idf; memcpy(&idf, &idbits, 4);
+                    tlo[sl] = make_float4(lo[0], lo[1], lo[2], idf); thi[sl] = make_float4(hi[0], hi[1], hi[2], 0.f);
+                    tch[sl] = make_int2(ids[0], ids[1]);
+                    tmeta[sl] = c | (leaf ? kLeafBit : 0); tcst[sl] = leaf ? (float)c : split;
+                }
+                BCK(cudaMemcpyAsync(nlo + next_id, tlo.data(), (size_t)inner * sizeof(float4), cudaMemcpyHostToDevice, st));
+                BCK(cudaMemcpyAsync(nhi + next_id, thi.data(), (size_t)inner * sizeof(float4), cudaMemcpyHostToDevice, st));
+                BCK(cudaMemcpyAsync(child + next_id, tch.data(), (size_t)inner * sizeof(int2), cudaMemcpyHostToDevice, st));
+                BCK(cudaMemcpyAsync(meta + next_id, tmeta.data(), (size_t)inner * 4, cudaMemcpyHostToDevice, st));
+                BCK(cudaMemcpyAsync(cst + next_id, tcst.data(), (size_t)inner * 4, cudaMemcpyHostToDevice, st));
+                k_set_parents<<<Grid(inner), kTB, 0, st>>>(next_id, inner, child, parent, next_id + inner - 1);
+                BCK(cudaStreamSynchronize(st));                               // the host vectors above go out of scope
+                next_id += inner;
+            }
+            if (next_id != total) throw std::runtime_error("bvh_device: node count mismatch after clustering");
+            // B4, B5
+            k_layout<<<Grid(total), kTB, 0, st>>>(total, parent, child, meta, first, state, ctr);
+            k_emit_tris<<<Grid(n), kTB, 0, st>>>(n, first, order, d_vertices, ix, first_tri, out->tris);
+            id_base = n; id_count = n - 1; reverse = 1; root = total - 1;
+        }
+
+        // ---- emission: binary nodes, 4-wide collapse, quantised twin
+        k_live_flags<<<Grid(id_count), kTB, 0, st>>>(id_base, id_count, state, live);
+        BCK(cub::DeviceScan::ExclusiveSum(cub_tmp, scan32_bytes, live, lscan, id_count, st));
         int32_t h_last[2] = {0, 0}, h_ctr[CTR_N];
-        BCK(cudaMemcpyAsync(&h_last[0], live + (n - 2), 4, cudaMemcpyDeviceToHost, st));
-        BCK(cudaMemcpyAsync(&h_last[1], lscan + (n - 2), 4, cudaMemcpyDeviceToHost, st));
+        BCK(cudaMemcpyAsync(&h_last[0], live + (id_count - 1), 4, cudaMemcpyDeviceToHost, st));
+        BCK(cudaMemcpyAsync(&h_last[1], lscan + (id_count - 1), 4, cudaMemcpyDeviceToHost, st));
         BCK(cudaMemcpyAsync(h_ctr, ctr, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
         float h_root[8];
         BCK(cudaMemcpyAsync(h_root, nlo + root, 16, cudaMemcpyDeviceToHost, st));
         BCK(cudaMemcpyAsync(h_root + 4, nhi + root, 16, cudaMemcpyDeviceToHost, st));
         BCK(cudaStreamSynchronize(st));
         const int live_total = h_last[0] + h_last[1];
-        out->depth2 = h_ctr[CTR_DEPTH];
+        if (!sah) out->depth2 = h_ctr[CTR_DEPTH];
         for (int k = 0; k < 3; k++) { out->bounds.lo[k] = h_root[k]; out->bounds.hi[k] = h_root[4 + k]; }
         if (live_total < 1) throw std::runtime_error("bvh_device: root collapsed into a leaf");
         if (out->depth2 > max_depth2) return false;
         out->n2 = live_total;
         BCK(cudaMalloc((void**)&out->nodes2, (size_t)live_total * 4 * sizeof(float4)));
-        k_emit_bvh2<<<Grid(n - 1), kTB, 0, st>>>(n, live_total, live, lscan, child, state, first, meta, nlo, nhi, node_base, tri_base, out->nodes2);
+        k_emit_bvh2<<<Grid(id_count), kTB, 0, st>>>(id_base, id_count, reverse, live_total, live, lscan, child, state, first, meta, nlo, nhi, node_base, tri_base, out->nodes2);
 
         // B6: every 4-wide node is a distinct live binary node, so live_total bounds their number
         BCK(cudaMalloc((void**)&out->nodes4, (size_t)live_total * 8 * sizeof(float4)));
         {
             int4 root_item = make_int4(root, 0, 0, 0);
             BCK(cudaMemcpyAsync(items[0], &root_item, sizeof root_item, cudaMemcpyHostToDevice, st));
-            int32_t init_ctr[CTR_N] = {0, 1, 0, h_ctr[CTR_DEPTH]};
+            int32_t init_ctr[CTR_N] = {0, 1, 0, out->depth2};
             BCK(cudaMemcpyAsync(ctr, init_ctr, sizeof init_ctr, cudaMemcpyHostToDevice, st));
             int n_items = 1, q = 0;
             while (n_items > 0) {

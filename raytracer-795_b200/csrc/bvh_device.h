@@ -45,7 +45,8 @@ struct DeviceBlas {
 // tri_base added (positions of this mesh's segments in the scene-wide arrays).  Returns false (and frees everything)
 // when the build does not converge or the tree is deeper than max_depth2 / needs more than max_stack4 stack entries - the
 // caller then uses the host builder.  Throws std::runtime_error on CUDA errors.  tri_count must be >= 8.
-bool BuildBlasOnDevice(const float* d_vertices, const int32_t* d_tri_idx, int first_tri, int tri_count, float int_test_eps,
+constexpr int kDeviceAlgoPloc = 0, kDeviceAlgoSah = 1;
+bool BuildBlasOnDevice(const float* d_vertices, const int32_t* d_tri_idx, int first_tri, int tri_count, float int_test_eps, int algorithm,
                        int node_base, int node4_base, int tri_base, int max_depth2, int max_stack4, cudaStream_t st, DeviceBlas* out);
 void FreeDeviceBlas(DeviceBlas* b);
 

@@ -184,7 +184,7 @@ void Validate(const RtSceneDesc* s) {
         if (l.type < RT_LIGHT_POINT || l.type > RT_LIGHT_ENVIRONMENT) bad("unknown light type");
         if (l.type == RT_LIGHT_ENVIRONMENT && (l.image < 0 || l.image >= s->num_images)) bad("environment light image index out of range");
     }
-    if (s->bvh_builder < RT_BVH_AUTO || s->bvh_builder > RT_BVH_DEVICE_PLOC) bad("bvh_builder must be one of RT_BVH_*");
+    if (s->bvh_builder < RT_BVH_AUTO || s->bvh_builder > RT_BVH_DEVICE_SAH) bad("bvh_builder must be one of RT_BVH_*");
     if (s->env_light_index < -1 || s->env_light_index >= s->num_lights) bad("env_light_index out of range");
     if (s->background_texture < -1 || s->background_texture >= s->num_textures) bad("background_texture out of range");
 }
@@ -219,7 +219,7 @@ bool BuildAndUpload(RtScene* sc, const RtSceneDesc* s, bool allow_device) {
     std::vector<Aabb> mesh_bounds(s->num_meshes);
     int n2_total = 0, n4_total = 0, tri_total = 0;
     int builder = s->bvh_builder;
-    if (const char* e = getenv("RT795_BVH_BUILDER")) builder = !strcmp(e, "host") ? RT_BVH_HOST_SAH : !strcmp(e, "device") ? RT_BVH_DEVICE_PLOC : RT_BVH_AUTO;
+    if (const char* e = getenv("RT795_BVH_BUILDER")) builder = !strcmp(e, "host") ? RT_BVH_HOST_SAH : !strcmp(e, "device") || !strcmp(e, "ploc") ? RT_BVH_DEVICE_PLOC : !strcmp(e, "sah") ? RT_BVH_DEVICE_SAH : RT_BVH_AUTO;
     if (!allow_device) builder = RT_BVH_HOST_SAH;
     sc->stats.bvh_device_meshes = 0; sc->stats.ms_bvh_device = 0; sc->stats.bvh_ploc_iterations = 0;
     for (int m = 0; m < s->num_meshes; m++) {
@@ -228,11 +228,12 @@ bool BuildAndUpload(RtScene* sc, const RtSceneDesc* s, bool allow_device) {
         MeshSeg& sg = segs.back();
         const int node_base = n2_total, base4 = n4_total, tri_base = tri_total;
         mesh_root[m] = node_base; mesh_root4[m] = base4;
-        bool want_device = builder == RT_BVH_DEVICE_PLOC ? me.tri_count >= 8 : builder == RT_BVH_AUTO && me.tri_count >= kDeviceBuildMinTris;
+        bool want_device = (builder == RT_BVH_DEVICE_PLOC || builder == RT_BVH_DEVICE_SAH) ? me.tri_count >= 8 : builder == RT_BVH_AUTO && me.tri_count >= kDeviceBuildMinTris;
+        int algo = builder == RT_BVH_DEVICE_PLOC ? kDeviceAlgoPloc : kDeviceAlgoSah;   // AUTO: the host's tree, built on the device
         if (want_device) {
             // depth limits leave room for a TLAS of the same order as the host's (checked exactly below; a miss rebuilds on the host)
             try {
-                sg.on_device = BuildBlasOnDevice(sc->vertices.p, sc->tri_idx.p, me.first_tri, me.tri_count, eps, node_base, base4, tri_base,
+                sg.on_device = BuildBlasOnDevice(sc->vertices.p, sc->tri_idx.p, me.first_tri, me.tri_count, eps, algo, node_base, base4, tri_base,
                                                  kStackSize - 12, kStackSize - 12, st, &sg.dev);
             } catch (const std::exception&) {
                 // e.g. not enough free HBM for the builder's temporaries: the host builder needs none.  A sticky CUDA error

@@ -2,7 +2,7 @@
 // and writes each camera's <ImageName> (P3 PPM for "*.png*" names, half-float EXR otherwise, src/Image.cpp:26-34).
 // Extra, optional knobs after the scene path:  --f32 (also dump <ImageName>.f32 raw floats)  --device N
 // --cache (keep / reuse <scene.xml>.rt795blob, the prepared scene, while its sources are unchanged)
-// --integrator path|reference  --bvh auto|host|device (per-mesh BVH builder)  --seed S  --tonemap KEY BURN SAT GAMMA (writes <ImageName>.tm.ppm)
+// --integrator path|reference  --bvh auto|host|ploc|sah (per-mesh BVH builder)  --seed S  --tonemap KEY BURN SAT GAMMA (writes <ImageName>.tm.ppm)
 #include "../../include/rt795.h"
 #include <chrono>
 #include <cstdio>
@@ -12,7 +12,7 @@
 #include <vector>
 
 int main(int argc, char* argv[]) {
-    if (argc < 2) { fprintf(stderr, "usage: %s scene.xml [--f32] [--cache] [--device N] [--integrator path|reference] [--bvh auto|host|device] [--seed S] [--tonemap key burn sat gamma]\n", argv[0]); return 2; }
+    if (argc < 2) { fprintf(stderr, "usage: %s scene.xml [--f32] [--cache] [--device N] [--integrator path|reference] [--bvh auto|host|ploc|sah] [--seed S] [--tonemap key burn sat gamma]\n", argv[0]); return 2; }
     bool f32 = false, tonemap = false, cache = false;
     int device = 0, bvh = RT_BVH_AUTO;
     float tm[4] = {0.18f, 1.0f, 1.0f, 2.2f};
@@ -25,7 +25,7 @@ int main(int argc, char* argv[]) {
         else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--seed") && i + 1 < argc) opts.seed = strtoull(argv[++i], nullptr, 10);
         else if (!strcmp(argv[i], "--integrator") && i + 1 < argc) opts.integrator = !strcmp(argv[++i], "path") ? RT_INTEGRATOR_PATH : RT_INTEGRATOR_REFERENCE;
-        else if (!strcmp(argv[i], "--bvh") && i + 1 < argc) { const char* b = argv[++i]; bvh = !strcmp(b, "host") ? RT_BVH_HOST_SAH : !strcmp(b, "device") ? RT_BVH_DEVICE_PLOC : RT_BVH_AUTO; }
+        else if (!strcmp(argv[i], "--bvh") && i + 1 < argc) { const char* b = argv[++i]; bvh = !strcmp(b, "host") ? RT_BVH_HOST_SAH : !strcmp(b, "device") || !strcmp(b, "ploc") ? RT_BVH_DEVICE_PLOC : !strcmp(b, "sah") ? RT_BVH_DEVICE_SAH : RT_BVH_AUTO; }
         else if (!strcmp(argv[i], "--tonemap") && i + 4 < argc) { tonemap = true; for (int k = 0; k < 4; k++) tm[k] = (float)atof(argv[++i]); }
         else { fprintf(stderr, "unknown option %s\n", argv[i]); return 2; }
     }

@@ -77,9 +77,10 @@ def _box2(row, k):
     return (np.array([row[4 * k + 0], row[4 * k + 2], row[8 + 2 * k]]), np.array([row[4 * k + 1], row[4 * k + 3], row[8 + 2 * k + 1]]))
 
 
-def test_device_tree_is_a_conservative_partition(rt, scene_dir):
+@pytest.mark.parametrize("builder", ["RT_BVH_DEVICE_PLOC", "RT_BVH_DEVICE_SAH"])
+def test_device_tree_is_a_conservative_partition(rt, scene_dir, builder):
     xml = rt.scenes.scene_c3(os.path.join(scene_dir, "c3dev"), res=(96, 54), spp=1, n=96, deterministic=True)   # 18 050 triangles
-    hs, (dev,) = _scenes(rt, xml, [rt.RT_BVH_DEVICE_PLOC])
+    hs, (dev,) = _scenes(rt, xml, [getattr(rt, builder)])
     st = dev.stats()
     assert st.bvh_device_meshes >= 1 and 3 <= st.bvh_ploc_iterations <= 400
     tris, _ = dev.read_bvh(rt.RT_DEBUG_TRIS)
@@ -121,11 +122,12 @@ def test_device_tree_is_a_conservative_partition(rt, scene_dir):
     dev.close(); hs.close()
 
 
-def test_device_and_host_builders_trace_the_same_hits(rt, scene_dir):
+@pytest.mark.parametrize("builder", ["RT_BVH_DEVICE_PLOC", "RT_BVH_DEVICE_SAH"])
+def test_device_and_host_builders_trace_the_same_hits(rt, scene_dir, builder):
     """Primary hits (binary BVH, rt_trace_primary) and rendered frames (4-wide BVH) with the device-built and the
     host-built tree: same closest hit everywhere up to float ties at triangle edges."""
     xml = rt.scenes.scene_c4(os.path.join(scene_dir, "c4dev"), res=(256, 144), spp=4, n=120, deterministic=True)   # 28 322 triangles x 16 instances
-    hs, (host, dev) = _scenes(rt, xml, [rt.RT_BVH_HOST_SAH, rt.RT_BVH_DEVICE_PLOC])
+    hs, (host, dev) = _scenes(rt, xml, [rt.RT_BVH_HOST_SAH, getattr(rt, builder)])
     assert host.stats().bvh_device_meshes == 0 and dev.stats().bvh_device_meshes >= 1
     cam = hs.camera(0)
     ha, hb = host.trace_primary(cam), dev.trace_primary(cam)
@@ -147,21 +149,26 @@ def test_builder_selection_and_small_meshes(rt, scene_dir):
     """AUTO keeps small meshes on the host; DEVICE builds anything of >= 8 triangles on the GPU (Cornell walls: 10-12
     triangles) and the frames agree; an unknown builder id is rejected."""
     xml = rt.scenes.scene_c2(os.path.join(scene_dir, "c2dev"), res=96, spp=1)
-    hs, (auto, dev) = _scenes(rt, xml, [rt.RT_BVH_AUTO, rt.RT_BVH_DEVICE_PLOC])
+    hs, (auto, dev, dev2) = _scenes(rt, xml, [rt.RT_BVH_AUTO, rt.RT_BVH_DEVICE_PLOC, rt.RT_BVH_DEVICE_SAH])
     assert auto.stats().bvh_device_meshes == 0
     cam = hs.camera(0)
-    ha, hb = auto.trace_primary(cam), dev.trace_primary(cam)
-    assert (ha["full"] == hb["full"]).all()
-    same = (ha["object"] == hb["object"]) & (ha["primitive"] == hb["primitive"])
-    assert same.mean() > 0.999
+    ha = auto.trace_primary(cam)
+    for d in (dev, dev2):
+        assert d.stats().bvh_device_meshes >= 1
+        hb = d.trace_primary(cam)
+        assert (ha["full"] == hb["full"]).all()
+        same = (ha["object"] == hb["object"]) & (ha["primitive"] == hb["primitive"])
+        assert same.mean() > 0.999
+    dev2.close()
     with pytest.raises(rt.RtError):
-        rt.Scene(hs.desc, 0, bvh_builder=7)
+        rt.Scene(hs.desc, 0, bvh_builder=9)
     for s in (auto, dev):
         s.close()
     hs.close()
 
 
-def test_device_build_handles_duplicate_and_degenerate_triangles(rt, scene_dir, tmp_path):
+@pytest.mark.parametrize("builder", ["RT_BVH_DEVICE_PLOC", "RT_BVH_DEVICE_SAH"])
+def test_device_build_handles_duplicate_and_degenerate_triangles(rt, scene_dir, tmp_path, builder):
     """All-ties input: many copies of the same triangles (every merge distance ties) plus zero-area triangles.  The build
     must terminate (buddy tie-break) and still partition every triangle."""
     v, f, uv = rt.scenes.displaced_sphere(24)
@@ -170,7 +177,7 @@ def test_device_build_handles_duplicate_and_degenerate_triangles(rt, scene_dir, 
     d = os.path.join(scene_dir, "dupmesh")
     xml = rt.scenes.scene_c3(d, res=(64, 36), spp=1, n=24, deterministic=True, name="dup")
     rt.scenes.write_ply(os.path.join(d, "dup_mesh.ply"), v, f, uv)
-    hs, (host, dev) = _scenes(rt, xml, [rt.RT_BVH_HOST_SAH, rt.RT_BVH_DEVICE_PLOC])
+    hs, (host, dev) = _scenes(rt, xml, [rt.RT_BVH_HOST_SAH, getattr(rt, builder)])
     assert dev.stats().bvh_device_meshes >= 1
     tris, _ = dev.read_bvh(rt.RT_DEBUG_TRIS)
     ids = tris.view(np.int32)[:, 3]
