@@ -1,4 +1,5 @@
 #include "imageio.h"
+#include "jpeg.h"
 #include <zlib.h>
 #include <cmath>
 #include <cstdio>
@@ -220,8 +221,28 @@ bool LoadImageFile(const std::string& path, LoadedImage* out, std::string* err) 
     // dispatch exactly as the Texture ctor does (src/Texture.cpp:8-22): ".png" anywhere, else ".exr", else JPEG
     if (NameHasExt(path.c_str(), "png")) return LoadPng(path, out, err);
     if (NameHasExt(path.c_str(), "exr")) return LoadExr(path, out, err);
-    *err = "JPEG textures are not supported by this host shell (convert to PNG/EXR): " + path;
-    return false;
+    return LoadJpeg(path, out, err);
+}
+
+// Texture::ReadJPG (src/Texture.cpp:191-240) keeps libjpeg's interleaved scanlines and numComponents; GetColorAtPixel
+// (:62-66) then reads raw[(j*w+i)*nc + 0..2].  For 3 components that is the pixel's RGB.  For a greyscale file (nc = 1) it
+// is the pixel and its two right-hand neighbours in scanline order (wrapping into the next row, running past the buffer at
+// the very end) - reproduced here, with the last two reads clamped to the final sample.
+bool LoadJpeg(const std::string& path, LoadedImage* out, std::string* err) {
+    std::vector<unsigned char> file;
+    if (!ReadAll(path, &file, err)) return false;
+    int w = 0, h = 0, nc = 0;
+    std::vector<uint8_t> px;
+    std::string why;
+    if (!DecodeJpeg(file, &w, &h, &nc, &px, &why)) { *err = why + ": " + path; return false; }
+    out->width = w; out->height = h; out->format = 0 /* RT_IMG_RGBA8 */;
+    out->bytes.resize((size_t)w * h * 4);
+    const size_t n = (size_t)w * h * nc;
+    for (size_t i = 0; i < (size_t)w * h; i++) {
+        for (int c = 0; c < 3; c++) { size_t k = i * nc + c; out->bytes[i * 4 + c] = px[k < n ? k : n - 1]; }
+        out->bytes[i * 4 + 3] = 255;
+    }
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------- writers

@@ -20,6 +20,7 @@ struct LoadedImage {
 bool NameHasExt(const char* name, const char* ext3);   // the reference's ".png"/".exr" substring scan (src/Texture.cpp:133-183)
 bool LoadPng(const std::string& path, LoadedImage* out, std::string* err);
 bool LoadExr(const std::string& path, LoadedImage* out, std::string* err);
+bool LoadJpeg(const std::string& path, LoadedImage* out, std::string* err);   // baseline / extended sequential (host/jpeg.h)
 bool LoadImageFile(const std::string& path, LoadedImage* out, std::string* err);
 
 bool SavePpmP3(const std::string& path, const float* rgb, int nx, int ny, std::string* err);

@@ -307,3 +307,71 @@ def test_scene_blob_round_trip_staleness_and_corruption(rt, tmp_path):
     with pytest.raises(rt.RtError):
         rt.HostScene(blob=os.path.join(d, "missing.blob"))
     a.close()
+
+
+def _load_image_texture(rt, tmp, name):
+    import ctypes as C
+    tex = f'<Textures><Images><Image id="1">{name}</Image></Images><TextureMap id="1" type="image"><ImageId>1</ImageId><DecalMode>replace_kd</DecalMode></TextureMap></Textures>'
+    objs = '<Sphere id="1"><Material>1</Material><Center>1</Center><Radius>1</Radius><Textures>1</Textures></Sphere>'
+    hs = rt.HostScene(write_scene(tmp, textures=tex, objects=objs))
+    im = hs.desc.contents.images[0]
+    px = np.ctypeslib.as_array(C.cast(im.pixels, C.POINTER(C.c_ubyte)), shape=(im.height, im.width, 4)).copy()
+    hs.close()
+    return px
+
+
+def test_jpeg_decoder_matches_libjpeg(rt, tmp_path):
+    """Image textures in JPEG (Texture::ReadJPG, src/Texture.cpp:191-240): the baseline decoder reproduces libjpeg's default
+    arithmetic (islow IDCT, fancy h2v1/h2v2 upsampling, fixed-point YCbCr->RGB), checked against PIL's libjpeg decode on smooth
+    and noisy images, odd sizes, every common chroma subsampling, restart intervals and greyscale (with the reference's
+    neighbour-read quirk for one-component files)."""
+    from PIL import Image
+    d = str(tmp_path / "j")
+    os.makedirs(d, exist_ok=True)
+    rng = np.random.default_rng(7)
+    yy, xx = np.mgrid[0:61, 0:83]
+    smooth = np.stack([127 + 120 * np.sin(xx / 9.0), 127 + 120 * np.cos(yy / 7.0), (xx * 3 + yy * 2) % 256], axis=-1).astype(np.uint8)
+    noisy = rng.integers(0, 256, size=(37, 23, 3)).astype(np.uint8)
+    tiny = rng.integers(0, 256, size=(5, 3, 3)).astype(np.uint8)
+    cases = []
+    for name, img in (("smooth", smooth), ("noisy", noisy), ("tiny", tiny)):
+        for sub in (0, 1, 2):                                            # 4:4:4, 4:2:2, 4:2:0
+            for q in (95, 60):
+                cases.append((f"{name}_s{sub}_q{q}.jpg", img, dict(quality=q, subsampling=sub)))
+    cases.append(("restart.jpg", smooth, dict(quality=85, subsampling=2, restart_marker_blocks=3)))
+    cases.append(("optimized.jpg", smooth, dict(quality=85, subsampling=2, optimize=True)))
+    worst = 0
+    for fn, img, kw in cases:
+        path = os.path.join(d, fn)
+        try:
+            Image.fromarray(img).save(path, format="JPEG", **kw)
+        except TypeError:
+            continue                                                     # an older PIL without restart_marker_blocks
+        want = np.asarray(Image.open(path).convert("RGB"))
+        got = _load_image_texture(rt, d, fn)
+        assert got.shape[:2] == want.shape[:2] and (got[..., 3] == 255).all()
+        diff = np.abs(got[..., :3].astype(int) - want.astype(int)).max()
+        worst = max(worst, int(diff))
+        assert diff <= 1, (fn, diff)                                     # same integer arithmetic; <= 1 leaves room for a libjpeg variant's rounding
+    # greyscale: the reference reads raw[idx], raw[idx+1], raw[idx+2] with numComponents = 1 (src/Texture.cpp:62-66)
+    g = (127 + 100 * np.sin(xx / 5.0) * np.cos(yy / 6.0)).astype(np.uint8)
+    Image.fromarray(g, mode="L").save(os.path.join(d, "grey.jpg"), format="JPEG", quality=90)
+    want = np.asarray(Image.open(os.path.join(d, "grey.jpg")))
+    assert want.ndim == 2
+    flat = want.ravel()
+    idx = np.arange(flat.size)
+    quirk = np.stack([flat[np.minimum(idx + k, flat.size - 1)] for k in range(3)], axis=-1).reshape(want.shape + (3,))
+    got = _load_image_texture(rt, d, "grey.jpg")
+    assert np.abs(got[..., :3].astype(int) - quirk.astype(int)).max() <= 1
+    # unsupported flavours and corrupt files are errors with a reason, not crashes
+    Image.fromarray(smooth).save(os.path.join(d, "prog.jpg"), format="JPEG", progressive=True)
+    with pytest.raises(rt.RtError, match="progressive"):
+        _load_image_texture(rt, d, "prog.jpg")
+    data = open(os.path.join(d, "smooth_s2_q95.jpg"), "rb").read()
+    for i, mutate in enumerate((lambda x: x[: len(x) // 3], lambda x: x[:200], lambda x: b"\\xff\\xd8" + bytes(50), lambda x: x[:2] + x[40:])):
+        with open(os.path.join(d, f"bad{i}.jpg"), "wb") as f:
+            f.write(mutate(data))
+        try:
+            _load_image_texture(rt, d, f"bad{i}.jpg")                    # a truncated scan may still decode (zeros fed, like libjpeg); it must not crash
+        except rt.RtError:
+            pass
