@@ -604,6 +604,7 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
 
     size_t cap_hint = opts.queue_capacity > 0 ? (size_t)opts.queue_capacity : ((size_t)1 << 22);
     if (opts.queue_capacity <= 0) if (const char* e = getenv("RT795_QUEUE_CAP")) cap_hint = (size_t)atoll(e);
+    if ((unsigned long long)proto.tl.local_tiles * proto.tl.tw * proto.tl.th >= (1ull << 32)) throw Invalid{"frame too large: more than 2^32 pixel slots per rank"};
     unsigned long long total = (unsigned long long)proto.tl.local_tiles * proto.tl.tw * proto.tl.th * (unsigned long long)proto.cam.spp;
     // one pipeline when stages are timed / counted (clean per-stage numbers) or the frame is a single wave
     unsigned long long wave_hint = opts.wave_rays > 0 ? (unsigned long long)opts.wave_rays : (unsigned long long)cap_hint;
@@ -642,7 +643,7 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
                 int n = (int)std::min<unsigned long long>((unsigned long long)wave, total - base);
                 CK(cudaMemsetAsync(&dr.pp->counters.p->next_count, 0, sizeof(int32_t), ps));
                 dr.Timed(&res[p].ms_raygen, [&] {
-                    k_raygen<<<Blocks(n), kBlock, 0, ps>>>(dr.cam, dr.tl, dr.rc, max_depth, base, n, dr.pp->levels[0].View(), &dr.pp->counters.p->next_count, 0);
+                    k_raygen<<<Blocks(n), kBlock, 0, ps>>>(dr.cam, dr.tl, dr.rc, max_depth, (unsigned)(base / (unsigned long long)dr.cam.spp), (unsigned)(base % (unsigned long long)dr.cam.spp), n, dr.pp->levels[0].View(), &dr.pp->counters.p->next_count, 0);
                 });
                 dr.launches++;
                 CK(cudaMemcpyAsync(dr.pp->h_counters, dr.pp->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost, ps));
@@ -822,7 +823,7 @@ int rt_trace_primary(RtScene* sc, const RtCameraDesc* cam, RtHit* out_hits) {
         for (unsigned long long base = 0; base < total; base += (unsigned long long)wave) {
             int n = (int)std::min<unsigned long long>((unsigned long long)wave, total - base);
             CK(cudaMemsetAsync(pp->counters.p, 0, sizeof(DCounters), st));
-            k_raygen<<<Blocks(n), kBlock, 0, st>>>(dc, tl, rc, 0, base, n, pp->levels[0].View(), &pp->counters.p->next_count, 1);
+            k_raygen<<<Blocks(n), kBlock, 0, st>>>(dc, tl, rc, 0, (unsigned)base, 0u, n, pp->levels[0].View(), &pp->counters.p->next_count, 1);
             CK(cudaMemcpyAsync(pp->h_counters, pp->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             int n0 = pp->h_counters->next_count;

@@ -15,24 +15,35 @@ namespace rt795 {
 
 constexpr int kBlock = 128;
 
-// ---- warp-aggregated queue slot reservation (K5).  Must be called by all 32 lanes of the warp.
-RT_D int warp_reserve(int32_t* counter, int want /*0,1,2*/, int& total_out) {
+// ---- queue slot reservation (K5): ballot + prefix inside the warp, per-warp totals in shared memory, ONE atomicAdd per CTA per queue.
+// (First version: one atomicAdd per warp.)  A queue counter is a single address, served by a single L2 slice at
+// about one atomic per clock; with one atomic per warp the counters of a 4 Mi-ray launch took 130 k (raygen) to 390 k (shade,
+// two lights) serialised atomics - raygen 3.6 -> 1.9 ms per C4 frame, and the other pipeline's kernels stop queueing behind them.
+// Must be called by every thread of the CTA (kBlock threads); `scratch` is kBlock/32 + 1 ints of shared memory.
+RT_D int block_reserve(int32_t* counter, int want /*0,1,2*/, int* scratch) {
     const unsigned full = 0xffffffffu;
-    unsigned lane = threadIdx.x & 31u;
+    unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     unsigned b1 = __ballot_sync(full, want >= 1), b2 = __ballot_sync(full, want >= 2);
     unsigned lt = (1u << lane) - 1u;
-    int total = __popc(b1) + __popc(b2);
-    int base = 0;
-    if (lane == 0 && total) base = atomicAdd(counter, total);
-    base = __shfl_sync(full, base, 0);
-    total_out = total;
-    return base + __popc(b1 & lt) + __popc(b2 & lt);
+    if (lane == 0) scratch[warp] = __popc(b1) + __popc(b2);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < kBlock / 32; w++) { int c = scratch[w]; scratch[w] = tot; tot += c; }
+        scratch[kBlock / 32] = tot ? atomicAdd(counter, tot) : 0;
+    }
+    __syncthreads();
+    return scratch[kBlock / 32] + scratch[warp] + __popc(b1 & lt) + __popc(b2 & lt);
 }
 
 RT_D int meta_pack(int depth, uint32_t flags, int beer_mat) { return (depth & 0xff) | (int)((flags & 0xffu) << 8) | (beer_mat << 16); }
 
 // ---- K1
-__global__ void __launch_bounds__(kBlock) k_raygen(DCamera cam, DTiling tl, RenderConsts rc, int max_depth, unsigned long long work_base, int count,
+// Work item w = work_base + i enumerates (pixel slot, sample) with the sample fastest.  The host hands work_base over as
+// (base_rest, base_sample) = (work_base / spp, work_base % spp) so that every division here is 32-bit (64-bit division by a
+// run-time value is a ~100-instruction subroutine; this kernel had four of them per ray).
+__global__ void __launch_bounds__(kBlock) k_raygen(DCamera cam, DTiling tl, RenderConsts rc, int max_depth, unsigned base_rest, unsigned base_sample, int count,
                                                    DRayQueue q, int32_t* q_count, int center_only) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool active = i < count;
@@ -40,13 +51,13 @@ __global__ void __launch_bounds__(kBlock) k_raygen(DCamera cam, DTiling tl, Rend
     float time = 0.f;
     uint32_t pixel = 0, sample = 0;
     if (active) {
-        unsigned long long w = work_base + (unsigned long long)i;
         int spp = center_only ? 1 : cam.spp;
-        sample = (uint32_t)(w % (unsigned long long)spp);
-        unsigned long long rest = w / (unsigned long long)spp;
-        int tile_px = tl.tw * tl.th;
-        int pit = (int)(rest % (unsigned long long)tile_px);
-        int lt = (int)(rest / (unsigned long long)tile_px);
+        unsigned sw = base_sample + (unsigned)i, sq = sw / (unsigned)spp;
+        sample = sw - sq * (unsigned)spp;
+        unsigned rest = base_rest + sq;
+        unsigned tile_px = (unsigned)(tl.tw * tl.th);
+        int lt = (int)(rest / tile_px);
+        int pit = (int)(rest - (unsigned)lt * tile_px);
         int k = lt * tl.count + tl.rank;
         int tx = k % tl.tiles_x, ty = k / tl.tiles_x;
         int sb = pit >> 5, ln = pit & 31, sbx = tl.tw >> 3;        // 8x4 sub-blocks: one warp = one compact pixel block
@@ -85,8 +96,8 @@ __global__ void __launch_bounds__(kBlock) k_raygen(DCamera cam, DTiling tl, Rend
             }
         }
     }
-    int total;
-    int slot = warp_reserve(q_count, active ? 1 : 0, total);
+    __shared__ int s_res[kBlock / 32 + 1];
+    int slot = block_reserve(q_count, active ? 1 : 0, s_res);
     if (active) {
         q.o_time[slot] = make_float4(o.x, o.y, o.z, time);
         q.d_tmax[slot] = make_float4(d.x, d.y, d.z, 3.0e38f);
@@ -355,17 +366,18 @@ __global__ void __launch_bounds__(kBlock, RT795_SHADE_MIN_BLOCKS) k_shade(DScene
 
     warp_accum(accum, has_pend, pixel, pend);
     // ---- continuation rays -> next queue (pairs stay adjacent: slot, slot+1)
+    __shared__ int s_res[kBlock / 32 + 1];
     {
-        int total;
-        int slot = warp_reserve(&ctr->next_count, n_out, total);
+        int slot = block_reserve(&ctr->next_count, n_out, s_res);
         if (n_out) {
             if (slot + n_out > rc.queue_cap) atomicExch(&ctr->overflow, 1);
             else { write_ray(out, slot, pixel, r0); if (n_out == 2) write_ray(out, slot + 1, pixel, r1); }
         }
     }
     // ---- direct lighting: one shadow ray per light with a non-zero unoccluded contribution (Scene::BasicShading loop, src/Scene.cpp:252-264)
-    unsigned any_lit = __ballot_sync(0xffffffffu, lit);
-    if (any_lit) {
+    // (CTA-uniform loop: every thread takes part in each light's slot reservation; a light's rays of one CTA end up contiguous
+    // in the shadow queue, so the occlusion kernel's warps see rays towards one light from neighbouring hits)
+    if (__syncthreads_or(lit)) {
         for (int li = 0; li < sc.num_lights; li++) {
             LightSample ls;
             bool emit = false;
@@ -374,8 +386,7 @@ __global__ void __launch_bounds__(kBlock, RT795_SHADE_MIN_BLOCKS) k_shade(DScene
                 c = W * ls.radiance;
                 emit = !is_zero(c) && !any_nan(c);
             }
-            int total;
-            int slot = warp_reserve(&ctr->shadow_count, emit ? 1 : 0, total);
+            int slot = block_reserve(&ctr->shadow_count, emit ? 1 : 0, s_res);
             if (emit) {
                 if (slot >= rc.shadow_cap) atomicExch(&ctr->overflow, 1);
                 else {
