@@ -13,6 +13,10 @@
 // the full warp, blocked lanes idling inside the phase) raises the leaf-phase batch from 3.0 to 10.8 lanes (occlusion) and
 // 12.9 to 18.9 (closest hit) but drops the node-step batch from 15.9 to 11.8 and 24.2 to 20.0 lanes because leaf holders
 // wait for the slowest searcher: C4 frame 68.7 -> 77.0 ms.  The loose votes over __activemask() below are faster.
+// Third dead end: per-warp private batches of 32..256 queue entries (one visit to the global ray cursor per batch instead of per
+// fetch) - unlike the queue-slot reservations (kernels.cuh block_reserve), the cursor's same-address atomics are not what
+// limits these kernels: occlusion stage 30.8 -> 33.4..35.7 ms, closest hit 17.6 -> 17.7..24.3 ms (tail imbalance grows with
+// the batch).
 // Second dead end: 2 / 4 pending-leaf slots per lane instead of one (sibling leaves of a 4-wide node arrive in groups).  Leaf
 // phases drop 64.6 M -> 23.5 M (occlusion, 4 slots) and their batch rises 2.5 -> 4.3 lanes, but the extra speculative node
 // visits (8.28 -> 8.92 per ray) cost as much: occlusion stage +1.0 ms, closest hit -0.5 ms, frame +1 ms.
