@@ -748,6 +748,8 @@ int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out) {
             const char* tv = getenv("RT795_TRAVERSAL");
             sc->persistent = !(tv && std::string(tv) == "classic");
             if (const char* f = getenv("RT795_TRAVERSAL_FLAGS")) sc->trav_flags = sc->trav_flags_shadow = atoi(f);
+            if (const char* f = getenv("RT795_FLAGS_CLOSEST")) sc->trav_flags = atoi(f);
+            if (const char* f = getenv("RT795_FLAGS_OCCLUSION")) sc->trav_flags_shadow = atoi(f);
             if (const char* g = getenv("RT795_FULL_GRID")) sc->full_grid = atoi(g) != 0;
             if (const char* q = getenv("RT795_QNODES")) sc->quantised_occlusion = atoi(q) != 0;
             cudaDeviceProp prop;
