@@ -13,6 +13,10 @@
 // the full warp, blocked lanes idling inside the phase) raises the leaf-phase batch from 3.0 to 10.8 lanes (occlusion) and
 // 12.9 to 18.9 (closest hit) but drops the node-step batch from 15.9 to 11.8 and 24.2 to 20.0 lanes because leaf holders
 // wait for the slowest searcher: C4 frame 68.7 -> 77.0 ms.  The loose votes over __activemask() below are faster.
+// Fourth dead end: sign-specialised 256-byte nodes (every axis stored as [lo4|hi4] and again as [hi4|lo4], the ray's sign bit picks
+// the 32-byte half, one LDG.E.256 per axis: 4 load instructions per node instead of 7, no selects).  Correct, but slower:
+// occlusion 30.8 -> 33.1 ms (76 instead of 72 registers: 6 instead of 7 CTAs/SM), closest hit 17.6 -> 17.85 ms at unchanged
+// occupancy - the node array doubles (59 MB) and with it the L1/L2 footprint per visit; the wavefronts saved do not pay for it.
 // Third dead end: per-warp private batches of 32..256 queue entries (one visit to the global ray cursor per batch instead of per
 // fetch) - unlike the queue-slot reservations (kernels.cuh block_reserve), the cursor's same-address atomics are not what
 // limits these kernels: occlusion stage 30.8 -> 33.4..35.7 ms, closest hit 17.6 -> 17.7..24.3 ms (tail imbalance grows with
