@@ -329,17 +329,13 @@ inline bool DecodeJpeg(const std::vector<uint8_t>& file, int* width, int* height
     }
     const bool ycc = !adobe || adobe_transform != 0;                     // jdapimin.c default_decompress_parms: 3 components = YCbCr unless Adobe says RGB
     // jdcolor.c build_ycc_rgb_table
-    static int cr_r[256], cb_b[256], cr_g[256], cb_g[256];
-    static bool tabs = false;
-    if (!tabs) {
-        for (int i = 0; i < 256; i++) {
-            int x = i - 128;
-            cr_r[i] = (int)((91881LL * x + 32768) >> 16);                // FIX(1.40200)
-            cb_b[i] = (int)((116130LL * x + 32768) >> 16);               // FIX(1.77200)
-            cr_g[i] = -46802 * x;                                        // FIX(0.71414)
-            cb_g[i] = -22554 * x + 32768;                                // FIX(0.34414) + ONE_HALF
-        }
-        tabs = true;
+    int cr_r[256], cb_b[256], cr_g[256], cb_g[256];
+    for (int i = 0; i < 256; i++) {
+        int x = i - 128;
+        cr_r[i] = (int)((91881LL * x + 32768) >> 16);                    // FIX(1.40200)
+        cb_b[i] = (int)((116130LL * x + 32768) >> 16);                   // FIX(1.77200)
+        cr_g[i] = -46802 * x;                                            // FIX(0.71414)
+        cb_g[i] = -22554 * x + 32768;                                    // FIX(0.34414) + ONE_HALF
     }
     const int ow1 = comps[1].dw * (hmax / comps[1].h) + 2, ow2 = comps[2].dw * (hmax / comps[2].h) + 2;
     for (int y = 0; y < H; y++) {
