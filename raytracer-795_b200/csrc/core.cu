@@ -90,6 +90,7 @@ struct RtScene {
     // geometry + shading buffers
     DevBuf<float4> nodes, nodes4, tris, spheres;
     DevBuf<uint4> nodes4q;
+    DevBuf<float4> tris_w;
     // RT795_QNODES=1: the occlusion kernel walks the 8-bit quantised copy of the 4-wide BVH (4 instead of 7 loads per node).
     // Measured on C4: 39.1 ms vs 34.9 ms with fp32 nodes - the byte decode (24 PRMT + 24 FADD per node) costs more on the
     // ALU-limited kernel than the saved L1 wavefronts return, so fp32 nodes stay the default.
@@ -109,6 +110,7 @@ struct RtScene {
     bool persistent = true;            // K2/K4 as persistent warps with dynamic fetch (traverse_pt.cuh); RT795_TRAVERSAL=classic selects traverse.cuh
     int grid_extend = 0, grid_shadow = 0;   // resident CTAs: SM count x occupancy
     int trav_flags = 2, trav_flags_shadow = 3;   // TraceIO.flags for closest-hit / occlusion launches (measured best on C4; RT795_TRAVERSAL_FLAGS overrides both)
+    bool affine_tris = true;                // RT795_AFFINE_TRIS=0: Moeller-Trumbore on {v0,e1,e2} in the render kernels too (A/B)
     bool full_grid = false;                 // RT795_FULL_GRID=1: one thread per ray instead of resident warps
     // render state
     Pipe pipes[kPipes];
@@ -438,6 +440,14 @@ bool BuildAndUpload(RtScene* sc, const RtSceneDesc* s, bool allow_device) {
 
     DScene& d = sc->d;
     d.nodes4q = sc->nodes4q.p;
+    d.tris_w = nullptr;
+    if (sc->affine_tris && tri_total > 0) {
+        sc->tris_w.Alloc((size_t)tri_total * 3);
+        k_make_affine_tris<<<(tri_total + 255) / 256, 256, 0, st>>>(sc->tris.p, tri_total, sc->tris_w.p);
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        d.tris_w = sc->tris_w.p;
+    }
     d.nodes4 = sc->nodes4.p; d.obj_root4 = sc->obj_root4.p; d.tlas_root4 = tlas_base4;
     d.nodes = sc->nodes.p; d.tris = sc->tris.p; d.obj_xf = sc->obj_xf.p; d.spheres = sc->spheres.p; d.tlas_root = tlas_base;
     d.obj_sh = sc->obj_sh.p; d.tri_idx = sc->tri_idx.p; d.vertices = sc->vertices.p; d.normals = sc->normals.p; d.texcoords = sc->texcoords.p;
@@ -507,6 +517,7 @@ struct Driver {
                     TraceIO io{q.o_time, q.d_tmax, first, m, &pp->counters.p->ray_cursor, q.hit, q.hit_obj, nullptr, nullptr, sc->trav_flags};
                     int grid = sc->full_grid ? Blocks(m) : std::min(Blocks(m), sc->grid_extend);
                     if (count) k_trace_persistent<false, true><<<grid, kBlock, 0, st>>>(sc->d, io, pp->counters.p);
+                    else if (sc->d.tris_w) k_trace_persistent<false, false, false, true><<<grid, kBlock, 0, st>>>(sc->d, io, pp->counters.p);
                     else k_trace_persistent<false, false><<<grid, kBlock, 0, st>>>(sc->d, io, pp->counters.p);
                 } else if (count) k_extend<true><<<Blocks(m), kBlock, 0, st>>>(sc->d, q, first, m, pp->counters.p);
                 else k_extend<false><<<Blocks(m), kBlock, 0, st>>>(sc->d, q, first, m, pp->counters.p);
@@ -529,6 +540,7 @@ struct Driver {
                         int grid = sc->full_grid ? Blocks(shadow_n) : std::min(Blocks(shadow_n), sc->grid_shadow);
                         if (count) k_trace_persistent<true, true><<<grid, kBlock, 0, st>>>(sc->d, io, pp->counters.p);
                         else if (sc->quantised_occlusion) k_trace_persistent<true, false, true><<<grid, kBlock, 0, st>>>(sc->d, io, pp->counters.p);
+                        else if (sc->d.tris_w) k_trace_persistent<true, false, false, true><<<grid, kBlock, 0, st>>>(sc->d, io, pp->counters.p);
                         else k_trace_persistent<true, false><<<grid, kBlock, 0, st>>>(sc->d, io, pp->counters.p);
                     } else if (count) k_shadow<true><<<Blocks(shadow_n), kBlock, 0, st>>>(sc->d, sq, shadow_n, accum, pp->counters.p);
                     else k_shadow<false><<<Blocks(shadow_n), kBlock, 0, st>>>(sc->d, sq, shadow_n, accum, pp->counters.p);
@@ -752,11 +764,17 @@ int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out) {
             if (const char* f = getenv("RT795_FLAGS_OCCLUSION")) sc->trav_flags_shadow = atoi(f);
             if (const char* g = getenv("RT795_FULL_GRID")) sc->full_grid = atoi(g) != 0;
             if (const char* q = getenv("RT795_QNODES")) sc->quantised_occlusion = atoi(q) != 0;
+            if (const char* q = getenv("RT795_AFFINE_TRIS")) sc->affine_tris = atoi(q) != 0;
             cudaDeviceProp prop;
             CK(cudaGetDeviceProperties(&prop, device));
             int be = 1, bs = 1;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_persistent<false, false>, kBlock, 0));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_trace_persistent<true, false>, kBlock, 0));
+            if (sc->affine_tris) {
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_persistent<false, false, false, true>, kBlock, 0));
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_trace_persistent<true, false, false, true>, kBlock, 0));
+            } else {
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_persistent<false, false>, kBlock, 0));
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_trace_persistent<true, false>, kBlock, 0));
+            }
             sc->grid_extend = prop.multiProcessorCount * std::max(1, be);
             sc->grid_shadow = prop.multiProcessorCount * std::max(1, bs);
         }

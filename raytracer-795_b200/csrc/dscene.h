@@ -34,6 +34,7 @@ struct DScene {
     const int32_t* obj_root4;           // per top-level entry: BLAS root in nodes4 (spheres: unused)
     int32_t tlas_root4;
     const float4* nodes;                // BvhNode64 as 4 x float4 (binary; classic kernels + rt_trace_primary)
+    const float4* tris_w;               // same triangles as ray -> (u, v, w) affine maps, 3 rows x float4 (traverse_pt.cuh tri_test_affine); NULL if off
     const float4* tris;                 // 3 x float4 per triangle in leaf order: (v0, bits prim), (e1, 0), (e2, 0)
     const DObjectXf* obj_xf;
     const float4* spheres;              // center.xyz, R

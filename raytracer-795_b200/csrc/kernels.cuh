@@ -400,6 +400,27 @@ __global__ void __launch_bounds__(kBlock, RT795_SHADE_MIN_BLOCKS) k_shade(DScene
     }
 }
 
+// ---- {v0, e1, e2} records -> affine ray-to-triangle maps (dscene.h tris_w), one thread per triangle, in double for the inverse
+__global__ void k_make_affine_tris(const float4* __restrict__ tris, int n, float4* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = tris[3 * (size_t)i], b = tris[3 * (size_t)i + 1], c = tris[3 * (size_t)i + 2];
+    double A[3] = {a.x, a.y, a.z}, e1[3] = {b.x, b.y, b.z}, e2[3] = {c.x, c.y, c.z};
+    double nn[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+    double n2 = nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2];
+    float4* o = out + 3 * (size_t)i;
+    if (!(n2 > 0.0) || !(n2 < 1.0e300)) {                                // zero-area triangle: w = 1 everywhere, never hit
+        o[0] = o[1] = make_float4(0.f, 0.f, 0.f, 0.f); o[2] = make_float4(0.f, 0.f, 0.f, 1.f);
+        return;
+    }
+    double ru[3] = {(e2[1] * nn[2] - e2[2] * nn[1]) / n2, (e2[2] * nn[0] - e2[0] * nn[2]) / n2, (e2[0] * nn[1] - e2[1] * nn[0]) / n2};
+    double rv[3] = {(nn[1] * e1[2] - nn[2] * e1[1]) / n2, (nn[2] * e1[0] - nn[0] * e1[2]) / n2, (nn[0] * e1[1] - nn[1] * e1[0]) / n2};
+    double rw[3] = {nn[0] / n2, nn[1] / n2, nn[2] / n2};
+    o[0] = make_float4((float)ru[0], (float)ru[1], (float)ru[2], (float)-(ru[0] * A[0] + ru[1] * A[1] + ru[2] * A[2]));
+    o[1] = make_float4((float)rv[0], (float)rv[1], (float)rv[2], (float)-(rv[0] * A[0] + rv[1] * A[1] + rv[2] * A[2]));
+    o[2] = make_float4((float)rw[0], (float)rw[1], (float)rw[2], (float)-(rw[0] * A[0] + rw[1] * A[1] + rw[2] * A[2]));
+}
+
 // ---- K8
 __global__ void k_resolve(const float* __restrict__ accum, float* __restrict__ out, int n3, float inv_spp) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -13,6 +13,9 @@
 // the full warp, blocked lanes idling inside the phase) raises the leaf-phase batch from 3.0 to 10.8 lanes (occlusion) and
 // 12.9 to 18.9 (closest hit) but drops the node-step batch from 15.9 to 11.8 and 24.2 to 20.0 lanes because leaf holders
 // wait for the slowest searcher: C4 frame 68.7 -> 77.0 ms.  The loose votes over __activemask() below are faster.
+// Fifth dead end: prefetch.global.L1 of a postponed leaf's triangles (when the leaf is recorded) and / or of the nodes pushed on
+// the stack: frame +0.2 ms (leaves) to +1.5 ms (leaves + pushed nodes); the leaf phases run with few lanes but are not
+// waiting on those lines.
 // Fourth dead end: sign-specialised 256-byte nodes (every axis stored as [lo4|hi4] and again as [hi4|lo4], the ray's sign bit picks
 // the 32-byte half, one LDG.E.256 per axis: 4 load instructions per node instead of 7, no selects).  Correct, but slower:
 // occlusion 30.8 -> 33.1 ms (76 instead of 72 registers: 6 instead of 7 CTAs/SM), closest hit 17.6 -> 17.85 ms at unchanged
@@ -55,7 +58,7 @@ RT_D void pt_accum(float* accum, float4 c) {
     }
 }
 
-template <bool ANY_HIT, bool COUNT, bool QNODES = false>
+template <bool ANY_HIT, bool COUNT, bool QNODES = false, bool AFFINE_TRIS = false>
 __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io, DCounters* ctr) {
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
@@ -267,12 +270,12 @@ __global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io,
                 if (COUNT) { unsigned am = __activemask(); if ((int)lane == __ffs(am) - 1) { d_leafexec++; d_leaflanes += __popc(am); } }
                 int payload = ~leaf;
                 int first = payload >> 3, count = (payload & 7) + 1;
-                const float4* tp = sc.tris + (size_t)first * 3;
+                const float4* tp = (AFFINE_TRIS ? sc.tris_w : sc.tris) + (size_t)first * 3;
                 bool done = false;
                 for (int i = 0; i < count; i++, tp += 3) {
                     if (COUNT) ++cnt_prims;
                     float t, u, v; int prim;
-                    if (tri_test(tp, o, d, eps, tmax, t, u, v, prim)) {
+                    if (AFFINE_TRIS ? tri_test_affine(tp, o, d, eps, tmax, t, u, v) : tri_test(tp, o, d, eps, tmax, t, u, v, prim)) {
                         tmax = t; hb = u; hg = v; hprim = first + i; hobj = cur_obj;
                         if (ANY_HIT) { done = true; break; }
                     }
