@@ -58,8 +58,17 @@ RT_D void pt_accum(float* accum, float4 c) {
     }
 }
 
+// Resident CTAs per SM the compiler must leave room for (A/B knobs).  7 x 128 threads = 72 registers per thread: what the
+// occlusion kernel uses anyway, and 80 -> 72 for closest hit, whose stage drops 17.2 -> 16.65 ms on C4; 8 CTAs (64 registers)
+// gives the gain back.
+#ifndef RT795_MINB_ANY
+#define RT795_MINB_ANY 7
+#endif
+#ifndef RT795_MINB_CLOSEST
+#define RT795_MINB_CLOSEST 7
+#endif
 template <bool ANY_HIT, bool COUNT, bool QNODES = false, bool AFFINE_TRIS = false>
-__global__ void __launch_bounds__(128) k_trace_persistent(DScene sc, TraceIO io, DCounters* ctr) {
+__global__ void __launch_bounds__(128, (COUNT || QNODES) ? 0 : (ANY_HIT ? RT795_MINB_ANY : RT795_MINB_CLOSEST)) k_trace_persistent(DScene sc, TraceIO io, DCounters* ctr) {
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
