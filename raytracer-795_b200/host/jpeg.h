@@ -1,10 +1,10 @@
-// Baseline / extended-sequential JPEG decoder (8-bit, Huffman; SOF0 / SOF1) for image textures - the reference reads them
+// JPEG decoder (8-bit, Huffman; sequential SOF0 / SOF1 and progressive SOF2) for image textures - the reference reads them
 // through libjpeg (Texture::ReadJPG, src/Texture.cpp:191-240: jpeg_read_header + jpeg_start_decompress with the library
 // defaults + jpeg_read_scanlines), which is not available here, so the decode is re-implemented with libjpeg's default
 // arithmetic: the "islow" integer inverse DCT, "fancy" (triangle-filter) h2v1 / h2v2 chroma upsampling, and the fixed-point
 // YCbCr -> RGB tables - so the texels equal what the reference would see (checked bit for bit against another libjpeg-based
-// decoder in tests/test_host_loader.py).  Progressive (SOF2), arithmetic-coded, lossless, 12-bit and CMYK files are rejected
-// with a message.  Header-only, no dependencies.
+// decoder in tests/test_host_loader.py).  Sequential (SOF0 / SOF1) and progressive (SOF2) Huffman files are decoded;
+// arithmetic-coded, lossless, 12-bit and CMYK files are rejected with a message.  Header-only, no dependencies.
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -38,6 +38,7 @@ struct Component {
     int dw = 0, dh = 0;                    // downsampled_width / downsampled_height (real samples)
     int pred = 0;
     std::vector<uint8_t> plane;            // wblocks*8 x hblocks*8
+    std::vector<int16_t> coefs;            // progressive files: wblocks*hblocks blocks of 64 (natural order), refined scan by scan
 };
 
 struct BitReader {
@@ -138,15 +139,16 @@ inline bool DecodeJpeg(const std::vector<uint8_t>& file, int* width, int* height
     Huff hdc[4], hac[4];
     std::vector<Component> comps;
     int W = 0, H = 0, hmax = 1, vmax = 1, restart = 0;
-    bool have_frame = false, adobe = false; int adobe_transform = -1;
+    bool have_frame = false, adobe = false, progressive = false, geometry = false; int adobe_transform = -1;
+    int scans = 0, mcux = 0, mcuy = 0;
     bool done = false;
     while (!done) {
         // next marker
         while (p < end && *p != 0xff) p++;
         while (p < end && *p == 0xff) p++;
-        if (p >= end) return fail("JPEG: no image data (missing SOS/EOI)");
+        if (p >= end) { if (progressive && scans > 0) break; return fail("JPEG: no image data (missing SOS/EOI)"); }
         int m = *p++;
-        if (m == 0xd9) return fail("JPEG: EOI before any scan");
+        if (m == 0xd9) { if (progressive && scans > 0) break; return fail("JPEG: EOI before any scan"); }
         if (m == 0x01 || (m >= 0xd0 && m <= 0xd7)) continue;
         if (p + 2 > end) return fail("JPEG: truncated segment");
         int len = (p[0] << 8) | p[1];
@@ -177,6 +179,8 @@ inline bool DecodeJpeg(const std::vector<uint8_t>& file, int* width, int* height
                     h.Build();
                 }
                 break;
+            case 0xc2: progressive = true;   // SOF2: same frame header; coefficients arrive spread over several scans
+            // fall through
             case 0xc0: case 0xc1: {   // SOF0 / SOF1
                 if (se - s < 6) return fail("JPEG: truncated SOF");
                 if (s[0] != 8) return fail("JPEG: only 8-bit samples are supported");
@@ -195,44 +199,162 @@ inline bool DecodeJpeg(const std::vector<uint8_t>& file, int* width, int* height
                 }
                 have_frame = true;
             } break;
-            case 0xc2: return fail("JPEG: progressive files are not supported (re-save as baseline, or use PNG/EXR)");
             case 0xc3: case 0xc5: case 0xc6: case 0xc7: case 0xc9: case 0xca: case 0xcb: case 0xcd: case 0xce: case 0xcf:
                 return fail("JPEG: lossless / hierarchical / arithmetic-coded files are not supported");
             case 0xdd: if (se - s < 2) return fail("JPEG: truncated DRI"); restart = (s[0] << 8) | s[1]; break;
             case 0xee: if (se - s >= 12 && !memcmp(s, "Adobe", 5)) { adobe = true; adobe_transform = s[11]; } break;
-            case 0xda: {   // SOS: one interleaved scan with all components (baseline files written by every common encoder)
+            case 0xda: {   // SOS
                 if (!have_frame) return fail("JPEG: SOS before SOF");
                 if (se - s < 1) return fail("JPEG: truncated SOS");
                 int ns = s[0];
-                if (ns != (int)comps.size()) return fail("JPEG: non-interleaved multi-scan files are not supported");
-                if (se - s < 1 + 2 * ns + 3) return fail("JPEG: truncated SOS");
+                if (ns < 1 || ns > (int)comps.size() || se - s < 1 + 2 * ns + 3) return fail("JPEG: bad SOS");
+                if (!progressive && ns != (int)comps.size()) return fail("JPEG: non-interleaved sequential files are not supported");
+                Component* sc[4] = {nullptr, nullptr, nullptr, nullptr};
                 for (int i = 0; i < ns; i++) {
                     int cid = s[1 + 2 * i], tt = s[2 + 2 * i];
                     Component* c = nullptr;
                     for (auto& cc : comps) if (cc.id == cid) c = &cc;
                     if (!c) return fail("JPEG: SOS names an unknown component");
                     c->td = tt >> 4; c->ta = tt & 15;
-                    if (c->td > 3 || c->ta > 3 || !hdc[c->td].present || !hac[c->ta].present || !qt_ok[c->tq]) return fail("JPEG: scan refers to a missing table");
+                    if (c->td > 3 || c->ta > 3 || !qt_ok[c->tq]) return fail("JPEG: scan refers to a missing table");
+                    sc[i] = c;
                 }
-                done = true;
+                if (!geometry) {
+                    if (comps.size() == 1) { comps[0].h = comps[0].v = 1; hmax = vmax = 1; }   // a single-component image is never subsampled
+                    mcux = (W + 8 * hmax - 1) / (8 * hmax); mcuy = (H + 8 * vmax - 1) / (8 * vmax);
+                    if ((long long)mcux * mcuy * 64 * hmax * vmax > (1ll << 31)) return fail("JPEG: image too large");
+                    for (auto& c : comps) {
+                        c.wblocks = mcux * c.h; c.hblocks = mcuy * c.v;
+                        c.dw = (W * c.h + hmax - 1) / hmax; c.dh = (H * c.v + vmax - 1) / vmax;
+                        c.plane.assign((size_t)c.wblocks * 8 * c.hblocks * 8, 0);
+                        if (progressive) c.coefs.assign((size_t)c.wblocks * c.hblocks * 64, 0);
+                    }
+                    geometry = true;
+                }
+                if (!progressive) {
+                    for (int i = 0; i < ns; i++) if (!hdc[sc[i]->td].present || !hac[sc[i]->ta].present) return fail("JPEG: scan refers to a missing table");
+                    done = true;
+                    break;
+                }
+                // ---- one progressive scan (ITU T.81 Annex G; libjpeg jdphuff.c): spectral band [Ss, Se], successive approximation Ah -> Al
+                const int Ss = s[1 + 2 * ns], Se = s[2 + 2 * ns], Ah = s[3 + 2 * ns] >> 4, Al = s[3 + 2 * ns] & 15;
+                if (Ss > Se || Se > 63 || Al > 13 || (Ss == 0 && Se != 0) || (Ss > 0 && ns != 1)) return fail("JPEG: bad progressive scan parameters");
+                for (int i = 0; i < ns; i++) {
+                    if (Ss == 0 && Ah == 0 && !hdc[sc[i]->td].present) return fail("JPEG: scan refers to a missing table");
+                    if (Ss > 0 && !hac[sc[i]->ta].present) return fail("JPEG: scan refers to a missing table");
+                }
+                BitReader br{p, end};
+                int eobrun = 0, until = restart;
+                for (auto& c : comps) c.pred = 0;
+                auto do_restart = [&]() -> bool {
+                    const uint8_t* q = br.p;
+                    while (q + 1 < end && !(q[0] == 0xff && q[1] >= 0xd0 && q[1] <= 0xd7)) q++;
+                    if (q + 1 >= end) return false;
+                    br.p = q + 2; br.Reset();
+                    for (auto& c : comps) c.pred = 0;
+                    eobrun = 0; until = restart;
+                    return true;
+                };
+                auto decode_block = [&](Component& c, int16_t* blk) -> bool {
+                    if (Ss == 0) {
+                        if (Ah == 0) {                                    // DC first
+                            int sz;
+                            if (!DecodeSym(br, hdc[c.td], &sz) || sz > 11) return false;
+                            c.pred += sz ? Extend(br.Get(sz), sz) : 0;
+                            blk[0] = (int16_t)(c.pred * (1 << Al));
+                        } else if (br.Get(1)) blk[0] |= (int16_t)(1 << Al);   // DC refinement: one more bit
+                        return true;
+                    }
+                    if (Ah == 0) {                                        // AC first
+                        if (eobrun > 0) { eobrun--; return true; }
+                        for (int k = Ss; k <= Se; k++) {
+                            int rs;
+                            if (!DecodeSym(br, hac[c.ta], &rs)) return false;
+                            int r = rs >> 4, sz = rs & 15;
+                            if (sz) {
+                                k += r;
+                                if (k > 63) return false;
+                                blk[kZigzag[k]] = (int16_t)(Extend(br.Get(sz), sz) * (1 << Al));
+                            } else if (r == 15) k += 15;
+                            else { eobrun = (1 << r) - 1; if (r) eobrun += br.Get(r); break; }
+                        }
+                        return true;
+                    }
+                    // AC refinement
+                    const int p1 = 1 << Al, m1 = -(1 << Al);
+                    int k = Ss;
+                    if (eobrun == 0) {
+                        for (; k <= Se; k++) {
+                            int rs;
+                            if (!DecodeSym(br, hac[c.ta], &rs)) return false;
+                            int r = rs >> 4, sz = rs & 15, newval = 0;
+                            if (sz) { if (sz != 1) return false; newval = br.Get(1) ? p1 : m1; }
+                            else if (r != 15) { eobrun = 1 << r; if (r) eobrun += br.Get(r); break; }
+                            do {                                          // skip r zero-history coefficients, refining the non-zero ones passed
+                                int16_t* co = blk + kZigzag[k];
+                                if (*co != 0) {
+                                    if (br.Get(1) && (*co & p1) == 0) *co = (int16_t)(*co + (*co >= 0 ? p1 : m1));
+                                } else if (--r < 0) break;
+                                k++;
+                            } while (k <= Se);
+                            if (sz) { if (k > 63) return false; blk[kZigzag[k]] = (int16_t)newval; }
+                        }
+                    }
+                    if (eobrun > 0) {
+                        for (; k <= Se; k++) {
+                            int16_t* co = blk + kZigzag[k];
+                            if (*co != 0 && br.Get(1) && (*co & p1) == 0) *co = (int16_t)(*co + (*co >= 0 ? p1 : m1));
+                        }
+                        eobrun--;
+                    }
+                    return true;
+                };
+                if (ns == 1) {                                            // non-interleaved: the component's own block raster (not MCU-padded)
+                    Component& c = *sc[0];
+                    int bw = (c.dw + 7) / 8, bh = (c.dh + 7) / 8;
+                    for (int by = 0; by < bh; by++)
+                        for (int bx = 0; bx < bw; bx++) {
+                            if (restart && until == 0 && !do_restart()) return fail("JPEG: missing restart marker");
+                            if (!decode_block(c, c.coefs.data() + ((size_t)by * c.wblocks + bx) * 64)) return fail("JPEG: corrupt progressive scan");
+                            if (restart) until--;
+                        }
+                } else {
+                    for (int my = 0; my < mcuy; my++)
+                        for (int mx = 0; mx < mcux; mx++) {
+                            if (restart && until == 0 && !do_restart()) return fail("JPEG: missing restart marker");
+                            for (int i = 0; i < ns; i++) {
+                                Component& c = *sc[i];
+                                for (int by = 0; by < c.v; by++)
+                                    for (int bx = 0; bx < c.h; bx++)
+                                        if (!decode_block(c, c.coefs.data() + ((size_t)(my * c.v + by) * c.wblocks + (mx * c.h + bx)) * 64)) return fail("JPEG: corrupt progressive scan");
+                            }
+                            if (restart) until--;
+                        }
+                }
+                p = br.p;
+                scans++;
             } break;
             default: break;   // APPn, COM, ...
         }
     }
-    if ((comps.size() == 1)) { comps[0].h = comps[0].v = 1; hmax = vmax = 1; }   // a single-component scan is never subsampled
+    if (!geometry) return fail("JPEG: no scan");
     const int mcuw = 8 * hmax, mcuh = 8 * vmax;
-    const int mcux = (W + mcuw - 1) / mcuw, mcuy = (H + mcuh - 1) / mcuh;
-    if ((long long)mcux * mcuy * mcuw * mcuh > (1ll << 31)) return fail("JPEG: image too large");
-    for (auto& c : comps) {
-        c.wblocks = mcux * c.h; c.hblocks = mcuy * c.v;
-        c.dw = (W * c.h + hmax - 1) / hmax; c.dh = (H * c.v + vmax - 1) / vmax;
-        c.plane.assign((size_t)c.wblocks * 8 * c.hblocks * 8, 0);
+    (void)mcuw; (void)mcuh;
+    int coef[64];
+    if (progressive) {
+        // every scan has been folded into the coefficient arrays: dequantise + inverse DCT
+        for (auto& c : comps)
+            for (int by = 0; by < c.hblocks; by++)
+                for (int bx = 0; bx < c.wblocks; bx++) {
+                    const int16_t* blk = c.coefs.data() + ((size_t)by * c.wblocks + bx) * 64;
+                    for (int k = 0; k < 64; k++) coef[k] = blk[k] * qt[c.tq][k];
+                    IdctIslow(coef, c.plane.data() + (size_t)by * 8 * c.wblocks * 8 + bx * 8, c.wblocks * 8);
+                }
     }
-    // ---- entropy-coded data
+    // ---- entropy-coded data of a sequential file: one interleaved scan
     BitReader br{p, end};
     int until_restart = restart;
-    int coef[64];
-    for (int my = 0; my < mcuy; my++) {
+    for (int my = 0; !progressive && my < mcuy; my++) {
         for (int mx = 0; mx < mcux; mx++) {
             if (restart && until_restart == 0) {
                 // RSTn: byte-align, skip the marker, reset predictors

@@ -321,7 +321,7 @@ def _load_image_texture(rt, tmp, name):
 
 
 def test_jpeg_decoder_matches_libjpeg(rt, tmp_path):
-    """Image textures in JPEG (Texture::ReadJPG, src/Texture.cpp:191-240): the baseline decoder reproduces libjpeg's default
+    """Image textures in JPEG (Texture::ReadJPG, src/Texture.cpp:191-240): the sequential + progressive decoder reproduces libjpeg's default
     arithmetic (islow IDCT, fancy h2v1/h2v2 upsampling, fixed-point YCbCr->RGB), checked against PIL's libjpeg decode on smooth
     and noisy images, odd sizes, every common chroma subsampling, restart intervals and greyscale (with the reference's
     neighbour-read quirk for one-component files)."""
@@ -340,6 +340,10 @@ def test_jpeg_decoder_matches_libjpeg(rt, tmp_path):
                 cases.append((f"{name}_s{sub}_q{q}.jpg", img, dict(quality=q, subsampling=sub)))
     cases.append(("restart.jpg", smooth, dict(quality=85, subsampling=2, restart_marker_blocks=3)))
     cases.append(("optimized.jpg", smooth, dict(quality=85, subsampling=2, optimize=True)))
+    for name, img in (("smooth", smooth), ("noisy", noisy), ("tiny", tiny)):        # progressive: DC/AC first + refinement scans, EOB runs
+        for sub in (0, 1, 2):
+            cases.append((f"{name}_prog_s{sub}.jpg", img, dict(quality=80, subsampling=sub, progressive=True)))
+    cases.append(("prog_restart.jpg", smooth, dict(quality=30, subsampling=2, progressive=True, restart_marker_blocks=5)))
     worst = 0
     for fn, img, kw in cases:
         path = os.path.join(d, fn)
@@ -364,9 +368,18 @@ def test_jpeg_decoder_matches_libjpeg(rt, tmp_path):
     got = _load_image_texture(rt, d, "grey.jpg")
     assert np.abs(got[..., :3].astype(int) - quirk.astype(int)).max() <= 1
     # unsupported flavours and corrupt files are errors with a reason, not crashes
-    Image.fromarray(smooth).save(os.path.join(d, "prog.jpg"), format="JPEG", progressive=True)
-    with pytest.raises(rt.RtError, match="progressive"):
-        _load_image_texture(rt, d, "prog.jpg")
+    Image.fromarray(smooth).convert("CMYK").save(os.path.join(d, "cmyk.jpg"), format="JPEG")
+    with pytest.raises(rt.RtError, match="CMYK"):
+        _load_image_texture(rt, d, "cmyk.jpg")
+    for src in ("smooth_s2_q95.jpg", "smooth_prog_s2.jpg"):
+        data = open(os.path.join(d, src), "rb").read()
+        for i, mutate in enumerate((lambda x: x[: len(x) // 3], lambda x: x[: len(x) * 2 // 3], lambda x: x[:200])):
+            with open(os.path.join(d, f"cut{i}.jpg"), "wb") as f:
+                f.write(mutate(data))
+            try:
+                _load_image_texture(rt, d, f"cut{i}.jpg")
+            except rt.RtError:
+                pass
     data = open(os.path.join(d, "smooth_s2_q95.jpg"), "rb").read()
     for i, mutate in enumerate((lambda x: x[: len(x) // 3], lambda x: x[:200], lambda x: b"\\xff\\xd8" + bytes(50), lambda x: x[:2] + x[40:])):
         with open(os.path.join(d, f"bad{i}.jpg"), "wb") as f:
