@@ -674,12 +674,22 @@ CONFIGS = {
 
 
 # ------------------------------------------------------------------------------------------ feature-matrix scenes (parity coverage)
+def _rgb_test_image(w: int = 64, h: int = 48, seed: int = 3) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    return np.stack([(xx * 255 // max(1, w - 1)), (yy * 255 // max(1, h - 1)), ((xx // 8 + yy // 8) % 2) * 200 + rng.integers(0, 40, size=(h, w))], axis=-1).astype(np.uint8)
+
+
+def _write_jpeg(path: str, img: np.ndarray, **kw) -> None:
+    """JPEG texture through Pillow (test scenes only)."""
+    from PIL import Image
+    Image.fromarray(img).save(path, format="JPEG", **kw)
+
+
 def _write_png_rgb(path: str, w: int = 64, h: int = 48, seed: int = 3) -> None:
     """Small RGB8 PNG (non-interlaced) written with zlib only, readable by the oracle's png shim and the host shell."""
     import zlib
-    rng = np.random.default_rng(seed)
-    yy, xx = np.mgrid[0:h, 0:w]
-    img = np.stack([(xx * 255 // max(1, w - 1)), (yy * 255 // max(1, h - 1)), ((xx // 8 + yy // 8) % 2) * 200 + rng.integers(0, 40, size=(h, w))], axis=-1).astype(np.uint8)
+    img = _rgb_test_image(w, h, seed)
     raw = b"".join(b"\x00" + img[y].tobytes() for y in range(h))
 
     def chunk(t, d):
@@ -745,11 +755,20 @@ def scene_features(outdir: str, variant: str = "lights", res=(192, 144), spp: in
                               extra="      <RefractionIndex>1.6</RefractionIndex>\n      <AbsorptionIndex>2.5</AbsorptionIndex>\n")
             objects += sphere(k + 1, 2 + k, 9 + k, 0.7)
         objects += floor_mesh(1)
-    elif variant == "textures":
+    elif variant in ("textures", "textures_jpeg"):
         depth = 2
-        _write_png_rgb(os.path.join(outdir, f"{name}_t.png"))
+        e1, e3 = "png", "png"
+        if variant == "textures_jpeg":
+            # the same scene with its 8-bit images as JPEG (src/Texture.cpp:191-240): baseline 4:2:0, progressive 4:4:4 and a greyscale
+            # file, which the reference reads with numComponents = 1 (pixel + its two right-hand neighbours as R, G, B, :62-66)
+            e1, e3 = "jpg", "jpg"
+            _write_jpeg(os.path.join(outdir, f"{name}_t.jpg"), _rgb_test_image(), quality=92, subsampling=2)
+            _write_jpeg(os.path.join(outdir, f"{name}_bg.jpg"), _rgb_test_image(80, 60, seed=9), quality=85, subsampling=0, progressive=True)
+            _write_jpeg(os.path.join(outdir, f"{name}_g.jpg"), _rgb_test_image(72, 40, seed=5)[..., 2], quality=90)
+        else:
+            _write_png_rgb(os.path.join(outdir, f"{name}_t.png"))
+            _write_png_rgb(os.path.join(outdir, f"{name}_bg.png"), 80, 60, seed=9)
         checker_exr(os.path.join(outdir, f"{name}_t.exr"), 96, 64)
-        _write_png_rgb(os.path.join(outdir, f"{name}_bg.png"), 80, 60, seed=9)
         lights = ('<AmbientLight>20 20 20</AmbientLight>\n<PointLight id="1"><Position>1 9 7</Position><Intensity>4200 4200 4200</Intensity></PointLight>')
         maps = [("image", 1, "replace_kd", "nearest", 255, None, None, None), ("image", 2, "blend_kd", "bilinear", 255, None, None, None),
                 ("image", 1, "replace_all", "bilinear", 1, None, None, None), ("image", 1, "replace_normal", "bilinear", 255, None, None, None),
@@ -760,11 +779,14 @@ def scene_features(outdir: str, variant: str = "lights", res=(192, 144), spp: in
         for k, (ty, im, dm, ip, nz, nc, ns, bf) in enumerate(maps):
             tm += f'<TextureMap id="{k + 1}" type="{ty}">' + (f"<ImageId>{im}</ImageId>" if ty == "image" else "") + f"<DecalMode>{dm}</DecalMode><Interpolation>{ip}</Interpolation><Normalizer>{nz}</Normalizer>"
             tm += (f"<NoiseConversion>{nc}</NoiseConversion>" if nc else "") + (f"<NoiseScale>{ns}</NoiseScale>" if ns else "") + (f"<BumpFactor>{bf}</BumpFactor>" if bf else "") + "</TextureMap>\n"
-        textures = f'<Textures><Images><Image id="1">{name}_t.png</Image><Image id="2">{name}_t.exr</Image><Image id="3">{name}_bg.png</Image></Images>\n{tm}</Textures>'
+        if variant == "textures_jpeg":
+            tm += '<TextureMap id="10" type="image"><ImageId>4</ImageId><DecalMode>replace_kd</DecalMode><Interpolation>bilinear</Interpolation><Normalizer>255</Normalizer></TextureMap>\n'
+        img4 = f'<Image id="4">{name}_g.jpg</Image>' if variant == "textures_jpeg" else ""
+        textures = f'<Textures><Images><Image id="1">{name}_t.{e1}</Image><Image id="2">{name}_t.exr</Image><Image id="3">{name}_bg.{e3}</Image>{img4}</Images>\n{tm}</Textures>'
         transformations = '<Transformations><Scaling id="1">1.3 0.8 1</Scaling><Rotation id="1">40 0 1 0.3</Rotation><Translation id="1">0 0.4 0</Translation></Transformations>'
         tex = lambda ids: f"<Textures>{ids}</Textures>"
         objects = (sphere(1, 1, 9, 1.3, tex("1")) + sphere(2, 1, 10, 1.3, tex("2") + "<Transformations>s1 r1 t1</Transformations>") + sphere(3, 1, 11, 1.3, tex("4")) +
-                   sphere(4, 1, 12, 1.0, tex("5 6")) + sphere(5, 1, 13, 1.0, tex("7")) + sphere(6, 1, 14, 1.2, tex("3")) + floor_mesh(1, tex("9 7")))
+                   sphere(4, 1, 12, 1.0, tex("5 6")) + sphere(5, 1, 13, 1.0, tex("10" if variant == "textures_jpeg" else "7")) + sphere(6, 1, 14, 1.2, tex("3")) + floor_mesh(1, tex("9 7")))
         # a textured quad mesh with its own uv: replace_normal + bump from image on triangles
         verts += [(-7.5, 0.2, -6), (-2.5, 0.2, -6), (-2.5, 5.2, -7), (-7.5, 5.2, -7), (2.5, 0.2, -6), (7.5, 0.2, -6), (7.5, 5.2, -7), (2.5, 5.2, -7)]
         uvs += [(0, 0), (1, 0), (1, 1), (0, 1), (0, 0), (2, 0), (2, 2), (0, 2)]

@@ -248,7 +248,7 @@ def ctypes_byref(x):
 
 
 # ------------------------------------------------------------------------------------------------ feature matrix + edge cases
-@pytest.mark.parametrize("variant", ["lights", "brdf", "textures"])
+@pytest.mark.parametrize("variant", ["lights", "brdf", "textures", "textures_jpeg"])
 def test_feature_matrix_deterministic(rt, scene_dir, tmp_path, variant):
     """GPU vs oracle AND vs the unmodified reference binary on deterministic scenes covering every light type, BRDF,
     texture mode and material type."""

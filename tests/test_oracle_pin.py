@@ -116,10 +116,12 @@ def test_oracle_statistical_vs_live_reference(rt, scene_dir, have_ref, tmp_path,
     hs.close()
 
 
-@pytest.mark.parametrize("variant", ["lights", "brdf", "textures"])
+@pytest.mark.parametrize("variant", ["lights", "brdf", "textures", "textures_jpeg"])
 def test_oracle_feature_matrix_deterministic_vs_live_reference(rt, scene_dir, have_ref, tmp_path, variant):
     """Every light type, all eight BRDFs, every texture decal mode / interpolation / image format, transforms and the
-    mirror / conductor / dielectric recursion, against the unmodified reference on deterministic scenes."""
+    mirror / conductor / dielectric recursion, against the unmodified reference on deterministic scenes.  `textures_jpeg`:
+    the reference decodes its JPEG textures through an independent libjpeg (oracle/shim/jpeglib.h -> Pillow), the oracle's
+    scene comes from the product's own decoder (host/jpeg.h) - baseline, progressive and the greyscale neighbour-read quirk."""
     if not have_ref:
         pytest.skip("oracle/_ref not built")
     xml = rt.scenes.scene_features(os.path.join(scene_dir, "feat_" + variant), variant)
