@@ -37,7 +37,7 @@ typedef enum RtStatus {
     RT_ERR_CUDA = -2,      /* CUDA runtime failure (message holds cudaGetErrorString)    */
     RT_ERR_OOM = -3,       /* device or host allocation failed                           */
     RT_ERR_IO = -4,        /* host shell: file could not be read / written               */
-    RT_ERR_PARSE = -5,     /* host shell: malformed XML / PLY / EXR / PNG                */
+    RT_ERR_PARSE = -5,     /* host shell: malformed XML / PLY / EXR / PNG / JPEG / blob   */
     RT_ERR_OVERFLOW = -6   /* a wavefront queue would overflow (never silently dropped)  */
 } RtStatus;
 

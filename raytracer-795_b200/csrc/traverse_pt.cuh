@@ -120,15 +120,16 @@ __global__ void __launch_bounds__(128, (COUNT || QNODES) ? 0 : (ANY_HIT ? RT795_
         if (node != kSentinel) top_n = stack32[--sp];                                                  \
     } while (0)
 #define RT_POP()                                                                                       \
-    do { if (ANY_HIT) { RT_POP1(); break; }                                                            \
-      for (;;) {                                                                                       \
+    do { if (ANY_HIT) { RT_POP1(); } else {                                                            \
+      bool more_ = true;                                                                               \
+      while (more_) {                                                                                  \
         node = top_n;                                                                                  \
         if (node == kSentinel) break;                                                                  \
         float tt_ = top_t;                                                                             \
         unsigned long long e_ = stack[--sp];                                                           \
         top_n = (int)(unsigned)e_; top_t = __uint_as_float((unsigned)(e_ >> 32));                      \
-        if (node == kBlasExit || tt_ < tmax) break;                                                    \
-    } } while (0)
+        more_ = !(node == kBlasExit || tt_ < tmax);                                                    \
+      } } } while (0)
 
     while (true) {
         // ---------------- retire finished rays, fetch new ones
