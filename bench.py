@@ -183,9 +183,25 @@ def run_reference_arm(args, rt):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+class _QuietStdout:
+    """Keeps the process's stdout to the ONE JSON line: file descriptor 1 is pointed at stderr for the whole run (NCCL prints its
+    version banner with printf, below Python), and the line is written to the saved descriptor at the end."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.fd = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text: str):
+        sys.stdout.flush()
+        os.write(self.fd, (text + "\n").encode())
+
+
 def run_ours(args, rt):
     import torch
     import torch.distributed as dist
+
+    out = _QuietStdout()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -379,7 +395,7 @@ def run_ours(args, rt):
                         "api": "rt_render (host camera/options in, host framebuffer out)" if world == 1 else ("rt_render_device (K8 stores owned tiles into rank 0's frame over NVLink peer memory) + device barrier" if gather.mode == "p2p" else "rt_render_device + NCCL reduce") + " + D2H on rank 0",
                         "timing": "host clock around the synchronous call, max over ranks"},
                 "gpu_launches": int(lt.item()), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
-        print(json.dumps(line), flush=True)
+        out.emit(json.dumps(line))
     sc.close()
     hs.close()
     if world > 1:
