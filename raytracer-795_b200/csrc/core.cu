@@ -151,21 +151,29 @@ void Validate(const RtSceneDesc* s) {
     auto bad = [](const std::string& m) { throw Invalid{m}; };
     if (!s) bad("null scene description");
     if (s->abi_version != RT795_ABI_VERSION) bad("abi_version mismatch");
-    if (s->num_vertices < 0 || s->num_triangles < 0 || s->num_objects < 0) bad("negative count");
+    if (s->num_vertices < 0 || s->num_triangles < 0 || s->num_objects < 0 || s->num_meshes < 0 || s->num_spheres < 0 || s->num_textures < 0 ||
+        s->num_images < 0 || s->num_lights < 0 || s->num_texcoords < 0) bad("negative count");
+    if ((s->num_meshes && !s->meshes) || (s->num_spheres && !s->spheres) || (s->num_objects && !s->objects) || (s->num_textures && !s->textures) ||
+        (s->num_images && !s->images) || (s->num_lights && !s->lights) || (s->num_texcoords && !s->texcoords)) bad("array pointer missing for a non-zero count");
+    if (s->num_triangles > (1 << 28) || s->num_vertices > (1 << 30)) bad("scene too large (more than 2^28 triangles)");   // leaf refs carry 28-bit triangle indices
     if (s->num_vertices && !s->vertices) bad("vertices missing");
     if (s->num_triangles && !s->tri_indices) bad("tri_indices missing");
     if (s->num_materials < 1 || !s->materials) bad("at least one material is required");
     for (int i = 0; i < s->num_triangles * 3; i++) if (s->tri_indices[i] < 0 || s->tri_indices[i] >= s->num_vertices) bad("triangle vertex index out of range");
     for (int m = 0; m < s->num_meshes; m++) {
         const RtMesh& me = s->meshes[m];
-        if (me.first_tri < 0 || me.tri_count < 1 || me.first_tri + me.tri_count > s->num_triangles) bad("mesh triangle range out of bounds");
+        if (me.first_tri < 0 || me.tri_count < 1 || (long long)me.first_tri + me.tri_count > s->num_triangles) bad("mesh triangle range out of bounds");
         if (me.smooth && !s->vertex_normals) bad("smooth mesh without vertex_normals");
     }
     for (int t = 0; t < s->num_textures; t++) {
         const RtTexture& tx = s->textures[t];
         if (tx.type == RT_TEX_IMAGE && (tx.image < 0 || tx.image >= s->num_images)) bad("texture image index out of range");
     }
-    for (int i = 0; i < s->num_images; i++) if (s->images[i].width < 2 || s->images[i].height < 2 || !s->images[i].pixels) bad("image must be at least 2x2");
+    for (int i = 0; i < s->num_images; i++) {
+        if (s->images[i].width < 2 || s->images[i].height < 2 || !s->images[i].pixels) bad("image must be at least 2x2");
+        if (s->images[i].format != RT_IMG_RGBA8 && s->images[i].format != RT_IMG_RGBA32F) bad("unknown image format");
+        if ((long long)s->images[i].width * s->images[i].height > (1ll << 30)) bad("image too large");
+    }
     for (int i = 0; i < s->num_objects; i++) {
         const RtObject& o = s->objects[i];
         if (o.kind == RT_OBJ_SPHERE) { if (o.geom < 0 || o.geom >= s->num_spheres) bad("object sphere index out of range"); }

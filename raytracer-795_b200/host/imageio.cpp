@@ -148,19 +148,32 @@ bool LoadExr(const std::string& path, LoadedImage* out, std::string* err) {
         std::string name, type;
         if (pos >= f.size()) { *err = "truncated EXR header"; return false; }
         if (f[pos] == 0) { pos++; break; }
-        cstr(&name); cstr(&type);
+        if (!cstr(&name) || !cstr(&type) || pos + 4 > f.size()) { *err = "truncated EXR header"; return false; }
         int32_t sz; memcpy(&sz, &f[pos], 4); pos += 4;
-        if (pos + sz > f.size()) { *err = "truncated EXR header"; return false; }
+        if (sz < 0 || pos + (size_t)sz > f.size()) { *err = "truncated EXR header"; return false; }
+        const size_t aend = pos + (size_t)sz;
         if (name == "channels") {
             size_t p = pos;
-            while (f[p]) { Chan c; while (f[p]) c.name.push_back((char)f[p++]); p++; int32_t t; memcpy(&t, &f[p], 4); c.type = t; p += 16; chans.push_back(c); }
-        } else if (name == "compression") compression = f[pos];
-        else if (name == "dataWindow") { int32_t b[4]; memcpy(b, &f[pos], 16); xmin = b[0]; ymin = b[1]; xmax = b[2]; ymax = b[3]; }
+            while (p < aend && f[p]) {
+                Chan c;
+                while (p < aend && f[p]) c.name.push_back((char)f[p++]);
+                p++;
+                if (p + 16 > aend) { *err = "bad EXR channel list"; return false; }
+                int32_t t; memcpy(&t, &f[p], 4); c.type = t; p += 16;
+                if (t < 0 || t > 2 || chans.size() >= 64) { *err = "bad EXR channel list"; return false; }
+                chans.push_back(c);
+            }
+        } else if (name == "compression") { if (sz < 1) { *err = "bad EXR header"; return false; } compression = f[pos]; }
+        else if (name == "dataWindow") {
+            if (sz < 16) { *err = "bad EXR header"; return false; }
+            int32_t b[4]; memcpy(b, &f[pos], 16); xmin = b[0]; ymin = b[1]; xmax = b[2]; ymax = b[3];
+        }
         pos += sz;
     }
     if (compression != 0 && compression != 2 && compression != 3) { *err = "EXR compression not supported (NONE/ZIPS/ZIP only): " + path; return false; }
-    int w = xmax - xmin + 1, h = ymax - ymin + 1;
-    if (w <= 0 || h <= 0 || chans.empty()) { *err = "bad EXR header: " + path; return false; }
+    long long wl = (long long)xmax - xmin + 1, hl = (long long)ymax - ymin + 1;
+    if (wl <= 0 || hl <= 0 || wl > 65536 || hl > 65536 || chans.empty()) { *err = "bad EXR header: " + path; return false; }
+    int w = (int)wl, h = (int)hl;
     int lines_per_block = compression == 3 ? 16 : 1;
     int nblocks = (h + lines_per_block - 1) / lines_per_block;
     if (pos + 8ull * nblocks > f.size()) { *err = "truncated EXR offsets"; return false; }
@@ -184,11 +197,15 @@ bool LoadExr(const std::string& path, LoadedImage* out, std::string* err) {
         size_t p = offs[b];
         if (p + 8 > f.size()) { *err = "truncated EXR block"; return false; }
         int32_t y0, dsz; memcpy(&y0, &f[p], 4); memcpy(&dsz, &f[p + 4], 4); p += 8;
-        if (p + dsz > f.size()) { *err = "truncated EXR block"; return false; }
+        if (dsz < 0 || p + (size_t)dsz > f.size()) { *err = "truncated EXR block"; return false; }
+        if (y0 < ymin || y0 > ymax) { *err = "bad EXR block header"; return false; }
         int nl = std::min(lines_per_block, ymax - y0 + 1);
         size_t want = line_bytes * nl;
         block.resize(want);
-        if (compression == 0 || (size_t)dsz == want) memcpy(block.data(), &f[p], want);
+        if (compression == 0 || (size_t)dsz == want) {
+            if ((size_t)dsz < want) { *err = "truncated EXR block"; return false; }
+            memcpy(block.data(), &f[p], want);
+        }
         else {
             tmp.resize(want);
             uLongf got = want;

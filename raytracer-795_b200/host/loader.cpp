@@ -16,6 +16,8 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <new>
+#include <stdexcept>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -748,13 +750,24 @@ extern "C" {
 int rt_host_load_scene(const char* xml_path, RtHostScene** out) {
     if (!xml_path || !out) { SetLastError("rt_host_load_scene: null argument"); return RT_ERR_INVALID; }
     *out = nullptr;
-    RtHostScene* hs = new RtHostScene();
-    Loader ld(xml_path, hs);
-    std::string err;
-    if (!ld.Run(&err)) {
-        SetLastError("rt_host_load_scene: " + err);
+    RtHostScene* hs = nullptr;
+    try {                                                                // nothing may throw across the C boundary (a corrupt file can ask for absurd sizes)
+        hs = new RtHostScene();
+        Loader ld(xml_path, hs);
+        std::string err;
+        if (!ld.Run(&err)) {
+            SetLastError("rt_host_load_scene: " + err);
+            delete hs;
+            return ld.io_error() ? RT_ERR_IO : RT_ERR_PARSE;
+        }
+    } catch (const std::bad_alloc&) {
         delete hs;
-        return ld.io_error() ? RT_ERR_IO : RT_ERR_PARSE;
+        SetLastError("rt_host_load_scene: out of host memory");
+        return RT_ERR_OOM;
+    } catch (const std::exception& e) {
+        delete hs;
+        SetLastError(std::string("rt_host_load_scene: malformed input (") + e.what() + ")");
+        return RT_ERR_PARSE;
     }
     *out = hs;
     return RT_OK;
@@ -796,6 +809,7 @@ int rt_host_load_scene_blob(const char* blob_path, int check_sources, RtHostScen
     StatFile(blob_path, &fsize, &fmt);
     BlobReader r{f, true, fsize};
     RtHostScene* hs = new RtHostScene();
+    try {
     auto fail = [&](const std::string& why) { fclose(f); delete hs; SetLastError(std::string("rt_host_load_scene_blob: ") + blob_path + ": " + why); return RT_ERR_PARSE; };
     char magic[8];
     r.Raw(magic, 8);
@@ -836,6 +850,11 @@ int rt_host_load_scene_blob(const char* blob_path, int check_sources, RtHostScen
         (!hs->normals.empty() && hs->normals.size() != hs->vertices.size())) { delete hs; SetLastError(std::string("rt_host_load_scene_blob: ") + blob_path + ": inconsistent arrays"); return RT_ERR_PARSE; }
     hs->desc.abi_version = RT795_ABI_VERSION;
     BindDesc(hs);                                                         // rt_scene_create validates every index range again
+    } catch (const std::exception& e) {
+        delete hs;
+        SetLastError(std::string("rt_host_load_scene_blob: ") + blob_path + ": " + e.what());
+        return RT_ERR_PARSE;
+    }
     *out = hs;
     return RT_OK;
 }

@@ -388,3 +388,66 @@ def test_jpeg_decoder_matches_libjpeg(rt, tmp_path):
             _load_image_texture(rt, d, f"bad{i}.jpg")                    # a truncated scan may still decode (zeros fed, like libjpeg); it must not crash
         except rt.RtError:
             pass
+
+
+def test_mutated_inputs_never_crash(rt, tmp_path):
+    """Seeded fuzzing of every file format the host shell reads (XML, PLY, PNG, EXR, JPEG baseline + progressive, scene blob):
+    byte flips, truncations and spliced garbage must come back as an RtError or as a loadable scene - never as a crash or an
+    exception escaping the C boundary.  Loaded blobs are also pushed through rt_scene_create's validation (which runs before
+    any CUDA call, so this works without a GPU)."""
+    from PIL import Image
+    d = str(tmp_path / "fz")
+    rng = np.random.default_rng(2026)
+    xml = rt.scenes.scene_c4(d, res=(32, 18), spp=1, n=12, deterministic=True)
+    hs = rt.HostScene(xml)
+    hs.save_blob(os.path.join(d, "s.blob"))
+    hs.close()
+    img = rng.integers(0, 256, size=(21, 33, 3)).astype(np.uint8)
+    Image.fromarray(img).save(os.path.join(d, "a.jpg"), quality=80)
+    Image.fromarray(img).save(os.path.join(d, "p.jpg"), quality=80, progressive=True)
+    Image.fromarray(img).save(os.path.join(d, "a.png"))
+    rt.scenes.write_exr(os.path.join(d, "a.exr"), rng.random((9, 12, 3)).astype(np.float32))
+
+    def mutations(data, n):
+        for it in range(n):
+            b = bytearray(data)
+            if it % 3 == 0:
+                for _ in range(int(rng.integers(1, 6))):
+                    b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+            elif it % 3 == 1:
+                b = b[: int(rng.integers(1, len(b)))]
+            else:
+                i = int(rng.integers(0, len(b)))
+                j = int(rng.integers(i, min(len(b), i + 40)))
+                b[i:j] = bytes(rng.integers(0, 256, size=int(rng.integers(0, 40))).astype(np.uint8))
+            yield bytes(b)
+
+    outcomes = {"loaded": 0, "rejected": 0}
+    for src, ext in (("a.jpg", "jpg"), ("p.jpg", "jpg"), ("a.png", "png"), ("a.exr", "exr")):
+        for m in mutations(open(os.path.join(d, src), "rb").read(), 45):
+            with open(os.path.join(d, "f." + ext), "wb") as f:
+                f.write(m)
+            try:
+                _load_image_texture(rt, d, "f." + ext)
+                outcomes["loaded"] += 1
+            except rt.RtError:
+                outcomes["rejected"] += 1
+    for which, target in (("ply", os.path.join(d, "c4_mesh.ply")), ("xml", xml), ("blob", os.path.join(d, "s.blob"))):
+        orig = open(target, "rb").read()
+        for m in mutations(orig, 45):
+            with open(target, "wb") as f:
+                f.write(m)
+            try:
+                h = rt.HostScene(blob=target, check_sources=False) if which == "blob" else rt.HostScene(xml)
+            except rt.RtError:
+                outcomes["rejected"] += 1
+                continue
+            try:
+                rt.Scene(h.desc, 0).close()        # Validate() first; then RT_ERR_CUDA on a CPU-only box
+            except rt.RtError:
+                pass
+            h.close()
+            outcomes["loaded"] += 1
+        with open(target, "wb") as f:
+            f.write(orig)
+    assert outcomes["loaded"] > 0 and outcomes["rejected"] > 0
