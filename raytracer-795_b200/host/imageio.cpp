@@ -267,21 +267,26 @@ bool SavePpmP3(const std::string& path, const float* rgb, int nx, int ny, std::s
     FILE* o = fopen(path.c_str(), "w");
     if (!o) { *err = "cannot write " + path; return false; }
     fprintf(o, "P3\n%d %d\n255\n", nx, ny);
-    std::string line;
-    char num[16];
-    for (int y = 0; y < ny; y++) {
-        line.clear();
+    // "<value> " per component through a 256-entry table (6.2 M values for a 1080p frame: printf per value was 40 ms of the CLI)
+    char tab[256][4]; unsigned char len[256];
+    for (int v = 0; v < 256; v++) len[v] = (unsigned char)snprintf(tab[v], sizeof tab[v], "%d", v);
+    std::vector<char> line((size_t)nx * 3 * 4 + 1);
+    bool ok = true;
+    for (int y = 0; y < ny && ok; y++) {
+        char* w = line.data();
         for (int i = 0; i < nx * 3; i++) {
             float v = rgb[(size_t)y * nx * 3 + i];
             if (v > 255) v = 255;                      // src/Image.cpp:64-68
             if (!(v >= 0)) v = 0;                      // the reference's (unsigned char) cast of a negative/NaN is UB; clamp
-            snprintf(num, sizeof num, "%d ", (int)(unsigned char)v);
-            line += num;
+            int b = (int)(unsigned char)v;
+            memcpy(w, tab[b], len[b]); w += len[b];
+            *w++ = ' ';
         }
-        line += "\n";
-        fputs(line.c_str(), o);
+        *w++ = '\n';
+        ok = fwrite(line.data(), 1, (size_t)(w - line.data()), o) == (size_t)(w - line.data());
     }
-    fclose(o);
+    if (fclose(o) != 0) ok = false;
+    if (!ok) { *err = "write failed: " + path; return false; }
     return true;
 }
 
