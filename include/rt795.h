@@ -310,6 +310,14 @@ const RtSceneDesc* rt_host_scene_desc(const RtHostScene* hs);
 int rt_host_num_cameras(const RtHostScene* hs);
 const RtCameraDesc* rt_host_camera(const RtHostScene* hs, int i);
 const char* rt_host_camera_image_name(const RtHostScene* hs, int i);
+/* Per-camera extensions beyond src/Parser.h, in the course's XML vocabulary (SURVEY App. B lists them as not parsed by the
+ * reference snapshot): <Renderer>PathTracing</Renderer> + <RendererParams>NextEventEstimation RussianRoulette
+ * ImportanceSampling</RendererParams> select RT_INTEGRATOR_PATH and its options (without <Renderer> the options describe the
+ * reference integrator); <Tonemap><TMO>Photographic</TMO><TMOOptions>key burn%</TMOOptions><Saturation/><Gamma/></Tonemap>
+ * asks for a tone-mapped 8-bit image next to the HDR one (rt_tonemap's parameters). */
+typedef struct RtTonemap { int32_t enabled; float key, burn_percent, saturation, gamma; } RtTonemap;
+int rt_host_camera_render_opts(const RtHostScene* hs, int i, RtRenderOpts* out);
+int rt_host_camera_tonemap(const RtHostScene* hs, int i, RtTonemap* out);
 /* Writers with the reference's file semantics: names containing ".png" get a clamped P3 ASCII PPM
  * (src/Image.cpp:62-103), anything else a half-float B,G,R EXR (src/Helper.cpp:361-412). */
 int rt_host_save_image(const char* image_name, const float* rgb, int nx, int ny);

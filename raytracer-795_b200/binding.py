@@ -94,6 +94,10 @@ class RtRenderOpts(C.Structure):
                 ("queue_capacity", C.c_int32), ("collect_counters", C.c_int32), ("resolve_owned_only", C.c_int32)]
 
 
+class RtTonemap(C.Structure):
+    _fields_ = [("enabled", C.c_int32), ("key", C.c_float), ("burn_percent", C.c_float), ("saturation", C.c_float), ("gamma", C.c_float)]
+
+
 class RtHit(C.Structure):
     _fields_ = [("full", C.c_int32), ("object", C.c_int32), ("primitive", C.c_int32), ("t", C.c_float),
                 ("point", f3), ("normal", f3)]
@@ -118,6 +122,7 @@ HIT_DTYPE = np.dtype([("full", "<i4"), ("object", "<i4"), ("primitive", "<i4"), 
 CORE_SYMBOLS = ["rt_scene_create", "rt_scene_destroy", "rt_render", "rt_render_device", "rt_trace_primary", "rt_tonemap",
                 "rt_get_stats", "rt_debug_read_bvh", "rt_last_error", "rt_abi_version", "rt_device_count", "rt_host_load_scene",
                 "rt_host_save_scene_blob", "rt_host_load_scene_blob", "rt_host_load_scene_cached",
+                "rt_host_camera_render_opts", "rt_host_camera_tonemap",
                 "rt_host_free_scene", "rt_host_scene_desc", "rt_host_num_cameras", "rt_host_camera",
                 "rt_host_camera_image_name", "rt_host_save_image", "rt_host_save_f32"]
 
@@ -162,6 +167,8 @@ def load_core() -> C.CDLL:
         lib.rt_host_num_cameras.argtypes = [C.c_void_p]
         lib.rt_host_camera.argtypes = [C.c_void_p, C.c_int]
         lib.rt_host_camera.restype = P(RtCameraDesc)
+        lib.rt_host_camera_render_opts.argtypes = [C.c_void_p, C.c_int, P(RtRenderOpts)]
+        lib.rt_host_camera_tonemap.argtypes = [C.c_void_p, C.c_int, P(RtTonemap)]
         lib.rt_host_camera_image_name.argtypes = [C.c_void_p, C.c_int]
         lib.rt_host_camera_image_name.restype = C.c_char_p
         lib.rt_host_save_image.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
@@ -235,6 +242,16 @@ class HostScene:
 
     def camera(self, i: int = 0) -> RtCameraDesc:
         return self.lib.rt_host_camera(self.h, i).contents
+
+    def render_opts(self, i: int = 0) -> RtRenderOpts:
+        o = RtRenderOpts()
+        _check(self.lib.rt_host_camera_render_opts(self.h, i, C.byref(o)))
+        return o
+
+    def tonemap(self, i: int = 0) -> "RtTonemap":
+        t = RtTonemap()
+        _check(self.lib.rt_host_camera_tonemap(self.h, i, C.byref(t)))
+        return t
 
     def image_name(self, i: int = 0) -> str:
         return self.lib.rt_host_camera_image_name(self.h, i).decode()

@@ -123,6 +123,8 @@ struct RtHostScene {
     std::vector<RtCameraDesc> cameras;
     std::vector<std::string> image_names;
     std::vector<std::string> deps;        // every file the scene was read from (XML first): the blob cache's staleness check
+    std::vector<RtRenderOpts> cam_opts;   // per camera: <Renderer> / <RendererParams> (extensions for the path tracer)
+    std::vector<RtTonemap> cam_tonemap;   // per camera: <Tonemap> (extension)
 };
 
 namespace {
@@ -244,6 +246,32 @@ private:
             if (!have_plane) return Fail(err, "Camera needs NearPlane or FovY");
             hs_->cameras.push_back(cd);
             hs_->image_names.push_back(nm->GetText());
+            // ---- extensions beyond src/Parser.h (SURVEY App. B "not parsed by this snapshot"), in the course's XML vocabulary:
+            //   <Renderer>PathTracing</Renderer>  <RendererParams>NextEventEstimation RussianRoulette ImportanceSampling</RendererParams>
+            //   <Tonemap><TMO>Photographic</TMO><TMOOptions>key burn%</TMOOptions><Saturation>s</Saturation><Gamma>g</Gamma></Tonemap>
+            RtRenderOpts ro; memset(&ro, 0, sizeof ro);
+            ro.integrator = RT_INTEGRATOR_REFERENCE; ro.seed = 795; ro.pt_nee = 1; ro.pt_russian_roulette = 1; ro.pt_importance = 1;
+            if (auto e = c->FirstChildElement("Renderer")) {
+                const char* t = e->GetText();
+                if (t && StartsWith(t, "PathTracing")) {
+                    ro.integrator = RT_INTEGRATOR_PATH; ro.pt_nee = 0; ro.pt_russian_roulette = 0; ro.pt_importance = 0;   // opted into one by one
+                    if (auto pe = c->FirstChildElement("RendererParams")) {
+                        std::string ps = pe->GetText() ? pe->GetText() : "";
+                        if (ps.find("NextEventEstimation") != std::string::npos) ro.pt_nee = 1;
+                        if (ps.find("RussianRoulette") != std::string::npos) ro.pt_russian_roulette = 1;
+                        if (ps.find("ImportanceSampling") != std::string::npos) ro.pt_importance = 1;
+                    }
+                }
+            }
+            RtTonemap tm; memset(&tm, 0, sizeof tm);
+            if (auto e = c->FirstChildElement("Tonemap")) {
+                tm.enabled = 1; tm.key = 0.18f; tm.burn_percent = 1.0f; tm.saturation = 1.0f; tm.gamma = 2.2f;
+                if (auto o = e->FirstChildElement("TMOOptions")) { const char* t = o->GetText(); if (t) sscanf(t, "%f %f", &tm.key, &tm.burn_percent); }
+                if (auto o = e->FirstChildElement("Saturation")) o->QueryFloatText(&tm.saturation);
+                if (auto o = e->FirstChildElement("Gamma")) o->QueryFloatText(&tm.gamma);
+            }
+            hs_->cam_opts.push_back(ro);
+            hs_->cam_tonemap.push_back(tm);
         }
         if (hs_->cameras.empty()) return Fail(err, "no <Camera>");
         return true;
@@ -708,7 +736,7 @@ private:
 // source file it came from; a changed source makes it stale.
 namespace {
 
-const char kBlobMagic[8] = {'R', 'T', '7', '9', '5', 'S', 'B', '2'};
+const char kBlobMagic[8] = {'R', 'T', '7', '9', '5', 'S', 'B', '3'};
 
 struct BlobWriter {
     FILE* f; bool ok = true;
@@ -728,7 +756,7 @@ struct BlobReader {
 // layout fingerprint: a blob written by a library with different struct layouts must not be read
 uint64_t LayoutStamp() {
     const uint64_t sz[] = {sizeof(RtSceneDesc), sizeof(RtObject), sizeof(RtMaterial), sizeof(RtTexture), sizeof(RtLight), sizeof(RtCameraDesc),
-                           sizeof(RtMesh), sizeof(RtSphere), (uint64_t)RT795_ABI_VERSION};
+                           sizeof(RtMesh), sizeof(RtSphere), sizeof(RtRenderOpts), sizeof(RtTonemap), (uint64_t)RT795_ABI_VERSION};
     uint64_t h = 1469598103934665603ull;
     for (uint64_t v : sz) { h ^= v; h *= 1099511628211ull; }
     return h;
@@ -788,7 +816,7 @@ int rt_host_save_scene_blob(const RtHostScene* hs, const char* blob_path) {
     }
     w.Raw(&hs->desc, sizeof(RtSceneDesc));                               // scalars; the pointer fields are rebound on load
     w.Vec(hs->vertices); w.Vec(hs->normals); w.Vec(hs->texcoords); w.Vec(hs->tris);
-    w.Vec(hs->meshes); w.Vec(hs->spheres); w.Vec(hs->objects); w.Vec(hs->materials); w.Vec(hs->textures); w.Vec(hs->lights); w.Vec(hs->cameras);
+    w.Vec(hs->meshes); w.Vec(hs->spheres); w.Vec(hs->objects); w.Vec(hs->materials); w.Vec(hs->textures); w.Vec(hs->lights); w.Vec(hs->cameras); w.Vec(hs->cam_opts); w.Vec(hs->cam_tonemap);
     w.U64(hs->image_names.size());
     for (const std::string& n : hs->image_names) w.Str(n);
     w.U64(hs->image_store.size());
@@ -829,7 +857,7 @@ int rt_host_load_scene_blob(const char* blob_path, int check_sources, RtHostScen
     }
     r.Raw(&hs->desc, sizeof(RtSceneDesc));
     r.Vec(&hs->vertices); r.Vec(&hs->normals); r.Vec(&hs->texcoords); r.Vec(&hs->tris);
-    r.Vec(&hs->meshes); r.Vec(&hs->spheres); r.Vec(&hs->objects); r.Vec(&hs->materials); r.Vec(&hs->textures); r.Vec(&hs->lights); r.Vec(&hs->cameras);
+    r.Vec(&hs->meshes); r.Vec(&hs->spheres); r.Vec(&hs->objects); r.Vec(&hs->materials); r.Vec(&hs->textures); r.Vec(&hs->lights); r.Vec(&hs->cameras); r.Vec(&hs->cam_opts); r.Vec(&hs->cam_tonemap);
     uint64_t nn = r.U64();
     if (!r.ok || nn > 1u << 20) return fail("corrupt body");
     hs->image_names.resize(nn);
@@ -846,7 +874,7 @@ int rt_host_load_scene_blob(const char* blob_path, int check_sources, RtHostScen
     r.Raw(magic, 8);
     if (!r.ok || memcmp(magic, kBlobMagic, 8) != 0) return fail("truncated");
     fclose(f);
-    if (hs->cameras.size() != hs->image_names.size() || hs->vertices.size() % 3 || hs->tris.size() % 3 || hs->texcoords.size() % 2 ||
+    if (hs->cameras.size() != hs->image_names.size() || hs->cam_opts.size() != hs->cameras.size() || hs->cam_tonemap.size() != hs->cameras.size() || hs->vertices.size() % 3 || hs->tris.size() % 3 || hs->texcoords.size() % 2 ||
         (!hs->normals.empty() && hs->normals.size() != hs->vertices.size())) { delete hs; SetLastError(std::string("rt_host_load_scene_blob: ") + blob_path + ": inconsistent arrays"); return RT_ERR_PARSE; }
     hs->desc.abi_version = RT795_ABI_VERSION;
     BindDesc(hs);                                                         // rt_scene_create validates every index range again
@@ -876,6 +904,16 @@ int rt_host_load_scene_cached(const char* xml_path, const char* blob_path, RtHos
 const RtSceneDesc* rt_host_scene_desc(const RtHostScene* hs) { return hs ? &hs->desc : nullptr; }
 int rt_host_num_cameras(const RtHostScene* hs) { return hs ? (int)hs->cameras.size() : 0; }
 const RtCameraDesc* rt_host_camera(const RtHostScene* hs, int i) { return (hs && i >= 0 && i < (int)hs->cameras.size()) ? &hs->cameras[i] : nullptr; }
+int rt_host_camera_render_opts(const RtHostScene* hs, int i, RtRenderOpts* out) {
+    if (!hs || !out || i < 0 || i >= (int)hs->cam_opts.size()) { SetLastError("rt_host_camera_render_opts: bad argument"); return RT_ERR_INVALID; }
+    *out = hs->cam_opts[i];
+    return RT_OK;
+}
+int rt_host_camera_tonemap(const RtHostScene* hs, int i, RtTonemap* out) {
+    if (!hs || !out || i < 0 || i >= (int)hs->cam_tonemap.size()) { SetLastError("rt_host_camera_tonemap: bad argument"); return RT_ERR_INVALID; }
+    *out = hs->cam_tonemap[i];
+    return RT_OK;
+}
 const char* rt_host_camera_image_name(const RtHostScene* hs, int i) { return (hs && i >= 0 && i < (int)hs->image_names.size()) ? hs->image_names[i].c_str() : nullptr; }
 
 int rt_host_save_image(const char* image_name, const float* rgb, int nx, int ny) {

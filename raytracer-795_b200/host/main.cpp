@@ -1,6 +1,7 @@
 // CLI with the reference's contract (src/main.cpp:7-14): `raytracer scene.xml` renders every camera of the scene
 // and writes each camera's <ImageName> (P3 PPM for "*.png*" names, half-float EXR otherwise, src/Image.cpp:26-34).
 // Extra, optional knobs after the scene path:  --f32 (also dump <ImageName>.f32 raw floats)  --device N
+// A camera's <Renderer>/<RendererParams>/<Tonemap> elements (extensions) are honoured unless --integrator / --tonemap override them.
 // --cache (keep / reuse <scene.xml>.rt795blob, the prepared scene, while its sources are unchanged)
 // --integrator path|reference  --bvh auto|host|ploc|sah (per-mesh BVH builder)  --seed S  --tonemap KEY BURN SAT GAMMA (writes <ImageName>.tm.ppm)
 #include "../../include/rt795.h"
@@ -13,7 +14,7 @@
 
 int main(int argc, char* argv[]) {
     if (argc < 2) { fprintf(stderr, "usage: %s scene.xml [--f32] [--cache] [--device N] [--integrator path|reference] [--bvh auto|host|ploc|sah] [--seed S] [--tonemap key burn sat gamma]\n", argv[0]); return 2; }
-    bool f32 = false, tonemap = false, cache = false;
+    bool f32 = false, tonemap = false, cache = false, cli_integrator = false, cli_seed = false;
     int device = 0, bvh = RT_BVH_AUTO;
     float tm[4] = {0.18f, 1.0f, 1.0f, 2.2f};
     RtRenderOpts opts;
@@ -23,8 +24,8 @@ int main(int argc, char* argv[]) {
         if (!strcmp(argv[i], "--f32")) f32 = true;
         else if (!strcmp(argv[i], "--cache")) cache = true;
         else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
-        else if (!strcmp(argv[i], "--seed") && i + 1 < argc) opts.seed = strtoull(argv[++i], nullptr, 10);
-        else if (!strcmp(argv[i], "--integrator") && i + 1 < argc) opts.integrator = !strcmp(argv[++i], "path") ? RT_INTEGRATOR_PATH : RT_INTEGRATOR_REFERENCE;
+        else if (!strcmp(argv[i], "--seed") && i + 1 < argc) { opts.seed = strtoull(argv[++i], nullptr, 10); cli_seed = true; }
+        else if (!strcmp(argv[i], "--integrator") && i + 1 < argc) { opts.integrator = !strcmp(argv[++i], "path") ? RT_INTEGRATOR_PATH : RT_INTEGRATOR_REFERENCE; cli_integrator = true; }
         else if (!strcmp(argv[i], "--bvh") && i + 1 < argc) { const char* b = argv[++i]; bvh = !strcmp(b, "host") ? RT_BVH_HOST_SAH : !strcmp(b, "device") || !strcmp(b, "ploc") ? RT_BVH_DEVICE_PLOC : !strcmp(b, "sah") ? RT_BVH_DEVICE_SAH : RT_BVH_AUTO; }
         else if (!strcmp(argv[i], "--tonemap") && i + 4 < argc) { tonemap = true; for (int k = 0; k < 4; k++) tm[k] = (float)atof(argv[++i]); }
         else { fprintf(stderr, "unknown option %s\n", argv[i]); return 2; }
@@ -57,8 +58,14 @@ int main(int argc, char* argv[]) {
     for (int c = 0; c < rt_host_num_cameras(hs); c++) {
         const RtCameraDesc* cam = rt_host_camera(hs, c);
         std::vector<float> img((size_t)cam->nx * cam->ny * 3);
+        // the camera's own <Renderer> / <RendererParams> (extension elements) unless the command line says otherwise
+        RtRenderOpts co = opts;
+        if (!cli_integrator) {
+            RtRenderOpts xo;
+            if (rt_host_camera_render_opts(hs, c, &xo) == RT_OK) { uint64_t seed = cli_seed ? opts.seed : xo.seed; co = xo; co.seed = seed; }
+        }
         auto r0 = now();
-        if (rt_render(sc, cam, &opts, img.data()) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }
+        if (rt_render(sc, cam, &co, img.data()) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }
         auto r1 = now();
         RtStats st;
         rt_get_stats(sc, &st);
@@ -73,6 +80,18 @@ int main(int argc, char* argv[]) {
             std::string p = std::string(name) + ".tm.ppm";
             FILE* f = fopen(p.c_str(), "wb");
             if (f) { fprintf(f, "P6\n%d %d\n255\n", cam->nx, cam->ny); fwrite(ldr.data(), 1, ldr.size(), f); fclose(f); }
+        }
+        RtTonemap xt;
+        if (!tonemap && rt_host_camera_tonemap(hs, c, &xt) == RT_OK && xt.enabled) {
+            // <Tonemap> in the camera: the tone-mapped 8-bit frame goes next to the HDR one, "x.exr" -> "x.png" (written with the
+            // reference's ".png" semantics, i.e. a P3 PPM, src/Image.cpp:62-103)
+            std::vector<uint8_t> ldr((size_t)cam->nx * cam->ny * 3);
+            if (rt_tonemap(sc, img.data(), cam->nx, cam->ny, xt.key, xt.burn_percent, xt.saturation, xt.gamma, ldr.data()) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }
+            std::string p = name;
+            size_t dot = p.rfind(".exr");
+            p = dot != std::string::npos ? p.substr(0, dot) + ".png" : p + ".tm.png";
+            std::vector<float> lf(ldr.begin(), ldr.end());
+            if (rt_host_save_image(p.c_str(), lf.data(), cam->nx, cam->ny) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }
         }
         auto w0 = now();
         if (rt_host_save_image(name, img.data(), cam->nx, cam->ny) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }

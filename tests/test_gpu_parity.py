@@ -428,3 +428,22 @@ def test_cli_writes_the_reference_file_formats(rt, scene_dir, tmp_path):
     r2 = subprocess.run([exe, os.path.join(str(tmp_path), "nope.xml")], cwd=tmp_path, capture_output=True, text=True)
     assert r2.returncode == 1 and "cannot open" in r2.stderr
     hs.close()
+    # camera extensions: <Renderer>PathTracing ...</Renderer> picks the path tracer, <Tonemap> writes "x.png" next to "x.exr"
+    ext = ("<ImageName>c1ext.exr</ImageName><Renderer>PathTracing</Renderer><RendererParams>NextEventEstimation RussianRoulette ImportanceSampling</RendererParams>"
+           "<NumSamples>16</NumSamples><Tonemap><TMO>Photographic</TMO><TMOOptions>0.18 1</TMOOptions><Saturation>1.0</Saturation><Gamma>2.2</Gamma></Tonemap>")
+    xml2 = os.path.join(os.path.dirname(xml), "c1ext.xml")
+    open(xml2, "w").write(txt.replace("<ImageName>c1cli.png</ImageName>", ext))
+    r3 = subprocess.run([exe, xml2, "--f32"], cwd=tmp_path, capture_output=True, text=True)
+    assert r3.returncode == 0, r3.stderr
+    assert os.path.getsize(os.path.join(tmp_path, "c1ext.exr")) > 1000
+    toks = open(os.path.join(tmp_path, "c1ext.png")).read().split()
+    assert toks[:4] == ["P3", "96", "96", "255"]
+    ldr = np.array(toks[4:], dtype=np.int64).reshape(96, 96, 3)
+    hs2 = rt.HostScene(xml2)
+    sc2 = rt.Scene(hs2.desc, 0)
+    img = sc2.render(hs2.camera(0), hs2.render_opts(0))                  # same options, same seed: the CLI's HDR frame
+    assert np.allclose(rt.read_f32(os.path.join(tmp_path, "c1ext.exr.f32")), img, rtol=1e-4, atol=1e-4)
+    t = hs2.tonemap(0)
+    want = sc2.tonemap(img, key=t.key, burn=t.burn_percent, saturation=t.saturation, gamma=t.gamma).astype(np.int64)
+    assert (np.abs(ldr - want) <= 1).mean() >= 0.999
+    sc2.close(); hs2.close()

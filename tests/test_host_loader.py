@@ -451,3 +451,28 @@ def test_mutated_inputs_never_crash(rt, tmp_path):
         with open(target, "wb") as f:
             f.write(orig)
     assert outcomes["loaded"] > 0 and outcomes["rejected"] > 0
+
+
+def test_camera_renderer_and_tonemap_extensions(rt, tmp_path):
+    """<Renderer> / <RendererParams> / <Tonemap> in a camera (course vocabulary; not parsed by the reference snapshot, SURVEY
+    App. B) -> rt_host_camera_render_opts / rt_host_camera_tonemap, and they survive the scene blob."""
+    d = str(tmp_path / "ext")
+    extra = ("<Renderer>PathTracing</Renderer><RendererParams>NextEventEstimation ImportanceSampling</RendererParams>"
+             "<Tonemap><TMO>Photographic</TMO><TMOOptions>0.25 2.5</TMOOptions><Saturation>0.8</Saturation><Gamma>2.4</Gamma></Tonemap>")
+    xml = write_scene(d, camextra=extra)
+    hs = rt.HostScene(xml)
+    o, t = hs.render_opts(0), hs.tonemap(0)
+    assert o.integrator == rt.RT_INTEGRATOR_PATH and (o.pt_nee, o.pt_russian_roulette, o.pt_importance) == (1, 0, 1) and o.seed == 795
+    assert t.enabled == 1 and (t.key, t.burn_percent, t.saturation, t.gamma) == pytest.approx((0.25, 2.5, 0.8, 2.4))
+    blob = os.path.join(d, "s.blob")
+    hs.save_blob(blob)
+    hb = rt.HostScene(blob=blob)
+    assert bytes(hb.render_opts(0)) == bytes(o) and bytes(hb.tonemap(0)) == bytes(t)
+    with pytest.raises(rt.RtError):
+        hs.render_opts(3)
+    hb.close(); hs.close()
+    # a plain reference scene: the reference integrator, no tone map
+    hs = rt.HostScene(write_scene(str(tmp_path / "plain")))
+    o, t = hs.render_opts(0), hs.tonemap(0)
+    assert o.integrator == rt.RT_INTEGRATOR_REFERENCE and t.enabled == 0
+    hs.close()
