@@ -33,13 +33,26 @@ import __graft_entry__ as ge  # noqa: E402
 B_RAY = {"c1": 224, "c2": 400, "c3": 784, "c4": 1040, "c5": 416}
 
 WORKLOADS = {
-    # name: (generator kwargs for the full configuration, kwargs for the bounded CPU sample)
-    "c4": (dict(res=(1920, 1080), spp=64, n=660), dict(res=(480, 270), spp=4, n=660)),
-    "c3": (dict(res=(1920, 1080), spp=16, n=187), dict(res=(480, 270), spp=4, n=187)),
-    "c2": (dict(res=1024, spp=100), dict(res=128, spp=16)),
+    # name: (generator kwargs for the full configuration, kwargs for the bounded CPU sample).  The CPU sample keeps the full
+    # RESOLUTION (same pixel footprint, same ray distribution over the scene) and cuts only the samples per pixel.
+    "c4": (dict(res=(1920, 1080), spp=64, n=660), dict(res=(1920, 1080), spp=2, n=660)),
+    "c3": (dict(res=(1920, 1080), spp=16, n=187), dict(res=(1920, 1080), spp=2, n=187)),
+    "c2": (dict(res=1024, spp=100), dict(res=1024, spp=2)),
     "c1": (dict(res=800), dict(res=800)),
-    "c5": (dict(res=(3840, 2160), spp=1024), dict(res=(240, 135), spp=4)),
+    "c5": (dict(res=(3840, 2160), spp=1024), dict(res=(480, 270), spp=4)),   # the reference has no path tracer: direct lighting only, not like-for-like
 }
+SMOKE_WORKLOADS = {"c4": dict(res=(480, 270), spp=4, n=660), "c3": dict(res=(480, 270), spp=4, n=187), "c2": dict(res=128, spp=16), "c1": dict(res=200),
+                   "c5": dict(res=(240, 135), spp=4)}
+
+
+def load_scenes():
+    """The synthetic scene generators (raytracer-795_b200/scenes.py, numpy only) WITHOUT importing the product package: the
+    reference arm must not load librt795.so or anything around it."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("rt795_scenes", os.path.join(ROOT, "raytracer-795_b200", "scenes.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def scene_cache_dir() -> str:
@@ -49,10 +62,12 @@ def scene_cache_dir() -> str:
 
 
 def make_scene(rt, config: str, kw: dict, tag: str) -> str:
+    """`rt` is the product package or the bare scenes module (load_scenes())."""
+    scenes = getattr(rt, "scenes", rt)
     d = os.path.join(scene_cache_dir(), f"{config}_{tag}")
     xml = os.path.join(d, f"{config}.xml")
     if not os.path.exists(xml):
-        rt.scenes.CONFIGS[config]["gen"](d, **kw)
+        scenes.CONFIGS[config]["gen"](d, **kw)
     return xml
 
 
@@ -124,59 +139,66 @@ def ncu_traffic(config: str, kernel: str):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def ref_binary() -> str | None:
-    p = os.path.join(ROOT, "oracle", "_ref", "ref_raytracer")
+def ref_bench_binary() -> str | None:
+    p = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
     return p if os.path.exists(p) else None
 
 
-def count_reference_rays(rt, xml: str) -> int:
-    """Closest-hit queries the reference algorithm issues for this scene (counted by the instrumented oracle port;
-    the reference itself cannot count).  CPU only."""
-    hs = rt.HostScene(xml)
-    lib = rt.load_oracle()
-    lib.oracle_ray_queries(1)
-    rt.oracle_render(hs.desc, hs.camera(0), threads=os.cpu_count() or 1)
-    n = int(lib.oracle_ray_queries(1))
-    hs.close()
-    return n
+def run_reference_frames(xml: str, frames: int) -> tuple[list[float], list[int], str, int]:
+    """`frames` renders of camera 0 by the reference's own CPU implementation on the host cores.  Returns (render-only seconds
+    per frame, closest-hit queries per frame, kind, cores).
 
-
-def time_reference_once(rt, xml: str) -> tuple[float, str, int]:
-    """Render-only seconds of one frame on the host cores.  Returns (seconds, kind, cores)."""
-    exe = ref_binary()
+    kind "reference": oracle/_ref/ref_bench = the UNMODIFIED reference sources (compiled by oracle/Makefile against stand-in
+    headers) driven by oracle/harness/bench_main.cpp: scene parsed and BVHs built once, then each frame is the reference's own
+    8 hard-coded std::threads on Scene::ThreadedRendering (src/Scene.cpp:269-292, 340-356).  Rays are counted INSIDE that binary
+    by a link-time wrapper around BVHMethods::FindIntersection (oracle/harness/count_wrap.cpp).  No product code is loaded.
+    kind "port": oracle/_ref absent -> the oracle port (oracle/restate.cpp) with all host threads."""
+    exe = ref_bench_binary()
     if exe:
         with tempfile.TemporaryDirectory() as td:
-            r = subprocess.run([exe, xml], cwd=td, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, check=True)
-        m = re.search(r"RT795_RENDER_SECONDS ([0-9.eE+-]+)", r.stderr)
-        return float(m.group(1)), "reference", 8          # 8 hard-coded std::threads, src/Scene.cpp:272, 340-347
+            r = subprocess.run([exe, xml, str(frames)], cwd=td, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, check=True)
+        recs = re.findall(r"RT795_FRAME \d+ seconds ([0-9.eE+-]+) queries (\d+)", r.stdout)
+        assert len(recs) == frames, r.stdout[-2000:]
+        return [float(a) for a, _ in recs], [int(b) for _, b in recs], "reference", 8
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_api as orc
+    rt = ge.load_package()
     hs = rt.HostScene(xml)
     cores = os.cpu_count() or 1
-    t0 = time.perf_counter()
-    rt.oracle_render(hs.desc, hs.camera(0), threads=cores)
-    dt = time.perf_counter() - t0
+    lib = orc.load_oracle()
+    secs, qs = [], []
+    for _ in range(frames):
+        lib.oracle_ray_queries(1)
+        t0 = time.perf_counter()
+        orc.oracle_render(hs.desc, hs.camera(0), threads=cores)
+        secs.append(time.perf_counter() - t0)
+        qs.append(int(lib.oracle_ray_queries(1)))
     hs.close()
-    return dt, "port", cores
+    return secs, qs, "port", cores
 
 
-def run_reference_arm(args, rt):
+def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    scenes = load_scenes()
     full_kw, sample_kw = WORKLOADS[args.config]
-    xml = make_scene(rt, args.config, sample_kw, "sample")
-    rays = count_reference_rays(rt, xml)
-    for _ in range(args.warmup):
-        time_reference_once(rt, xml)
-    secs, kind, cores = [], "reference", 8
-    for _ in range(args.steps):
-        s, kind, cores = time_reference_once(rt, xml)
-        secs.append(s)
+    if args.small:
+        sample_kw = SMOKE_WORKLOADS[args.config]
+    xml = make_scene(scenes, args.config, sample_kw, "refsample_small" if args.small else "refsample")
+    secs, qs, kind, cores = run_reference_frames(xml, args.warmup + args.steps)
+    secs, qs = secs[args.warmup:], qs[args.warmup:]
     ms = 1e3 * float(np.mean(secs))
+    rays = float(np.mean(qs))
     val = rays / (ms * 1e-3) / 1e6
-    sample = f"{args.config} scene at {sample_kw} (full: {full_kw}); rays = closest-hit queries counted by the oracle port"
+    label = scenes.CONFIGS[args.config]["label"]
+    sample = (f"{args.config} scene, one frame per step at {sample_kw} (full workload: {full_kw}); rays = BVHMethods::FindIntersection calls counted "
+              f"inside the {'unmodified reference binary (link-time wrapper)' if kind == 'reference' else 'oracle port'}; parse + BVH build outside the timed region")
+    res = sample_kw["res"] if isinstance(sample_kw["res"], (tuple, list)) else (sample_kw["res"], sample_kw["res"])
     line = {"impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": rt.scenes.CONFIGS[args.config]["label"], "sample": sample, "rays_per_step": rays},
+            "config": {"workload": label, "resolution": [int(res[0]), int(res[1])], "spp": int(sample_kw.get("spp", 1)), "rays_per_frame": rays,
+                       "integrator": "reference", "sample": sample},
             "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -223,7 +245,7 @@ def run_ours(args, rt):
 
     full_kw, sample_kw = WORKLOADS[args.config]
     if args.small:
-        full_kw = sample_kw
+        full_kw = sample_kw = SMOKE_WORKLOADS[args.config]
     tag = "small" if args.small else "full"
     if args.spp > 0 and "spp" in full_kw:
         full_kw = dict(full_kw, spp=args.spp)
@@ -377,11 +399,11 @@ def run_ours(args, rt):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sxml = make_scene(rt, args.config, sample_kw, "sample")
-        secs, kind, cores = time_reference_once(rt, sxml)
-        rrays = count_reference_rays(rt, sxml)
+        sxml = make_scene(rt, args.config, sample_kw, "refsample_small" if args.small else "refsample")
+        (secs,), (rrays,), kind, cores = run_reference_frames(sxml, 1)
         cpu_baseline = {"value": rrays / secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind, "seconds": secs,
-                        "sample": f"{args.config} scene at {sample_kw}: {rrays} closest-hit queries (counted by the oracle port) in {secs:.2f} s render-only"}
+                        "sample": f"{args.config} scene at {sample_kw}: {rrays} closest-hit queries (BVHMethods::FindIntersection calls counted inside the "
+                                  f"{'unmodified reference binary' if kind == 'reference' else 'oracle port'}) in {secs:.2f} s render-only"}
 
     if rank == 0:
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -414,11 +436,10 @@ def main():
     ap.add_argument("--bvh", default="auto", choices=["host", "ploc", "sah", "auto"], help="per-mesh BVH builder (RtSceneDesc.bvh_builder)")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel of the workload (exploration; the headline run uses the configuration's own)")
     args = ap.parse_args()
-    rt = ge.load_package()
     if args.impl == "reference":
-        run_reference_arm(args, rt)
+        run_reference_arm(args)                                   # never imports the product package
     else:
-        run_ours(args, rt)
+        run_ours(args, ge.load_package())
 
 
 if __name__ == "__main__":

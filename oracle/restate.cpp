@@ -1011,6 +1011,49 @@ int oracle_trace_primary(const RtSceneDesc* s, const RtCameraDesc* cam, int thre
     return 0;
 }
 
+// Photographic tone map: CPU statement of DESIGN.md §7 "Tone map" in double precision.  NO reference code exists
+// (pages/Page5.md:47-53 names a "global tonemapping operator", :101 and pages/Page7.md:35 say the author's own was
+// buggy and never shipped): this restates the Reinhard et al. 2002 global operator with the course's TMOOptions
+// (key, burn %), Saturation and Gamma - parity unpinned by the reference, pinned against this independent statement.
+//   Lbar = exp(mean log(1e-5 + L)), Ls = key L / Lbar, L_white = centre of the 4096-bin histogram cell (over
+//   [0, max Ls]) in which the cumulative pixel count first reaches (100 - burn)% (burn <= 0: max Ls),
+//   Ld = Ls (1 + Ls / L_white^2) / (1 + Ls), c' = (c / L)^saturation Ld, out = round(255 clamp(c')^(1/gamma)).
+int oracle_tonemap(const float* rgb, int nx, int ny, float key, float burn_percent, float saturation, float gamma, unsigned char* out_rgb8) {
+    const int bins = 4096;
+    const size_t npix = (size_t)nx * ny;
+    auto lum = [&](size_t i) { double L = 0.2126 * (double)rgb[3 * i] + 0.7152 * (double)rgb[3 * i + 1] + 0.0722 * (double)rgb[3 * i + 2]; return L >= 0.0 ? L : 0.0; };
+    double sum = 0.0, mx = 0.0;
+    for (size_t i = 0; i < npix; i++) { double L = lum(i); sum += std::log(1e-5 + L); mx = std::max(mx, L); }
+    double lbar = std::exp(sum / (double)npix);
+    double scale = (double)key / std::max(lbar, 1e-20);
+    double max_scaled = std::max(mx * scale, 1e-20);
+    double lwhite = max_scaled;
+    if (burn_percent > 0.f) {
+        std::vector<unsigned long long> hist(bins, 0);
+        for (size_t i = 0; i < npix; i++) {
+            int b = (int)(lum(i) * scale / max_scaled * (bins - 1));
+            hist[std::min(bins - 1, std::max(0, b))]++;
+        }
+        unsigned long long target = (unsigned long long)((double)npix * (100.0 - (double)burn_percent) / 100.0), acc = 0;
+        int b = 0;
+        for (; b < bins; b++) { acc += hist[b]; if (acc >= target) break; }
+        lwhite = std::max(1e-20, (b + 0.5) / (bins - 1) * max_scaled);
+    }
+    double inv_gamma = 1.0 / std::max((double)gamma, 1e-6);
+    for (size_t i = 0; i < npix; i++) {
+        double L = 0.2126 * (double)rgb[3 * i] + 0.7152 * (double)rgb[3 * i + 1] + 0.0722 * (double)rgb[3 * i + 2];
+        if (!(L > 0.0)) { out_rgb8[3 * i] = out_rgb8[3 * i + 1] = out_rgb8[3 * i + 2] = 0; continue; }
+        double Ls = L * scale;
+        double Ld = Ls * (1.0 + Ls / (lwhite * lwhite)) / (1.0 + Ls);
+        for (int k = 0; k < 3; k++) {
+            double v = std::pow(std::max((double)rgb[3 * i + k], 0.0) / L, (double)saturation) * Ld;
+            v = std::min(1.0, std::max(0.0, v));
+            out_rgb8[3 * i + k] = (unsigned char)(255.0 * std::pow(v, inv_gamma) + 0.5);
+        }
+    }
+    return 0;
+}
+
 // Number of closest-hit queries issued since the last reset, to within 1024 per thread (used to express the
 // reference arm's throughput in rays/s: the reference itself cannot count).
 unsigned long long oracle_ray_queries(int reset) { unsigned long long v = g_ray_queries.load(); if (reset) g_ray_queries.store(0); return v; }

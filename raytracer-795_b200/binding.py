@@ -1,4 +1,4 @@
-"""ctypes binding of include/rt795.h (the C ABI) plus the oracle's entry points.
+"""ctypes binding of include/rt795.h (the C ABI).
 
 This is the thin test/bench driver over the shared library; the product is the C ABI itself.  Struct layouts
 here must match include/rt795.h field for field (tests/test_abi.py checks sizes against the compiled library).
@@ -15,8 +15,6 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CORE_SO = os.path.join(HERE, "lib", "librt795.so")
-ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle795.so")
-ORACLE_REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 RT_OK = 0
 (RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_OOM, RT_ERR_IO, RT_ERR_PARSE, RT_ERR_OVERFLOW) = (-1, -2, -3, -4, -5, -6)
@@ -134,7 +132,6 @@ class RtError(RuntimeError):
 
 
 _core = None
-_oracle = None
 
 
 def load_core() -> C.CDLL:
@@ -175,27 +172,6 @@ def load_core() -> C.CDLL:
         lib.rt_host_save_f32.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
         _core = lib
     return _core
-
-
-def load_oracle() -> C.CDLL:
-    """TEST INFRASTRUCTURE: the CPU restatement (oracle/restate.cpp).  Never used by the product path."""
-    global _oracle
-    if _oracle is None:
-        if not os.path.exists(ORACLE_SO):
-            raise RuntimeError(f"{ORACLE_SO} is missing: run `make -C oracle restate`")
-        lib = C.CDLL(ORACLE_SO)
-        P = C.POINTER
-        lib.oracle_render.argtypes = [P(RtSceneDesc), P(RtCameraDesc), P(RtRenderOpts), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
-        lib.oracle_trace_primary.argtypes = [P(RtSceneDesc), P(RtCameraDesc), C.c_int, C.c_void_p]
-        lib.oracle_ray_queries.argtypes = [C.c_int]
-        lib.oracle_ray_queries.restype = C.c_uint64
-        lib.oracle_perlin.argtypes = [C.c_float] * 4 + [C.c_int]
-        lib.oracle_perlin.restype = C.c_float
-        lib.oracle_philox.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
-        lib.oracle_conductor_fresnel.argtypes = [C.c_float] * 3
-        lib.oracle_conductor_fresnel.restype = C.c_float
-        _oracle = lib
-    return _oracle
 
 
 def _check(code: int) -> None:
@@ -332,32 +308,8 @@ class Scene:
             pass
 
 
-# ------------------------------------------------------------------------------------------- oracle helpers (tests / bench only)
-def oracle_render(desc, cam: RtCameraDesc, opts: Optional[RtRenderOpts] = None, rows=(0, 0), cols=(0, 0), threads: int = 8) -> np.ndarray:
-    lib = load_oracle()
-    opts = opts or default_opts()
-    out = np.zeros((cam.ny, cam.nx, 3), dtype=np.float32)
-    lib.oracle_render(desc, C.byref(cam), C.byref(opts), rows[0], rows[1], cols[0], cols[1], threads, out.ctypes.data)
-    return out
-
-
-def oracle_trace_primary(desc, cam: RtCameraDesc, threads: int = 8) -> np.ndarray:
-    lib = load_oracle()
-    out = np.zeros((cam.ny, cam.nx), dtype=HIT_DTYPE)
-    lib.oracle_trace_primary(desc, C.byref(cam), threads, out.ctypes.data)
-    return out
-
-
 def read_f32(path: str) -> np.ndarray:
+    """Reads a raw float32 frame written by rt_host_save_f32 (int32 nx, ny, then ny*nx*3 floats)."""
     raw = np.fromfile(path, dtype=np.uint8)
     nx, ny = np.frombuffer(raw[:8], dtype="<i4")
     return np.frombuffer(raw[8:], dtype="<f4").reshape(ny, nx, 3).copy()
-
-
-REF_HIT_DTYPE = np.dtype([("full", "<i4"), ("label", "<i4"), ("t", "<f4"), ("point", "<f4", (3,)), ("normal", "<f4", (3,))])
-
-
-def read_ref_hits(path: str) -> np.ndarray:
-    raw = np.fromfile(path, dtype=np.uint8)
-    nx, ny = np.frombuffer(raw[:8], dtype="<i4")
-    return np.frombuffer(raw[8:], dtype=REF_HIT_DTYPE).reshape(ny, nx).copy()

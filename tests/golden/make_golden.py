@@ -20,6 +20,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_api as orc  # noqa: E402
 
 CASES = {
     # name: (generator, kwargs)
@@ -40,7 +42,7 @@ def main():
             subprocess.run([os.path.join(ref, "ref_hits"), xml, os.path.join(td, "hits.bin")], cwd=td, check=True, stdout=subprocess.DEVNULL)
             f32 = [f for f in os.listdir(td) if f.endswith(".f32")][0]
             img = rt.read_f32(os.path.join(td, f32))
-            hits = rt.read_ref_hits(os.path.join(td, "hits.bin"))
+            hits = orc.read_ref_hits(os.path.join(td, "hits.bin"))
         np.savez_compressed(os.path.join(HERE, name + ".npz"), radiance=img, hit_full=hits["full"].astype(np.int8), hit_label=hits["label"],
                             hit_t=hits["t"], hit_point=hits["point"], hit_normal=hits["normal"])
         print(name, img.shape, "hit fraction", hits["full"].mean(), os.path.getsize(os.path.join(HERE, name + ".npz")), "bytes")

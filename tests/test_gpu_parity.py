@@ -5,6 +5,8 @@ import subprocess
 import numpy as np
 import pytest
 
+import oracle_api as orc
+
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -34,7 +36,7 @@ def test_c1_primary_hits_vs_oracle(c1):
     rt, xml, hs, sc = c1
     cam = hs.camera(0)
     g = sc.trace_primary(cam)
-    o = rt.oracle_trace_primary(hs.desc, cam)
+    o = orc.oracle_trace_primary(hs.desc, cam)
     same = hit_agreement(g, o)
     assert same.mean() >= 0.999, same.mean()
     both = same & (g["full"] == 1)
@@ -44,19 +46,45 @@ def test_c1_primary_hits_vs_oracle(c1):
     assert np.quantile(dn, 0.999) <= 1e-3
 
 
+def discontinuity_mask(ref, rel=0.02):
+    """Pixels of the REFERENCE image next to a radiance discontinuity (object silhouette, shadow edge, or either of them seen
+    through a mirror chain): some 8-neighbour differs by more than `rel` of the local value.  A pixel there can land on the other
+    side of the edge with a last-ulp difference in a hit point, so its value is compared statistically (count), not pointwise."""
+    pad = np.pad(ref, ((1, 1), (1, 1), (0, 0)), mode="edge")
+    h, w, _ = ref.shape
+    edge = np.zeros((h, w), dtype=bool)
+    for dy in (0, 1, 2):
+        for dx in (0, 1, 2):
+            nb = pad[dy:dy + h, dx:dx + w]
+            edge |= (np.abs(nb - ref) / np.maximum(np.abs(ref), 1.0)).max(axis=-1) > rel
+    return edge
+
+
+def assert_pointwise(img, ref, same, label, max_tol=1e-2, mean_tol=1e-3, outlier_budget=2.5e-4):
+    """north_star tolerance: mean rel err <= 1e-3 and MAX <= 1e-2 per pixel.  The max is asserted over every pixel whose primary hit
+    agrees and which is not on a radiance discontinuity of the reference image; pixels ON a discontinuity that exceed the tolerance
+    are counted, printed and bounded by an explicit budget (fraction of the frame)."""
+    r = rel_err(img, ref).max(axis=-1)
+    edge = discontinuity_mask(ref)
+    smooth = same & ~edge
+    out_edge = int((r[same & edge] > max_tol).sum())
+    print(f"[{label}] pixels {r.size}, primary-hit agreement {same.mean():.6f}, on a discontinuity {int(edge.sum())}, "
+          f"max rel err off discontinuities {r[smooth].max():.3e}, mean {r[same].mean():.3e}, discontinuity pixels above {max_tol:g}: {out_edge}")
+    assert r[same].mean() <= mean_tol, r[same].mean()
+    assert r[smooth].max() <= max_tol, (r[smooth].max(), np.argwhere(smooth & (r > max_tol))[:8])
+    assert out_edge <= outlier_budget * r.size, (out_edge, r.size)
+
+
 def test_c1_radiance_vs_oracle(c1):
     """C1 is deterministic (1 spp, point light): mean rel err <= 1e-3, max <= 1e-2 on pixels whose primary hit agrees."""
     rt, xml, hs, sc = c1
     cam = hs.camera(0)
     img = sc.render(cam)
-    ref = rt.oracle_render(hs.desc, cam)
+    ref = orc.oracle_render(hs.desc, cam)
     g = sc.trace_primary(cam)
-    o = rt.oracle_trace_primary(hs.desc, cam)
+    o = orc.oracle_trace_primary(hs.desc, cam)
     same = hit_agreement(g, o)
-    r = rel_err(img, ref).max(axis=-1)
-    assert r[same].mean() <= 1e-3, r[same].mean()
-    # discontinuities (shadow edges / silhouettes seen in mirrors) may flip on a few pixels
-    assert np.quantile(r[same], 0.999) <= 1e-2, np.quantile(r[same], 0.999)
+    assert_pointwise(img, ref, same, "C1 vs oracle")
     st = sc.stats()
     assert st.launches > 0 and st.rays_primary == cam.nx * cam.ny
 
@@ -70,9 +98,7 @@ def test_c1_radiance_vs_reference_binary(c1, have_ref, tmp_path):
     subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_raytracer"), xml], cwd=tmp_path, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     ref = rt.read_f32(os.path.join(tmp_path, hs.image_name(0) + ".f32"))
     img = sc.render(cam)
-    r = rel_err(img, ref).max(axis=-1)
-    assert r.mean() <= 1e-3, r.mean()
-    assert np.quantile(r, 0.995) <= 1e-2, np.quantile(r, 0.995)
+    assert_pointwise(img, ref, np.ones(img.shape[:2], dtype=bool), "C1 vs unmodified reference binary")
 
 
 # ------------------------------------------------------------------------------------------------ C2..C5 (reduced sizes)
@@ -91,7 +117,7 @@ def _check_vs_oracle(rt, hs, sc, opts=None, mean_tol=2e-3, q=0.98, q_tol=1e-2):
     where a sample straddles a geometric / shadow discontinuity."""
     cam = hs.camera(0)
     img = sc.render(cam, opts)
-    ref = rt.oracle_render(hs.desc, cam, opts)
+    ref = orc.oracle_render(hs.desc, cam, opts)
     assert np.isfinite(img).all()
     r = rel_err(img, ref).max(axis=-1)
     assert np.quantile(r, q) <= q_tol, (np.quantile(r, q), r.mean())
@@ -133,7 +159,7 @@ def test_c3_mesh_vs_oracle_and_reference(rt, scene_dir, tmp_path):
     xml = rt.scenes.scene_c3(os.path.join(scene_dir, "c3"), res=(320, 180), spp=4, n=64)
     hs, sc = _load(rt, xml)
     cam = hs.camera(0)
-    same = hit_agreement(sc.trace_primary(cam), rt.oracle_trace_primary(hs.desc, cam))
+    same = hit_agreement(sc.trace_primary(cam), orc.oracle_trace_primary(hs.desc, cam))
     assert same.mean() >= 0.999, same.mean()
     img, _ = _check_vs_oracle(rt, hs, sc)
     _check_vs_reference_statistical(rt, xml, hs, img, str(tmp_path))
@@ -146,7 +172,7 @@ def test_c4_instances_vs_oracle_and_reference(rt, scene_dir, tmp_path):
     xml = rt.scenes.scene_c4(os.path.join(scene_dir, "c4"), res=(320, 180), spp=4, n=48)
     hs, sc = _load(rt, xml)
     cam = hs.camera(0)
-    g, o = sc.trace_primary(cam), rt.oracle_trace_primary(hs.desc, cam)
+    g, o = sc.trace_primary(cam), orc.oracle_trace_primary(hs.desc, cam)
     same = hit_agreement(g, o)
     assert same.mean() >= 0.999, same.mean()
     both = same & (g["full"] == 1)
@@ -232,6 +258,40 @@ def test_tonemap_runs_and_is_monotone(rt, scene_dir):
     sc.close(); hs.close()
 
 
+def _tonemap_agrees(rt, sc, img, label, **kw):
+    got = sc.tonemap(img, **kw).astype(np.int64)
+    want = orc.oracle_tonemap(img, **kw).astype(np.int64)
+    d = np.abs(got - want)
+    print(f"[tonemap {label} {kw}] exact {float((d == 0).mean()):.5f}, within 1 LSB {float((d <= 1).mean()):.5f}, max {int(d.max())}")
+    assert (d <= 1).mean() >= 0.999, (label, kw, float((d <= 1).mean()))
+    assert d.max() <= 3, (label, kw, int(d.max()))
+    return got
+
+
+def test_tonemap_vs_oracle(rt, scene_dir):
+    """K7 against its independent CPU statement (oracle_tonemap, double precision): +-1 LSB on >= 99.9 % of the pixels, for the
+    rendered HDR frames (C1 radiance in 0..~1e3; the C5 path-traced frame with its sun) and a synthetic 8-decade log-normal image,
+    with and without burn-out, saturation != 1 and two gammas."""
+    xml = rt.scenes.scene_c1(os.path.join(scene_dir, "c1tmo"), res=160)
+    hs, sc = _load(rt, xml)
+    img = sc.render(hs.camera(0))
+    for kw in (dict(key=0.18, burn=1.0, saturation=1.0, gamma=2.2), dict(key=0.36, burn=0.0, saturation=0.7, gamma=1.8), dict(key=0.09, burn=5.0, saturation=1.3, gamma=2.2)):
+        _tonemap_agrees(rt, sc, img, "c1", **kw)
+    rng = np.random.default_rng(5)
+    syn = np.exp(rng.normal(0.0, 3.0, size=(96, 128, 3))).astype(np.float32)
+    syn[:4] = 0.0                                                    # black rows: L = 0 pixels
+    syn[10, 10] = 5e6                                                # a firefly far above the white point
+    for kw in (dict(key=0.18, burn=1.0, saturation=1.0, gamma=2.2), dict(key=0.18, burn=0.0, saturation=0.5, gamma=2.2)):
+        out = _tonemap_agrees(rt, sc, syn, "lognormal", **kw)
+        assert (out[:4] == 0).all()
+    sc.close(); hs.close()
+    xml5 = rt.scenes.scene_c5(os.path.join(scene_dir, "c5tmo"), res=(160, 90), spp=16)
+    hs5, sc5 = _load(rt, xml5)
+    img5 = sc5.render(hs5.camera(0), rt.default_opts(integrator=rt.RT_INTEGRATOR_PATH))
+    _tonemap_agrees(rt, sc5, img5, "c5", key=0.18, burn=1.0, saturation=1.0, gamma=2.2)
+    sc5.close(); hs5.close()
+
+
 def test_errors_are_reported_not_fatal(rt):
     with pytest.raises(rt.RtError) as e:
         rt.HostScene("/nonexistent/dir/scene.xml")
@@ -255,10 +315,10 @@ def test_feature_matrix_deterministic(rt, scene_dir, tmp_path, variant):
     xml = rt.scenes.scene_features(os.path.join(scene_dir, "gfeat_" + variant), variant)
     hs, sc = _load(rt, xml)
     cam = hs.camera(0)
-    same = hit_agreement(sc.trace_primary(cam), rt.oracle_trace_primary(hs.desc, cam))
+    same = hit_agreement(sc.trace_primary(cam), orc.oracle_trace_primary(hs.desc, cam))
     assert same.mean() >= 0.999, same.mean()
     img = sc.render(cam)
-    ref = rt.oracle_render(hs.desc, cam)
+    ref = orc.oracle_render(hs.desc, cam)
     r = rel_err(img, ref).max(axis=-1)
     assert r[same].mean() <= 1e-3, r[same].mean()
     assert np.quantile(r[same], 0.995) <= 1e-2, np.quantile(r[same], 0.995)
@@ -298,7 +358,7 @@ def test_edge_cases(rt, scene_dir):
         hs, sc = _load(rt, p)
         cam = hs.camera(0)
         img = sc.render(cam)
-        ref = rt.oracle_render(hs.desc, cam)
+        ref = orc.oracle_render(hs.desc, cam)
         assert np.allclose(img, ref, rtol=1e-5, atol=1e-5), tag
         if tag == "empty":
             assert np.allclose(img, [3, 4, 5])
@@ -317,6 +377,41 @@ def test_edge_cases(rt, scene_dir):
 
 
 # ------------------------------------------------------------------------------------------------ BASELINE.json full sizes
+FULL_WINDOWS = {"c4": (500, 900), "c3": (520, 930), "c2": (700, 470), "c5": (1500, 2020)}   # (row0, col0) of the 32x48 oracle window
+
+
+@pytest.mark.parametrize("config", ["c2", "c5"])
+def test_full_size_window_c2_c5(rt, scene_dir, config):
+    """Full-size C2 (1024x1024x100 spp: dielectric + rough conductor, area light, depth 6) and C5 at its full 3840x2160 resolution
+    (path tracer with NEE + RR + cosine sampling, HDR environment + emissive quad; spp overridden to 16 - the full 1024 spp frame is
+    8.5 G paths): the oracle renders a 32x48 pixel window of the SAME full-size frame with the same Philox streams (the window
+    straddles the dielectric sphere's silhouette in C2, the mirror sphere's in C5) and must match the GPU frame there."""
+    import bench
+    full_kw, _ = bench.WORKLOADS[config]
+    tag = "full"
+    if config == "c5":
+        full_kw = dict(full_kw, spp=16); tag = "full_spp16"
+    xml = bench.make_scene(rt, config, full_kw, tag)
+    hs, sc = _load(rt, xml)
+    cam = hs.camera(0)
+    opts = rt.default_opts(integrator=rt.RT_INTEGRATOR_PATH) if config == "c5" else rt.default_opts()
+    img = sc.render(cam, opts)
+    assert np.isfinite(img).all()
+    st = sc.stats()
+    assert st.rays_primary == cam.nx * cam.ny * cam.num_samples
+    assert st.rays_secondary > 0
+    r0, c0 = FULL_WINDOWS[config]
+    ref = orc.oracle_render(hs.desc, cam, opts, rows=(r0, r0 + 32), cols=(c0, c0 + 48), threads=os.cpu_count() or 8)
+    a, b = img[r0:r0 + 32, c0:c0 + 48], ref[r0:r0 + 32, c0:c0 + 48]
+    assert b.max() > 0
+    r = rel_err(a, b).max(axis=-1)
+    q, qtol, mtol = (0.95, 1e-2, 3e-3) if config == "c2" else (0.90, 2e-2, 1e-2)
+    print(f"[{config} full-size window] q{q} rel err {np.quantile(r, q):.3e}, median {np.median(r):.3e}, means {a.mean():.5f} / {b.mean():.5f}")
+    assert np.quantile(r, q) <= qtol and abs(a.mean() - b.mean()) <= mtol * b.mean(), (np.quantile(r, q), a.mean(), b.mean())
+    assert np.median(r) <= 1e-4, np.median(r)                       # same samples: the typical pixel agrees to float rounding
+    sc.close(); hs.close()
+
+
 @pytest.mark.parametrize("config", ["c3", "c4"])
 def test_full_size_region_and_properties(rt, scene_dir, config):
     """Full-size C3 (69k triangles, 1920x1080x16) / C4 (870k triangles x16 instances, 1920x1080x64): the oracle renders a
@@ -333,8 +428,8 @@ def test_full_size_region_and_properties(rt, scene_dir, config):
     st = sc.stats()
     assert st.rays_primary == cam.nx * cam.ny * cam.num_samples
     # (1) window parity against the oracle
-    r0, c0 = (500, 900) if config == "c4" else (520, 930)
-    ref = rt.oracle_render(hs.desc, cam, rows=(r0, r0 + 32), cols=(c0, c0 + 48), threads=os.cpu_count() or 8)
+    r0, c0 = FULL_WINDOWS[config]
+    ref = orc.oracle_render(hs.desc, cam, rows=(r0, r0 + 32), cols=(c0, c0 + 48), threads=os.cpu_count() or 8)
     a, b = img[r0:r0 + 32, c0:c0 + 48], ref[r0:r0 + 32, c0:c0 + 48]
     assert b.max() > 0
     r = rel_err(a, b).max(axis=-1)
@@ -397,7 +492,7 @@ def test_many_lights_chunking_and_levels(rt, scene_dir):
         f.write(xml)
     hs, sc = _load(rt, p)
     cam = hs.camera(0)
-    ref = rt.oracle_render(hs.desc, cam)
+    ref = orc.oracle_render(hs.desc, cam)
     img = sc.render(cam, rt.default_opts(queue_capacity=1024, wave_rays=1024))
     r = rel_err(img, ref).max(axis=-1)
     assert r.mean() <= 1e-3 and np.quantile(r, 0.99) <= 1e-2, (r.mean(), np.quantile(r, 0.99))
@@ -418,7 +513,7 @@ def test_cli_writes_the_reference_file_formats(rt, scene_dir, tmp_path):
     assert toks[:4] == ["P3", "96", "96", "255"]
     got = np.array(toks[4:], dtype=np.int64).reshape(96, 96, 3)
     hs = rt.HostScene(xml)
-    ref = rt.oracle_render(hs.desc, hs.camera(0))
+    ref = orc.oracle_render(hs.desc, hs.camera(0))
     want = np.clip(ref, 0, 255).astype(np.uint8).astype(np.int64)
     assert (np.abs(got - want) <= 1).mean() >= 0.999       # (unsigned char) truncation can flip at an integer boundary
     assert (got == want).mean() >= 0.98
@@ -444,6 +539,6 @@ def test_cli_writes_the_reference_file_formats(rt, scene_dir, tmp_path):
     img = sc2.render(hs2.camera(0), hs2.render_opts(0))                  # same options, same seed: the CLI's HDR frame
     assert np.allclose(rt.read_f32(os.path.join(tmp_path, "c1ext.exr.f32")), img, rtol=1e-4, atol=1e-4)
     t = hs2.tonemap(0)
-    want = sc2.tonemap(img, key=t.key, burn=t.burn_percent, saturation=t.saturation, gamma=t.gamma).astype(np.int64)
+    want = orc.oracle_tonemap(img, key=t.key, burn=t.burn_percent, saturation=t.saturation, gamma=t.gamma).astype(np.int64)   # the CPU statement, not the CUDA path again
     assert (np.abs(ldr - want) <= 1).mean() >= 0.999
     sc2.close(); hs2.close()

@@ -6,10 +6,12 @@ import os
 import numpy as np
 import pytest
 
+import oracle_api as orc
+
 
 def test_philox_known_answer_vectors(rt):
     """Random123 kat_vectors for philox4x32-10.  The oracle returns floats (x >> 8) * 2^-24; compare the top 24 bits."""
-    lib = rt.load_oracle()
+    lib = orc.load_oracle()
     vecs = [((0, 0, 0, 0), 0, (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
             ((0xffffffff,) * 4, 0xffffffffffffffff, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
             ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0x299f31d0 << 32) | 0xa4093822, (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
@@ -23,7 +25,7 @@ def test_philox_known_answer_vectors(rt):
 
 def test_perlin_lattice_points(rt):
     """Perlin value at lattice points is 0 -> 0.5 after the linear conversion, 0 after absval (src/Perlin.cpp:52-84)."""
-    lib = rt.load_oracle()
+    lib = orc.load_oracle()
     for p in [(0, 0, 0), (1, 2, 3), (-4, 7, -2)]:
         assert lib.oracle_perlin(*map(float, p), 1.0, 1) == pytest.approx(0.5, abs=1e-6)
         assert lib.oracle_perlin(*map(float, p), 1.0, 0) == pytest.approx(0.0, abs=1e-6)
@@ -33,7 +35,7 @@ def test_perlin_lattice_points(rt):
 
 def test_conductor_fresnel_normal_incidence(rt):
     """rs = rp at normal incidence: ((n-1)^2 + k^2) / ((n+1)^2 + k^2) (src/Scene.cpp:135-146)."""
-    lib = rt.load_oracle()
+    lib = orc.load_oracle()
     n, k = 0.37, 2.82
     expect = ((n - 1) ** 2 + k * k) / ((n + 1) ** 2 + k * k)
     assert lib.oracle_conductor_fresnel(n, k, 1.0) == pytest.approx(expect, rel=1e-5)
@@ -66,15 +68,15 @@ def test_camera_corner_rays_and_sphere_roots(rt, tmp_path):
     p = _one_object_scene(rt, str(tmp_path), body, verts="0 0 -5", res=(2, 2))
     hs = rt.HostScene(p)
     cam = hs.camera(0)
-    hits = rt.oracle_trace_primary(hs.desc, cam, threads=1)
+    hits = orc.oracle_trace_primary(hs.desc, cam, threads=1)
     # 2x2 image on a [-1,1]^2 plane at distance 1: pixel centres at (+-0.5, +-0.5, -1); the unit sphere at z=-5 is missed by all four
     assert hits["full"].sum() == 0
-    img = rt.oracle_render(hs.desc, cam, threads=1)
+    img = orc.oracle_render(hs.desc, cam, threads=1)
     assert np.allclose(img, [7, 8, 9])   # camera-ray miss -> BackgroundColor
     hs.close()
     p = _one_object_scene(rt, str(tmp_path / "b"), body, verts="0 0 -5", res=(1, 1))
     hs = rt.HostScene(p)
-    hits = rt.oracle_trace_primary(hs.desc, hs.camera(0), threads=1)
+    hits = orc.oracle_trace_primary(hs.desc, hs.camera(0), threads=1)
     assert hits["full"][0, 0] == 1 and hits["t"][0, 0] == pytest.approx(4.0, abs=1e-5)
     assert np.allclose(hits["normal"][0, 0], [0, 0, 1], atol=1e-6)
     hs.close()
@@ -86,7 +88,7 @@ def test_triangle_edge_rule(rt, tmp_path):
     body = '<Triangle id="1"><Material>1</Material><Indices>2 3 4</Indices></Triangle>'
     p = _one_object_scene(rt, str(tmp_path), body, res=(1, 1))
     hs = rt.HostScene(p)
-    hits = rt.oracle_trace_primary(hs.desc, hs.camera(0), threads=1)
+    hits = orc.oracle_trace_primary(hs.desc, hs.camera(0), threads=1)
     assert hits["full"][0, 0] == 1 and hits["t"][0, 0] == pytest.approx(5.0, rel=1e-6)   # (0,0,-5) lies on edge a-b
     hs.close()
 
@@ -97,7 +99,34 @@ def test_point_light_inverse_square_and_ambient(rt, tmp_path):
     lights = "<AmbientLight>10 20 30</AmbientLight><PointLight id=\"1\"><Position>0 0 -3</Position><Intensity>400 400 400</Intensity></PointLight>"
     p = _one_object_scene(rt, str(tmp_path), body, lights=lights, res=(1, 1), verts="0 0 0\n 3 -3 -5\n -3 -3 -5\n 0 3 -5")
     hs = rt.HostScene(p)
-    img = rt.oracle_render(hs.desc, hs.camera(0), threads=1)
+    img = orc.oracle_render(hs.desc, hs.camera(0), threads=1)
     # hit point (0,0,-5), normal +z (towards the camera), light 2 units in front: E = 400/4 = 100, cos = 1
     assert np.allclose(img[0, 0], [110, 120, 130], rtol=1e-5)
     hs.close()
+
+
+def test_oracle_tonemap_against_numpy_formula():
+    """The tone-map oracle (oracle_tonemap) against the same operator written with numpy (float64), and closed-form cases:
+    a constant grey image maps to key*(1+key/key^2)/(1+key) = 1 at burn 0 (white point = the image's own luminance)."""
+    rng = np.random.default_rng(11)
+    img = np.exp(rng.normal(0.0, 2.0, size=(40, 56, 3))).astype(np.float32)
+    for key, burn, sat, gamma in ((0.18, 0.0, 1.0, 2.2), (0.3, 2.0, 0.6, 1.7)):
+        got = orc.oracle_tonemap(img, key=key, burn=burn, saturation=sat, gamma=gamma).astype(np.int64)
+        x = img.astype(np.float64)
+        L = np.maximum(x @ np.array([0.2126, 0.7152, 0.0722]), 0.0)
+        scale = key / np.exp(np.mean(np.log(1e-5 + L)))
+        Ls = L * scale
+        mx = Ls.max()
+        lw = mx
+        if burn > 0:
+            hist = np.bincount(np.clip((Ls / mx * 4095).astype(np.int64), 0, 4095).ravel(), minlength=4096)
+            b = int(np.searchsorted(np.cumsum(hist), int(L.size * (100.0 - burn) / 100.0)))
+            lw = (b + 0.5) / 4095 * mx
+        Ld = Ls * (1 + Ls / lw ** 2) / (1 + Ls)
+        v = np.clip((np.maximum(x, 0) / L[..., None]) ** sat * Ld[..., None], 0, 1)
+        want = np.floor(255.0 * v ** (1.0 / gamma) + 0.5).astype(np.int64)
+        assert (np.abs(got - want) <= 1).mean() == 1.0 and (got == want).mean() > 0.995
+    grey = np.full((8, 8, 3), 7.5, dtype=np.float32)
+    out = orc.oracle_tonemap(grey, key=0.18, burn=0.0, saturation=1.0, gamma=2.2)
+    assert (out == 255).all()
+    assert (orc.oracle_tonemap(np.zeros((4, 4, 3), np.float32)) == 0).all()

@@ -8,6 +8,8 @@ import sys
 import numpy as np
 import pytest
 
+import oracle_api as orc
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -28,7 +30,7 @@ def _worker(rank, world, port, xml, out_path):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     hs = rt.HostScene(xml)
     cam = hs.camera(0)
-    full = rt.oracle_render(hs.desc, cam, threads=2)
+    full = orc.oracle_render(hs.desc, cam, threads=2)
     mask = rt.tiling.tile_mask(cam.nx, cam.ny, rank, world)
     assert mask.sum() > 0
     part = np.where(mask[..., None], full, 0.0).astype(np.float32)

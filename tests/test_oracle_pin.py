@@ -7,6 +7,8 @@ import subprocess
 import numpy as np
 import pytest
 
+import oracle_api as orc
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 
@@ -17,23 +19,12 @@ CASES = {
 }
 
 
-def labels_to_object_prim(desc, label):
-    """Inverse of the relabelling in oracle/harness/hits_main.cpp: object hits carry base_i + k, instance hits -(j+1)."""
-    d = desc.contents
-    nprims = []
-    for i in range(d.num_objects):
-        o = d.objects[i]
-        nprims.append(1 if o.kind == 0 else d.meshes[o.geom].tri_count)
-    # instances are the trailing entries that share a mesh with an earlier entry ... the harness numbers bases first
-    return nprims
-
-
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_oracle_matches_golden_radiance(rt, scene_dir, name):
     gen, kw = CASES[name]
     xml = getattr(rt.scenes, gen)(os.path.join(scene_dir, name), **kw)
     hs = rt.HostScene(xml)
-    img = rt.oracle_render(hs.desc, hs.camera(0))
+    img = orc.oracle_render(hs.desc, hs.camera(0))
     gold = np.load(os.path.join(GOLD, name + ".npz"))["radiance"]
     assert img.shape == gold.shape
     r = np.abs(img - gold) / np.maximum(np.abs(gold), 1.0)
@@ -50,7 +41,7 @@ def test_oracle_matches_golden_primary_hits(rt, scene_dir, name):
     xml = getattr(rt.scenes, gen)(os.path.join(scene_dir, name + "_h"), **kw)
     hs = rt.HostScene(xml)
     d = hs.desc.contents
-    hits = rt.oracle_trace_primary(hs.desc, hs.camera(0))
+    hits = orc.oracle_trace_primary(hs.desc, hs.camera(0))
     g = np.load(os.path.join(GOLD, name + ".npz"))
     assert (hits["full"] == g["hit_full"]).all()
     full = hits["full"] == 1
@@ -89,7 +80,7 @@ def test_oracle_c1_bit_exact_vs_live_reference(rt, scene_dir, have_ref, tmp_path
     subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_raytracer"), xml], cwd=tmp_path, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     hs = rt.HostScene(xml)
     ref = rt.read_f32(os.path.join(tmp_path, hs.image_name(0) + ".f32"))
-    img = rt.oracle_render(hs.desc, hs.camera(0))
+    img = orc.oracle_render(hs.desc, hs.camera(0))
     assert (img == ref).mean() >= 0.999
     hs.close()
 
@@ -109,7 +100,7 @@ def test_oracle_statistical_vs_live_reference(rt, scene_dir, have_ref, tmp_path,
         os.makedirs(d)
         subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_raytracer"), xml], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         refs.append(rt.read_f32(os.path.join(d, hs.image_name(0) + ".f32")))
-    img = rt.oracle_render(hs.desc, hs.camera(0))
+    img = orc.oracle_render(hs.desc, hs.camera(0))
 
     from conftest import assert_statistically_equal
     assert_statistically_equal(refs[0], refs[1], img, b=6)
@@ -128,7 +119,7 @@ def test_oracle_feature_matrix_deterministic_vs_live_reference(rt, scene_dir, ha
     subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_raytracer"), xml], cwd=tmp_path, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     hs = rt.HostScene(xml)
     ref = rt.read_f32(os.path.join(tmp_path, hs.image_name(0) + ".f32"))
-    img = rt.oracle_render(hs.desc, hs.camera(0))
+    img = orc.oracle_render(hs.desc, hs.camera(0))
     r = np.abs(img - ref) / np.maximum(np.abs(ref), 1.0)
     assert r.mean() <= 1e-5, r.mean()
     assert np.quantile(r, 0.999) <= 1e-3, np.quantile(r, 0.999)
@@ -150,6 +141,6 @@ def test_oracle_feature_matrix_stochastic_vs_live_reference(rt, scene_dir, have_
         os.makedirs(d)
         subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_raytracer"), xml], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         refs.append(rt.read_f32(os.path.join(d, hs.image_name(0) + ".f32")))
-    img = rt.oracle_render(hs.desc, hs.camera(0))
+    img = orc.oracle_render(hs.desc, hs.camera(0))
     assert_statistically_equal(refs[0], refs[1], img, b=6)
     hs.close()
