@@ -281,6 +281,11 @@ def run_ours(args, rt):
         gather.finish()                                       # p2p: device barrier after the peer stores; nccl: SUM reduce to rank 0
 
     host_np = host_frame.numpy().reshape(cam.ny, cam.nx, 3)
+    pageable_np = np.empty((cam.ny, cam.nx, 3), dtype=np.float32)   # what the reference hands over: new float[] (src/Image.cpp:8)
+    pageable_np.fill(0.0)
+
+    def e2e_pageable_step(o):
+        sc.render(cam, o, out=pageable_np)
 
     def e2e_step(o):
         if world == 1:
@@ -359,6 +364,10 @@ def run_ours(args, rt):
     e2e_step(opts)                                            # untimed: first-use allocations of the host-buffer path
     barrier()
     ms_e2e = timed(e2e_step, args.steps, wall=True)
+    ms_e2e_pageable = None
+    if world == 1:
+        e2e_pageable_step(opts)
+        ms_e2e_pageable = timed(e2e_pageable_step, args.steps, wall=True) / args.steps
 
     rays_local = torch.tensor(traced, dtype=torch.float64, device=dev)
     lt = torch.tensor([timed_launches], dtype=torch.float64, device=dev)
@@ -415,7 +424,10 @@ def run_ours(args, rt):
                            "bvh_builder": args.bvh, "bvh_device_meshes": int(sstats.bvh_device_meshes)},
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(cam_host.numel()), "d2h_bytes_per_step": int(npix * 12),
                         "api": "rt_render (host camera/options in, host framebuffer out)" if world == 1 else ("rt_render_device (K8 stores owned tiles into rank 0's frame over NVLink peer memory) + device barrier" if gather.mode == "p2p" else "rt_render_device + NCCL reduce") + " + D2H on rank 0",
-                        "timing": "host clock around the synchronous call, max over ranks"},
+                        "timing": "host clock around the synchronous call, max over ranks",
+                        "host_buffer": "page-locked (DMA straight into it)",
+                        "pageable_host_buffer": None if ms_e2e_pageable is None else {"ms_per_step": ms_e2e_pageable, "value": rays_frame / (ms_e2e_pageable * 1e-3) / 1e6,
+                            "note": "same call with an ordinary malloc'ed frame, as the reference's Image::_data is: staged through the library's pinned buffer + host memcpy"}},
                 "gpu_launches": int(lt.item()), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
         out.emit(json.dumps(line))
     sc.close()

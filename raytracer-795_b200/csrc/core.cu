@@ -70,9 +70,10 @@ struct QueueBufs {
 
 }  // namespace
 
-// Per-pipeline render state.  Two pipelines (own stream, ray queues, shadow queue, counters) process alternate waves of a
-// frame from two host threads, so the tail of one wave's kernels (last rays finishing on a mostly idle GPU) and the host
-// round trips of its queue-size readbacks overlap with the other wave's work.
+// Per-pipeline render state.  Alternate waves of a frame go to two pipelines (own stream, ray queues, shadow queue, counters),
+// all enqueued by ONE host thread without a single round trip inside the frame: every kernel reads its input size from device
+// memory (DCounters).  Two streams, so that the tail of one wave's persistent kernels (last rays finishing on a mostly idle
+// GPU) overlaps with the other wave's work.
 struct Pipe {
     cudaStream_t st = nullptr;
     std::vector<QueueBufs> levels;
@@ -83,18 +84,24 @@ struct Pipe {
 };
 constexpr int kPipes = 4;      // upper bound; RtScene::npipes_wanted (default 2, RT795_PIPES) are used
 
+typedef void (*TraceKernel)(DScene, TraceIO, DCounters*);
+typedef void (*RaygenTraceKernel)(DScene, TraceIO, DCounters*, RaygenArgs);
+
 struct RtScene {
     int device = 0;
+    int sm_count = 148;
     cudaStream_t stream = nullptr;
     DScene d{};
     // geometry + shading buffers
-    DevBuf<float4> nodes, nodes4, tris, spheres;
-    DevBuf<uint4> nodes4q;
+    DevBuf<float4> nodes4, tris, spheres;
+    DevBuf<float4> nodes2_debug;       // binary BVH the 4-wide one is collapsed from: resident only with RT795_DEBUG_BVH=1 (rt_debug_read_bvh)
+    DevBuf<uint4> nodes4q;             // 8-bit quantised twin of nodes4: resident only with RT795_QNODES=1 or RT795_DEBUG_BVH=1
     DevBuf<float4> tris_w;
     // RT795_QNODES=1: the occlusion kernel walks the 8-bit quantised copy of the 4-wide BVH (4 instead of 7 loads per node).
     // Measured on C4: 39.1 ms vs 34.9 ms with fp32 nodes - the byte decode (24 PRMT + 24 FADD per node) costs more on the
     // ALU-limited kernel than the saved L1 wavefronts return, so fp32 nodes stay the default.
     bool quantised_occlusion = false;
+    bool keep_debug_bvh = false;
     DevBuf<int32_t> obj_root4;
     DevBuf<DObjectXf> obj_xf;
     DevBuf<DObjectSh> obj_sh;
@@ -106,16 +113,27 @@ struct RtScene {
     std::vector<DevBuf<unsigned char>> image_px;
     DevBuf<RtLight> lights;
     bool has_dielectric = false;
+    bool has_specular = false;             // some material spawns continuation rays (mirror / conductor / dielectric)
     int bvh_depth = 0;
-    bool persistent = true;            // K2/K4 as persistent warps with dynamic fetch (traverse_pt.cuh); RT795_TRAVERSAL=classic selects traverse.cuh
+    int tlas_base2 = 0;
+    // kernel variants (A/B switches, all default to the measured best): RT795_SMEM_TLAS, RT795_FUSED_RAYGEN
+    bool smem_tlas = true, fused_raygen = true;
+    int trace_smem = 0;                    // dynamic shared memory of the traversal launches (staged top level), 0 = not staged
+    TraceKernel k_closest = nullptr, k_closest_count = nullptr, k_any = nullptr, k_any_count = nullptr;
+    RaygenTraceKernel k_rg_closest = nullptr, k_rg_closest_count = nullptr;
     int grid_extend = 0, grid_shadow = 0;   // resident CTAs: SM count x occupancy
     int trav_flags = 2, trav_flags_shadow = 3;   // TraceIO.flags for closest-hit / occlusion launches (measured best on C4; RT795_TRAVERSAL_FLAGS overrides both)
-    bool affine_tris = true;                // RT795_AFFINE_TRIS=0: Moeller-Trumbore on {v0,e1,e2} in the render kernels too (A/B)
     bool full_grid = false;                 // RT795_FULL_GRID=1: one thread per ray instead of resident warps
     // render state
     Pipe pipes[kPipes];
     size_t queue_cap = 0, shadow_cap = 0;
+    // Frames are first enqueued optimistically (whole levels, two ping-pong queue buffers); a queue overflow flagged by the device
+    // halves `wave_limit` and redoes the frame, and below kMinOptimisticWave the chunked, host-synchronised driver takes over.
+    size_t wave_limit = 0;                  // 0 = not limited yet
+    size_t learnt_cap = 0;                  // queue capacity wave_limit / force_chunked were learnt with
+    bool force_chunked = false, env_chunked = false;   // RT795_DRIVER=chunked, or learnt from overflows
     DevBuf<float> accum, out_dev;
+    float* h_stage = nullptr; size_t h_stage_n = 0;   // pinned staging for rt_render's host framebuffer
     DevBuf<RtHit> hits_dev;
     // tone map scratch
     DevBuf<double> tm_sum; DevBuf<float> tm_max; DevBuf<unsigned> tm_hist; DevBuf<float> tm_in; DevBuf<uint8_t> tm_out;
@@ -284,7 +302,7 @@ bool BuildAndUpload(RtScene* sc, const RtSceneDesc* s, bool allow_device) {
                 int payload = ~ch; int first = (payload >> 3) + tri_base;
                 return (int32_t)~((first << 3) | (payload & 7));
             };
-            QuantiseBvh4(b4, &sg.h4q);
+            if (sc->quantised_occlusion || sc->keep_debug_bvh) QuantiseBvh4(b4, &sg.h4q);
             for (BvhNode64Q& nq : sg.h4q)
                 for (int c = 0; c < 4; c++) { int32_t ch; memcpy(&ch, &nq.w[4 + c], 4); ch = rebase(ch, base4); memcpy(&nq.w[4 + c], &ch, 4); }
             sg.h4 = std::move(b4.nodes);
@@ -330,7 +348,7 @@ bool BuildAndUpload(RtScene* sc, const RtSceneDesc* s, bool allow_device) {
             for (int k = 0; k < 3; k++) { ob.lo[k] = sp.center[k] - sp.radius; ob.hi[k] = sp.center[k] + sp.radius; }
             root = ~o.geom;
         } else {
-            ob = mesh_bounds[o.geom]; root = mesh_root[o.geom]; max_blas_depth = std::max(max_blas_depth, mesh_depth[o.geom]);
+            ob = mesh_bounds[o.geom]; root = mesh_root4[o.geom]; max_blas_depth = std::max(max_blas_depth, mesh_depth[o.geom]);
             root4[i] = mesh_root4[o.geom]; max_blas_stack4 = std::max(max_blas_stack4, mesh_stack4[o.geom]);
         }
         x.blur_root = make_float4(o.blur[0], o.blur[1], o.blur[2], BitsToFloat(root));
@@ -383,7 +401,7 @@ bool BuildAndUpload(RtScene* sc, const RtSceneDesc* s, bool allow_device) {
         sc->bvh_depth = need2;
     }
     std::vector<BvhNode64Q> tq;
-    QuantiseBvh4(t4, &tq);
+    if (sc->quantised_occlusion || sc->keep_debug_bvh) QuantiseBvh4(t4, &tq);
     auto tlas_ref = [&](int32_t ch, int inner_base) {
         if (ch == kNoChild) return ch;
         if (ch >= 0) return ch + inner_base;
@@ -403,9 +421,13 @@ bool BuildAndUpload(RtScene* sc, const RtSceneDesc* s, bool allow_device) {
     static_assert(sizeof(BvhNode64) == 64, "node size");
     static_assert(sizeof(BvhNode128) == 128, "node4 size");
     static_assert(sizeof(BvhNode64Q) == 64, "quantised node size");
-    sc->nodes.Alloc((size_t)n2_total * 4);
+    // Resident for rendering: the 4-wide nodes, the triangle records (shading) and their affine maps (traversal).  The binary BVH
+    // the 4-wide one was collapsed from and the quantised twin are uploaded only for rt_debug_read_bvh (RT795_DEBUG_BVH=1) / the
+    // quantised occlusion variant (RT795_QNODES=1): 45 MB less next to C4's 71 MB traversal working set.
+    const bool want2 = sc->keep_debug_bvh, want4q = sc->keep_debug_bvh || sc->quantised_occlusion;
+    if (want2) sc->nodes2_debug.Alloc((size_t)n2_total * 4);
     sc->nodes4.Alloc((size_t)n4_total * 8);
-    sc->nodes4q.Alloc((size_t)n4_total * 4);
+    if (want4q) sc->nodes4q.Alloc((size_t)n4_total * 4);
     sc->tris.Alloc((size_t)tri_total * 3);
     {
         size_t o2 = 0, o4 = 0, ot = 0;
@@ -414,15 +436,15 @@ bool BuildAndUpload(RtScene* sc, const RtSceneDesc* s, bool allow_device) {
         };
         for (MeshSeg& sg : segs) {
             bool d = sg.on_device;
-            put(sc->nodes.p + o2 * 4, d ? (const void*)sg.dev.nodes2 : (const void*)sg.h2.data(), (size_t)sg.n2 * 64, d);
+            if (want2) put(sc->nodes2_debug.p + o2 * 4, d ? (const void*)sg.dev.nodes2 : (const void*)sg.h2.data(), (size_t)sg.n2 * 64, d);
             put(sc->nodes4.p + o4 * 8, d ? (const void*)sg.dev.nodes4 : (const void*)sg.h4.data(), (size_t)sg.n4 * 128, d);
-            put(sc->nodes4q.p + o4 * 4, d ? (const void*)sg.dev.nodes4q : (const void*)sg.h4q.data(), (size_t)sg.n4 * 64, d);
+            if (want4q) put(sc->nodes4q.p + o4 * 4, d ? (const void*)sg.dev.nodes4q : (const void*)sg.h4q.data(), (size_t)sg.n4 * 64, d);
             put(sc->tris.p + ot * 3, d ? (const void*)sg.dev.tris : (const void*)sg.htris.data(), (size_t)sg.ntris * 48, d);
             o2 += sg.n2; o4 += sg.n4; ot += sg.ntris;
         }
-        put(sc->nodes.p + o2 * 4, tl.nodes.data(), tl.nodes.size() * 64, false);
+        if (want2) put(sc->nodes2_debug.p + o2 * 4, tl.nodes.data(), tl.nodes.size() * 64, false);
         put(sc->nodes4.p + o4 * 8, t4.nodes.data(), t4.nodes.size() * 128, false);
-        put(sc->nodes4q.p + o4 * 4, tq.data(), tq.size() * 64, false);
+        if (want4q) put(sc->nodes4q.p + o4 * 4, tq.data(), tq.size() * 64, false);
     }
     sc->obj_root4.Upload(root4.data(), root4.size(), st);
     sc->spheres.Upload(spheres.data(), spheres.size(), st);
@@ -447,24 +469,26 @@ bool BuildAndUpload(RtScene* sc, const RtSceneDesc* s, bool allow_device) {
     auto t2 = std::chrono::steady_clock::now();
 
     DScene& d = sc->d;
-    d.nodes4q = sc->nodes4q.p;
-    d.tris_w = nullptr;
-    if (sc->affine_tris && tri_total > 0) {
-        sc->tris_w.Alloc((size_t)tri_total * 3);
+    d.nodes4q = want4q ? sc->nodes4q.p : nullptr;
+    sc->tris_w.Alloc((size_t)std::max(1, tri_total) * 3);
+    if (tri_total > 0) {
         k_make_affine_tris<<<(tri_total + 255) / 256, 256, 0, st>>>(sc->tris.p, tri_total, sc->tris_w.p);
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
-        d.tris_w = sc->tris_w.p;
     }
-    d.nodes4 = sc->nodes4.p; d.obj_root4 = sc->obj_root4.p; d.tlas_root4 = tlas_base4;
-    d.nodes = sc->nodes.p; d.tris = sc->tris.p; d.obj_xf = sc->obj_xf.p; d.spheres = sc->spheres.p; d.tlas_root = tlas_base;
+    d.tris_w = sc->tris_w.p;
+    d.nodes4 = sc->nodes4.p; d.obj_root4 = sc->obj_root4.p; d.tlas_root4 = tlas_base4; d.tlas_nodes = (int)t4.nodes.size();
+    d.tris = sc->tris.p; d.obj_xf = sc->obj_xf.p; d.spheres = sc->spheres.p; sc->tlas_base2 = tlas_base;
     d.obj_sh = sc->obj_sh.p; d.tri_idx = sc->tri_idx.p; d.vertices = sc->vertices.p; d.normals = sc->normals.p; d.texcoords = sc->texcoords.p;
     d.materials = sc->materials.p; d.textures = sc->textures.p; d.images = sc->images.p; d.lights = sc->lights.p;
     d.num_lights = s->num_lights; d.num_objects = s->num_objects; d.max_depth = s->max_recursion_depth;
     d.shadow_eps = s->shadow_ray_eps; d.int_eps = s->int_test_eps;
     memcpy(d.background, s->background_color, 12); memcpy(d.ambient, s->ambient_light, 12);
     d.env_light = s->env_light_index; d.background_texture = s->background_texture;
-    for (int i = 0; i < s->num_materials; i++) if (s->materials[i].type == RT_MAT_DIELECTRIC) sc->has_dielectric = true;
+    for (int i = 0; i < s->num_materials; i++) {
+        if (s->materials[i].type == RT_MAT_DIELECTRIC) sc->has_dielectric = true;
+        if (s->materials[i].type != RT_MAT_NORMAL) sc->has_specular = true;
+    }
 
     sc->stats.bvh2_nodes = (uint64_t)n2_total;
     sc->stats.bvh_nodes = (uint64_t)n4_total; sc->stats.bvh_bytes = (uint64_t)n4_total * 128; sc->stats.tri_bytes = (uint64_t)tri_total * 48;   // the 4-wide BVH is the one the render kernels walk
@@ -475,6 +499,10 @@ bool BuildAndUpload(RtScene* sc, const RtSceneDesc* s, bool allow_device) {
 
 inline int Blocks(long long n) { return (int)((n + kBlock - 1) / kBlock); }
 
+constexpr size_t kMinOptimisticWave = 4096;   // below this wave size the chunked driver takes over
+
+struct StageEvents { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[4]; };   // 0 raygen(+first extend when fused), 1 extend, 2 shade, 3 shadow
+
 struct Driver {
     RtScene* sc;
     Pipe* pp;
@@ -482,104 +510,188 @@ struct Driver {
     DCamera cam;
     DTiling tl;
     RenderConsts rc;
+    RaygenArgs rg;
     bool count;        // node / primitive-test counters (collect_counters & 2)
     bool stage_time;   // per-stage CUDA-event timing (collect_counters & 1)
-    int nlevels;
+    bool path;
+    int nlev;          // ray-tree levels a wave can have (level 0 = camera rays)
+    int nbuf;          // queue buffers per pipeline (2 = ping-pong)
     bool branching;
     float* accum;
     DShadowQueue sq;
-    uint64_t launches = 0, secondary = 0, shadow = 0, n_extend = 0, n_shade = 0, n_shadow = 0;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> unused;
-    double ms_extend = 0, ms_shade = 0, ms_shadow = 0;
+    uint64_t launches = 0, n_extend = 0, n_shade = 0, n_shadow = 0, secondary = 0, shadow = 0;
+    StageEvents* sev = nullptr;
 
     template <typename F>
-    void Timed(double* acc, F&& f) {
+    void Timed(int stage, F&& f) {
         if (!stage_time) { f(); return; }
         cudaEvent_t a, b;
         CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
         CK(cudaEventRecord(a, st));
         f();
         CK(cudaEventRecord(b, st));
-        CK(cudaEventSynchronize(b));
-        float ms = 0; CK(cudaEventElapsedTime(&ms, a, b));
-        *acc += ms;
-        cudaEventDestroy(a); cudaEventDestroy(b);
+        sev->ev[stage].push_back({a, b});
     }
 
-    // Processes rays [0, n) of level `lv`; recursion depth is bounded by the queue level count.
+
+    void LaunchExtend(const DRayQueue& q, const int32_t* count_ptr, int first, int limit, int32_t* cursor) {
+        TraceIO io{};
+        io.q = q; io.count_ptr = count_ptr; io.first = first; io.limit = limit; io.cursor = cursor; io.flags = sc->trav_flags;
+        int grid = sc->full_grid ? Blocks(limit) : std::min(Blocks(limit), sc->grid_extend);
+        (count ? sc->k_closest_count : sc->k_closest)<<<std::max(1, grid), kBlock, count ? 0 : sc->trace_smem, st>>>(sc->d, io, pp->counters.p);
+        launches++; n_extend++;
+    }
+    void LaunchShadow(const int32_t* count_ptr, int limit, int32_t* cursor) {
+        TraceIO io{};
+        io.sq = sq; io.count_ptr = count_ptr; io.first = 0; io.limit = limit; io.cursor = cursor; io.accum = accum; io.flags = sc->trav_flags_shadow;
+        int grid = sc->full_grid ? Blocks(limit) : std::min(Blocks(limit), sc->grid_shadow);
+        (count ? sc->k_any_count : sc->k_any)<<<std::max(1, grid), kBlock, (count || sc->quantised_occlusion) ? 0 : sc->trace_smem, st>>>(sc->d, io, pp->counters.p);
+        launches++; n_shadow++;
+    }
+    void LaunchShade(const DRayQueue& in, const DRayQueue& out, const int32_t* in_count, int first, int limit, int32_t* out_count, int32_t* shadow_count) {
+        ShadeIO io{};
+        io.in = in; io.out = out; io.sq = sq; io.in_count = in_count; io.first = first; io.limit = limit;
+        io.out_count = out_count; io.shadow_count = shadow_count; io.overflow = &pp->counters.p->overflow; io.accum = accum;
+        if (in_count) {
+            // size known to the device only: grid-stride variant on a fixed grid (8 CTAs per SM queued: 2 rounds of the 4 resident)
+            int grid = std::max(1, std::min(Blocks(limit), sc->sm_count * 8));
+            if (path) k_shade<RT_INTEGRATOR_PATH, true><<<grid, kBlock, 0, st>>>(sc->d, cam, rc, io);
+            else k_shade<RT_INTEGRATOR_REFERENCE, true><<<grid, kBlock, 0, st>>>(sc->d, cam, rc, io);
+        } else {
+            int grid = std::max(1, Blocks(limit));
+            if (path) k_shade<RT_INTEGRATOR_PATH, false><<<grid, kBlock, 0, st>>>(sc->d, cam, rc, io);
+            else k_shade<RT_INTEGRATOR_REFERENCE, false><<<grid, kBlock, 0, st>>>(sc->d, cam, rc, io);
+        }
+        launches++; n_shade++;
+    }
+    // Camera rays of one wave into level 0 + their closest hits.  Fused: one launch, slot = work item, `n` slots.  Unfused (A/B and
+    // the chunked driver): k_raygen compacts into level 0 and counts into level_count[0].
+    void LaunchPrimary(unsigned long long base, int n, bool fused) {
+        DCounters* c = pp->counters.p;
+        RaygenArgs a = rg;
+        a.base_rest = (unsigned)(base / (unsigned long long)cam.spp); a.base_sample = (unsigned)(base % (unsigned long long)cam.spp);
+        DRayQueue q0 = pp->levels[0].View();
+        if (fused) {
+            Timed(0, [&] {
+                TraceIO io{};
+                io.q = q0; io.count_ptr = nullptr; io.first = 0; io.limit = n; io.cursor = &c->cursor_extend[0]; io.flags = sc->trav_flags;
+                int grid = sc->full_grid ? Blocks(n) : std::min(Blocks(n), sc->grid_extend);
+                (count ? sc->k_rg_closest_count : sc->k_rg_closest)<<<std::max(1, grid), kBlock, count ? 0 : sc->trace_smem, st>>>(sc->d, io, c, a);
+                launches++; n_extend++;
+            });
+        } else {
+            Timed(0, [&] { k_raygen<<<Blocks(n), kBlock, 0, st>>>(a, n, q0, &c->level_count[0]); launches++; });
+            Timed(1, [&] { LaunchExtend(q0, &c->level_count[0], 0, n, &c->cursor_extend[0]); });
+        }
+    }
+
+    // ---- optimistic driver: whole levels, no host round trip.  Level L lives in queue buffer L % 2; its size is only known to
+    // the device (level_count[L]); grids are sized by what the level can hold at most.
+    void EnqueueWave(unsigned long long base, int n) {
+        DCounters* c = pp->counters.p;
+        const bool fused = sc->fused_raygen;
+        LaunchPrimary(base, n, fused);
+        long long upper = n;
+        const int nl = std::max(1, sc->d.num_lights);
+        for (int lv = 0; lv < nlev; lv++) {
+            DRayQueue q = pp->levels[lv % 2].View(), nq = pp->levels[(lv + 1) % 2].View();
+            const int32_t* cnt = (lv == 0 && fused) ? nullptr : &c->level_count[lv];
+            if (lv > 0) Timed(1, [&] { LaunchExtend(q, cnt, 0, (int)upper, &c->cursor_extend[lv]); });
+            Timed(2, [&] { LaunchShade(q, nq, cnt, 0, (int)upper, &c->level_count[lv + 1], &c->shadow_count[lv]); });
+            if (sc->d.num_lights > 0 || path) {
+                long long sup = std::min<long long>((long long)rc.shadow_cap, upper * nl);
+                Timed(3, [&] { LaunchShadow(&c->shadow_count[lv], (int)sup, &c->cursor_shadow[lv]); });
+            }
+            upper = std::min<long long>((long long)rc.queue_cap, branching ? upper * 2 : upper);
+        }
+        k_wave_end<<<1, 256, 0, st>>>(c, nlev);
+        launches++;
+    }
+
+    // ---- chunked driver (fallback): a level is processed in chunks sized so that neither the next level (<= 2 rays per ray when
+    // a dielectric can branch) nor the shadow queue (<= L per ray) can overflow; deeper levels get their own buffers, and the host
+    // reads the two queue sizes after every shade pass.  Recursion depth is bounded by the queue level count.
     void ProcessLevel(int lv, int n) {
-        QueueBufs& qb = pp->levels[lv % nlevels];
-        QueueBufs& nb = pp->levels[(lv + 1) % nlevels];
+        DCounters* c = pp->counters.p;
+        QueueBufs& qb = pp->levels[lv % nbuf];
+        QueueBufs& nb = pp->levels[(lv + 1) % nbuf];
         DRayQueue q = qb.View(), nq = nb.View();
         int nl = std::max(1, sc->d.num_lights);
-        // chunk so that neither the next level (<= 2 rays per ray when a dielectric can branch) nor the shadow queue can overflow
         long long by_next = branching ? (long long)rc.queue_cap / 2 : rc.queue_cap;
         long long by_shadow = (long long)rc.shadow_cap / nl;
         int chunk = (int)std::max(1LL, std::min(by_next, by_shadow));
         for (int first = 0; first < n; first += chunk) {
             int m = std::min(chunk, n - first);
-            CK(cudaMemsetAsync(&pp->counters.p->next_count, 0, 2 * sizeof(int32_t), st));
-            if (sc->persistent) CK(cudaMemsetAsync(&pp->counters.p->ray_cursor, 0, sizeof(int32_t), st));
-            Timed(&ms_extend, [&] {
-                if (sc->persistent) {
-                    TraceIO io{q.o_time, q.d_tmax, first, m, &pp->counters.p->ray_cursor, q.hit, q.hit_obj, nullptr, nullptr, sc->trav_flags};
-                    int grid = sc->full_grid ? Blocks(m) : std::min(Blocks(m), sc->grid_extend);
-                    if (count) k_trace_persistent<false, true><<<grid, kBlock, 0, st>>>(sc->d, io, pp->counters.p);
-                    else if (sc->d.tris_w) k_trace_persistent<false, false, false, true><<<grid, kBlock, 0, st>>>(sc->d, io, pp->counters.p);
-                    else k_trace_persistent<false, false><<<grid, kBlock, 0, st>>>(sc->d, io, pp->counters.p);
-                } else if (count) k_extend<true><<<Blocks(m), kBlock, 0, st>>>(sc->d, q, first, m, pp->counters.p);
-                else k_extend<false><<<Blocks(m), kBlock, 0, st>>>(sc->d, q, first, m, pp->counters.p);
-            });
-            Timed(&ms_shade, [&] {
-                if (rc.integrator == RT_INTEGRATOR_PATH) k_shade<RT_INTEGRATOR_PATH><<<Blocks(m), kBlock, 0, st>>>(sc->d, cam, rc, q, first, m, nq, sq, pp->counters.p, accum);
-                else k_shade<RT_INTEGRATOR_REFERENCE><<<Blocks(m), kBlock, 0, st>>>(sc->d, cam, rc, q, first, m, nq, sq, pp->counters.p, accum);
-            });
-            launches += 2; n_extend++; n_shade++;
-            CK(cudaMemcpyAsync(pp->h_counters, pp->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemsetAsync(&c->level_count[lv + 1], 0, sizeof(int32_t), st));
+            CK(cudaMemsetAsync(&c->shadow_count[lv], 0, sizeof(int32_t), st));
+            CK(cudaMemsetAsync(&c->cursor_extend[lv], 0, sizeof(int32_t), st));
+            CK(cudaMemsetAsync(&c->cursor_shadow[lv], 0, sizeof(int32_t), st));
+            Timed(1, [&] { LaunchExtend(q, nullptr, first, m, &c->cursor_extend[lv]); });
+            Timed(2, [&] { LaunchShade(q, nq, nullptr, first, m, &c->level_count[lv + 1], &c->shadow_count[lv]); });
+            CK(cudaMemcpyAsync(pp->h_counters, c, sizeof(DCounters), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             CK(cudaGetLastError());
-            int next_n = pp->h_counters->next_count, shadow_n = pp->h_counters->shadow_count;
+            int next_n = pp->h_counters->level_count[lv + 1], shadow_n = pp->h_counters->shadow_count[lv];
             if (pp->h_counters->overflow) throw Invalid{"ray queue overflow (raise queue_capacity)"};
             if (shadow_n > 0) {
-                if (sc->persistent) CK(cudaMemsetAsync(&pp->counters.p->ray_cursor, 0, sizeof(int32_t), st));
-                Timed(&ms_shadow, [&] {
-                    if (sc->persistent) {
-                        TraceIO io{sq.o_time, sq.d_tmax, 0, shadow_n, &pp->counters.p->ray_cursor, nullptr, nullptr, sq.c_pixel, accum, sc->trav_flags_shadow};
-                        int grid = sc->full_grid ? Blocks(shadow_n) : std::min(Blocks(shadow_n), sc->grid_shadow);
-                        if (count) k_trace_persistent<true, true><<<grid, kBlock, 0, st>>>(sc->d, io, pp->counters.p);
-                        else if (sc->quantised_occlusion) k_trace_persistent<true, false, true><<<grid, kBlock, 0, st>>>(sc->d, io, pp->counters.p);
-                        else if (sc->d.tris_w) k_trace_persistent<true, false, false, true><<<grid, kBlock, 0, st>>>(sc->d, io, pp->counters.p);
-                        else k_trace_persistent<true, false><<<grid, kBlock, 0, st>>>(sc->d, io, pp->counters.p);
-                    } else if (count) k_shadow<true><<<Blocks(shadow_n), kBlock, 0, st>>>(sc->d, sq, shadow_n, accum, pp->counters.p);
-                    else k_shadow<false><<<Blocks(shadow_n), kBlock, 0, st>>>(sc->d, sq, shadow_n, accum, pp->counters.p);
-                });
-                launches++; n_shadow++;
+                Timed(3, [&] { LaunchShadow(nullptr, shadow_n, &c->cursor_shadow[lv]); });
                 shadow += (uint64_t)shadow_n;
             }
-            if (next_n > 0) {
+            if (next_n > 0 && lv + 1 < nlev) {
                 secondary += (uint64_t)next_n;
                 ProcessLevel(lv + 1, next_n);
             }
         }
     }
+    void ChunkedWave(unsigned long long base, int n) {
+        DCounters* c = pp->counters.p;
+        CK(cudaMemsetAsync(c, 0, offsetof(DCounters, overflow), st));
+        LaunchPrimaryUnfusedOnly(base, n);
+        CK(cudaMemcpyAsync(pp->h_counters, c, sizeof(DCounters), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        int n0 = pp->h_counters->level_count[0];
+        if (n0 > 0) ProcessLevel0(n0);
+    }
+    void LaunchPrimaryUnfusedOnly(unsigned long long base, int n) {
+        RaygenArgs a = rg;
+        a.base_rest = (unsigned)(base / (unsigned long long)cam.spp); a.base_sample = (unsigned)(base % (unsigned long long)cam.spp);
+        Timed(0, [&] { k_raygen<<<Blocks(n), kBlock, 0, st>>>(a, n, pp->levels[0].View(), &pp->counters.p->level_count[0]); launches++; });
+    }
+    void ProcessLevel0(int n0) { ProcessLevel(0, n0); }
 };
 
-void EnsureRenderBuffers(RtScene* sc, const RtRenderOpts* opts, int nlevels, size_t npix3, int npipe) {
+size_t QueueCapacity(const RtRenderOpts* opts) {
     // default 4 Mi rays per wave.  Every launch ends in a tail where the last rays finish on a mostly idle GPU; measured on C4
     // with ONE pipeline: 1 Mi 83.7 ms, 2 Mi 73.6, 4 Mi 67.6, 8 Mi 65.2, 16 Mi 64.9 per frame.  With two pipelines the tails
     // overlap with the other wave and the size matters little: 2 x 4 Mi 61.8, 2 x 8 Mi 62.9, 4 x 4 Mi 61.6, 3 x 16 Mi 63.7.
     size_t cap = opts->queue_capacity > 0 ? (size_t)opts->queue_capacity : ((size_t)1 << 22);
-    if (opts->queue_capacity <= 0) if (const char* e = getenv("RT795_QUEUE_CAP")) cap = (size_t)atoll(e);   // tuning override of the default
-    cap = std::max<size_t>(cap, 64);
-    size_t scap = (size_t)std::min(8, std::max(2, sc->d.num_lights)) * cap;   // a shade pass over `cap` rays emits <= num_lights shadow rays per ray
+    if (opts->queue_capacity <= 0) if (const char* e = getenv("RT795_QUEUE_CAP")) { long long v = atoll(e); if (v > 0) cap = (size_t)v; }   // tuning override of the default
+    return std::min<size_t>(std::max<size_t>(cap, 64), (size_t)1 << 28);
+}
+
+// Queue memory: 84 B per ray and level, 48 B per shadow-queue entry, per pipeline.  `nbuf` level buffers of `cap` rays each.  When
+// deep recursion asks for many level buffers (chunked driver: one per depth), the capacity shrinks so that the queues stay inside
+// a fixed share of the device memory that is free right now - MaxRecursionDepth 50 no longer asks for 37 GB.
+void EnsureRenderBuffers(RtScene* sc, const RtRenderOpts* opts, int nbuf, size_t npix3, int npipe) {
+    size_t cap = QueueCapacity(opts);
+    const size_t lights = (size_t)std::min(8, std::max(2, sc->d.num_lights));
+    if (nbuf > 2) {
+        size_t free_b = 0, total_b = 0, held = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        for (Pipe& pp : sc->pipes) { for (auto& l : pp.levels) held += l.o_time.n * 84; held += pp.sq_o.n * 48; }
+        size_t budget = (free_b + held) / 3;
+        size_t per_ray = (size_t)npipe * ((size_t)nbuf * 84 + lights * 48);
+        if (cap * per_ray > budget) cap = std::max<size_t>(1024, budget / per_ray);
+    }
+    size_t scap = lights * cap;   // a shade pass over `cap` rays emits <= num_lights shadow rays per ray
     sc->queue_cap = cap; sc->shadow_cap = scap;
     sc->accum.Alloc(npix3);
     for (int p = 0; p < npipe; p++) {
         Pipe& pp = sc->pipes[p];
         if (!pp.st) CK(cudaStreamCreateWithFlags(&pp.st, cudaStreamNonBlocking));
         if (!pp.done) CK(cudaEventCreateWithFlags(&pp.done, cudaEventDisableTiming));
-        if ((int)pp.levels.size() < nlevels) pp.levels.resize(nlevels);
-        for (int i = 0; i < nlevels; i++) pp.levels[i].Alloc(cap);
+        if ((int)pp.levels.size() < nbuf) pp.levels.resize(nbuf);
+        for (int i = 0; i < nbuf; i++) pp.levels[i].Alloc(cap);
         pp.sq_o.Alloc(scap); pp.sq_d.Alloc(scap); pp.sq_c.Alloc(scap);
         pp.counters.Alloc(1);
         if (!pp.h_counters) CK(cudaMallocHost((void**)&pp.h_counters, sizeof(DCounters)));
@@ -600,6 +712,17 @@ DTiling MakeTiling(const RtCameraDesc* cam, const RtRenderOpts* opts) {
     return t;
 }
 
+// Pixels of this rank's tiles that lie inside the image (tiles are cut by the right / bottom edge).
+unsigned long long OwnedPixels(const DTiling& t, int nx, int ny) {
+    unsigned long long px = 0;
+    for (int lt = 0; lt < t.local_tiles; lt++) {
+        int k = lt * t.count + t.rank;
+        int x0 = (k % t.tiles_x) * t.tw, y0 = (k / t.tiles_x) * t.th;
+        px += (unsigned long long)std::max(0, std::min(t.tw, nx - x0)) * (unsigned long long)std::max(0, std::min(t.th, ny - y0));
+    }
+    return px;
+}
+
 void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts_in, float* d_out, cudaStream_t user_stream) {
     if (!cam || cam->nx < 1 || cam->ny < 1) throw Invalid{"bad camera resolution"};
     RtRenderOpts opts;
@@ -613,79 +736,108 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
     proto.count = (opts.collect_counters & 2) != 0;
     proto.stage_time = (opts.collect_counters & 1) != 0;
     bool path = opts.integrator == RT_INTEGRATOR_PATH;
+    proto.path = path;
     int max_depth = path ? (opts.pt_max_depth > 0 ? opts.pt_max_depth : sc->d.max_depth) : sc->d.max_depth;
     if (max_depth < 0) max_depth = 0;
     if (max_depth > 250) throw Invalid{"recursion depth above 250 is not supported"};
     proto.branching = !path && sc->has_dielectric && max_depth > 0;
-    // Two ping-pong levels suffice when a level is always processed in ONE chunk (no branching and the shadow queue can take
-    // a full level); otherwise deeper levels must not overwrite a level that still has unprocessed chunks.
-    proto.nlevels = (proto.branching || sc->d.num_lights > 8) ? max_depth + 2 : 2;
+    // levels a wave can have: camera rays + one per bounce; a Whitted scene without mirror / conductor / dielectric has one
+    proto.nlev = path ? max_depth + 1 : (sc->has_specular ? max_depth + 1 : 1);
     size_t npix3 = (size_t)cam->nx * cam->ny * 3;
-
-    size_t cap_hint = opts.queue_capacity > 0 ? (size_t)opts.queue_capacity : ((size_t)1 << 22);
-    if (opts.queue_capacity <= 0) if (const char* e = getenv("RT795_QUEUE_CAP")) cap_hint = (size_t)atoll(e);
     if ((unsigned long long)proto.tl.local_tiles * proto.tl.tw * proto.tl.th >= (1ull << 32)) throw Invalid{"frame too large: more than 2^32 pixel slots per rank"};
-    unsigned long long total = (unsigned long long)proto.tl.local_tiles * proto.tl.tw * proto.tl.th * (unsigned long long)proto.cam.spp;
-    // one pipeline when stages are timed / counted (clean per-stage numbers) or the frame is a single wave
-    unsigned long long wave_hint = opts.wave_rays > 0 ? (unsigned long long)opts.wave_rays : (unsigned long long)cap_hint;
-    int npipe = (proto.stage_time || proto.count) ? 1 : (int)std::min<unsigned long long>((unsigned long long)sc->npipes_wanted, (total + wave_hint - 1) / wave_hint);
-    npipe = std::max(1, npipe);
-    EnsureRenderBuffers(sc, &opts, proto.nlevels, npix3, npipe);
+    const unsigned long long total = (unsigned long long)proto.tl.local_tiles * proto.tl.tw * proto.tl.th * (unsigned long long)proto.cam.spp;
+    const unsigned long long owned = OwnedPixels(proto.tl, cam->nx, cam->ny) * (unsigned long long)proto.cam.spp;
+
     proto.rc.seed = opts.seed; proto.rc.integrator = opts.integrator; proto.rc.pt_max_depth = max_depth; proto.rc.pt_nee = opts.pt_nee; proto.rc.pt_rr = opts.pt_russian_roulette;
-    proto.rc.pt_importance = opts.pt_importance; proto.rc.queue_cap = (int)sc->queue_cap; proto.rc.shadow_cap = (int)sc->shadow_cap;
-    proto.accum = sc->accum.p;
+    proto.rc.pt_importance = opts.pt_importance;
+    proto.rg.cam = proto.cam; proto.rg.tl = proto.tl; proto.rg.seed = opts.seed; proto.rg.max_depth = max_depth; proto.rg.base_rest = proto.rg.base_sample = 0; proto.rg.center_only = 0;
 
-    int wave = opts.wave_rays > 0 ? opts.wave_rays : (int)sc->queue_cap;
-    wave = (int)std::min<size_t>((size_t)wave, sc->queue_cap);
-    wave = std::max(32, wave / 32 * 32);
+    struct FrameResult { uint64_t waves = 0, launches = 0, n_extend = 0, n_shade = 0, n_shadow = 0, secondary = 0, shadow = 0; bool overflow = false; int npipe = 1; double ms[4] = {0, 0, 0, 0}; };
 
-    CK(cudaEventRecord(sc->ev0, st));
-    CK(cudaMemsetAsync(sc->accum.p, 0, npix3 * sizeof(float), st));
-    CK(cudaEventRecord(sc->ev_start, st));
+    // One attempt at the frame.  chunked = false: everything is enqueued without a host round trip and the device's overflow flag is
+    // read once at the end.
+    auto attempt = [&](bool chunked, FrameResult& fr) {
+        const size_t cap_hint = QueueCapacity(&opts);
+        unsigned long long wave_hint = opts.wave_rays > 0 ? (unsigned long long)opts.wave_rays : (unsigned long long)cap_hint;
+        if (!chunked && sc->wave_limit) wave_hint = std::min<unsigned long long>(wave_hint, sc->wave_limit);
+        // one pipeline when stages are timed / counted (clean per-stage numbers), in the chunked driver, or when the frame is a single wave
+        int npipe = (proto.stage_time || proto.count || chunked) ? 1 : (int)std::min<unsigned long long>((unsigned long long)sc->npipes_wanted, (total + wave_hint - 1) / std::max<unsigned long long>(1, wave_hint));
+        npipe = std::max(1, npipe);
+        const int nbuf = chunked ? ((proto.branching || sc->d.num_lights > 8) ? proto.nlev + 1 : 2) : 2;
+        EnsureRenderBuffers(sc, &opts, nbuf, npix3, npipe);
+        proto.nbuf = nbuf;
+        proto.rc.queue_cap = (int)sc->queue_cap; proto.rc.shadow_cap = (int)sc->shadow_cap;
+        proto.accum = sc->accum.p;
+        int wave = (int)std::min<unsigned long long>(wave_hint, (unsigned long long)sc->queue_cap);
+        wave = std::max(32, wave / 32 * 32);
+        fr = FrameResult();
+        fr.npipe = npipe;
 
-    struct PipeResult { uint64_t primary = 0, waves = 0; double ms_raygen = 0; std::exception_ptr err; };
-    Driver drs[kPipes];
-    PipeResult res[kPipes];
-    auto run_pipe = [&](int p) {
-        try {
-            CK(cudaSetDevice(sc->device));
+        CK(cudaMemsetAsync(sc->accum.p, 0, npix3 * sizeof(float), st));
+        CK(cudaEventRecord(sc->ev_start, st));
+        Driver drs[kPipes];
+        StageEvents sev[kPipes];
+        for (int p = 0; p < npipe; p++) {
             Driver& dr = drs[p];
             dr = proto;
             dr.pp = &sc->pipes[p];
             dr.st = dr.pp->st;
+            dr.sev = &sev[p];
             dr.sq = DShadowQueue{dr.pp->sq_o.p, dr.pp->sq_d.p, dr.pp->sq_c.p};
-            cudaStream_t ps = dr.st;
-            CK(cudaStreamWaitEvent(ps, sc->ev_start, 0));              // after the accumulator was cleared on the caller's stream
-            CK(cudaMemsetAsync(dr.pp->counters.p, 0, sizeof(DCounters), ps));
-            unsigned long long w = 0;
-            for (unsigned long long base = 0; base < total; base += (unsigned long long)wave, w++) {
-                if ((int)(w % (unsigned long long)npipe) != p) continue;
-                int n = (int)std::min<unsigned long long>((unsigned long long)wave, total - base);
-                CK(cudaMemsetAsync(&dr.pp->counters.p->next_count, 0, sizeof(int32_t), ps));
-                dr.Timed(&res[p].ms_raygen, [&] {
-                    k_raygen<<<Blocks(n), kBlock, 0, ps>>>(dr.cam, dr.tl, dr.rc, max_depth, (unsigned)(base / (unsigned long long)dr.cam.spp), (unsigned)(base % (unsigned long long)dr.cam.spp), n, dr.pp->levels[0].View(), &dr.pp->counters.p->next_count, 0);
-                });
-                dr.launches++;
-                CK(cudaMemcpyAsync(dr.pp->h_counters, dr.pp->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost, ps));
-                CK(cudaStreamSynchronize(ps));
-                int n0 = dr.pp->h_counters->next_count;
-                res[p].primary += (uint64_t)n0; res[p].waves++;
-                if (n0 > 0) dr.ProcessLevel(0, n0);
-            }
-            CK(cudaEventRecord(dr.pp->done, ps));
-        } catch (...) { res[p].err = std::current_exception(); }
+            CK(cudaStreamWaitEvent(dr.st, sc->ev_start, 0));          // after the accumulator was cleared on the caller's stream
+            CK(cudaMemsetAsync(dr.pp->counters.p, 0, sizeof(DCounters), dr.st));
+        }
+        unsigned long long w = 0;
+        for (unsigned long long base = 0; base < total; base += (unsigned long long)wave, w++) {
+            Driver& dr = drs[w % (unsigned long long)npipe];
+            int n = (int)std::min<unsigned long long>((unsigned long long)wave, total - base);
+            if (chunked) dr.ChunkedWave(base, n); else dr.EnqueueWave(base, n);
+            fr.waves++;
+        }
+        for (int p = 0; p < npipe; p++) {
+            Pipe& pp = sc->pipes[p];
+            CK(cudaMemcpyAsync(pp.h_counters, pp.counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost, pp.st));
+            CK(cudaEventRecord(pp.done, pp.st));
+        }
+        for (int p = 0; p < npipe; p++) CK(cudaStreamWaitEvent(st, sc->pipes[p].done, 0));
+        for (int p = 0; p < npipe; p++) CK(cudaStreamSynchronize(sc->pipes[p].st));   // the one host wait of the frame (counters + overflow flag)
+        CK(cudaGetLastError());
+        for (int p = 0; p < npipe; p++) {
+            const Driver& dr = drs[p];
+            const DCounters* hc = sc->pipes[p].h_counters;
+            fr.launches += dr.launches; fr.n_extend += dr.n_extend; fr.n_shade += dr.n_shade; fr.n_shadow += dr.n_shadow;
+            if (chunked) { fr.secondary += dr.secondary; fr.shadow += dr.shadow; }
+            else { fr.secondary += hc->total_secondary; fr.shadow += hc->total_shadow; }
+            if (hc->overflow) fr.overflow = true;
+            for (int k = 0; k < 4; k++)
+                for (auto& e : sev[p].ev[k]) {
+                    float ms = 0; CK(cudaEventElapsedTime(&ms, e.first, e.second));
+                    fr.ms[k] += ms;
+                    cudaEventDestroy(e.first); cudaEventDestroy(e.second);
+                }
+        }
     };
-    if (npipe == 1) run_pipe(0);
-    else {
-        std::vector<std::thread> workers;
-        for (int p = 1; p < npipe; p++) workers.emplace_back([&, p] { run_pipe(p); });
-        run_pipe(0);
-        for (auto& t : workers) t.join();
+
+    {   // what earlier frames learnt about overflows holds for the queue capacity it was learnt with
+        size_t cap_now = QueueCapacity(&opts);
+        if (cap_now != sc->learnt_cap) { sc->learnt_cap = cap_now; sc->wave_limit = 0; sc->force_chunked = sc->env_chunked; }
     }
-    for (int p = 0; p < npipe; p++) if (res[p].err) { for (int q = 0; q < npipe; q++) cudaStreamSynchronize(sc->pipes[q].st); std::rethrow_exception(res[p].err); }
-    for (int p = 0; p < npipe; p++) CK(cudaStreamWaitEvent(st, sc->pipes[p].done, 0));
+    CK(cudaEventRecord(sc->ev0, st));
+    FrameResult fr;
+    bool chunked = sc->force_chunked;
+    for (;;) {
+        attempt(chunked, fr);
+        if (!fr.overflow) break;
+        if (chunked) throw Invalid{"ray queue overflow (raise queue_capacity)"};
+        // a level outgrew its queue: redo the frame with half the wave (remembered for the scene's next frames)
+        size_t cur = sc->wave_limit ? sc->wave_limit : (size_t)std::min<unsigned long long>(opts.wave_rays > 0 ? (unsigned long long)opts.wave_rays : ~0ull, (unsigned long long)sc->queue_cap);
+        sc->wave_limit = cur / 2;
+        if (sc->wave_limit < kMinOptimisticWave) { sc->force_chunked = true; chunked = true; }
+    }
     double ms_resolve = 0;
-    proto.Timed(&ms_resolve, [&] {
+    {
+        cudaEvent_t ra = nullptr, rb = nullptr;
+        if (proto.stage_time) { CK(cudaEventCreate(&ra)); CK(cudaEventCreate(&rb)); CK(cudaEventRecord(ra, st)); }
         float inv_spp = 1.0f / (float)proto.cam.spp;
         if (opts.resolve_owned_only && proto.tl.count > 1) {
             long long n = (long long)proto.tl.local_tiles * proto.tl.th * (proto.tl.tw >> 2);
@@ -693,31 +845,27 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
         } else {
             k_resolve<<<Blocks((long long)npix3), kBlock, 0, st>>>(sc->accum.p, d_out, (int)npix3, inv_spp);
         }
-    });
+        if (proto.stage_time) { CK(cudaEventRecord(rb, st)); CK(cudaEventSynchronize(rb)); float ms = 0; CK(cudaEventElapsedTime(&ms, ra, rb)); ms_resolve = ms; cudaEventDestroy(ra); cudaEventDestroy(rb); }
+    }
     CK(cudaEventRecord(sc->ev1, st));
     CK(cudaEventSynchronize(sc->ev1));
     CK(cudaGetLastError());
     float ms = 0; CK(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1));
     RtStats& s = sc->stats;
-    s.rays_primary = s.rays_secondary = s.rays_shadow = s.launches = s.waves = 0;
-    s.ms_extend = s.ms_shade = s.ms_shadow = s.ms_raygen = 0;
-    s.launches_extend = s.launches_shade = s.launches_shadow = 0;
+    s.rays_primary = owned; s.rays_secondary = fr.secondary; s.rays_shadow = fr.shadow; s.launches = fr.launches + 1 /* k_resolve */; s.waves = fr.waves;
+    const bool fused_used = sc->fused_raygen && !chunked;         // K1 ran inside the first closest-hit launch of each wave
+    s.ms_raygen = fused_used ? 0.0 : fr.ms[0]; s.ms_extend = fr.ms[1] + (fused_used ? fr.ms[0] : 0.0); s.ms_shade = fr.ms[2]; s.ms_shadow = fr.ms[3];
+    s.launches_extend = fr.n_extend; s.launches_shade = fr.n_shade; s.launches_shadow = fr.n_shadow;
     s.node_visits = s.prim_tests = s.node_visits_shadow = s.prim_tests_shadow = 0;
     for (int k = 0; k < 8; k++) s.diag[k] = 0;
-    for (int p = 0; p < npipe; p++) {
-        const Driver& dr = drs[p];
-        s.rays_primary += res[p].primary; s.rays_secondary += dr.secondary; s.rays_shadow += dr.shadow; s.launches += dr.launches; s.waves += res[p].waves;
-        s.ms_extend += dr.ms_extend; s.ms_shade += dr.ms_shade; s.ms_shadow += dr.ms_shadow; s.ms_raygen += res[p].ms_raygen;
-        s.launches_extend += dr.n_extend; s.launches_shade += dr.n_shade; s.launches_shadow += dr.n_shadow;
-        if (proto.count) {
-            Pipe& pp = sc->pipes[p];
-            CK(cudaMemcpy(pp.h_counters, pp.counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost));
-            s.node_visits += pp.h_counters->node_visits; s.prim_tests += pp.h_counters->prim_tests;
-            s.node_visits_shadow += pp.h_counters->node_visits_shadow; s.prim_tests_shadow += pp.h_counters->prim_tests_shadow;
-            for (int k = 0; k < 8; k++) s.diag[k] += pp.h_counters->diag[k];
+    if (proto.count) {
+        for (int p = 0; p < fr.npipe; p++) {
+            const DCounters* hc = sc->pipes[p].h_counters;
+            s.node_visits += hc->node_visits; s.prim_tests += hc->prim_tests;
+            s.node_visits_shadow += hc->node_visits_shadow; s.prim_tests_shadow += hc->prim_tests_shadow;
+            for (int k = 0; k < 8; k++) s.diag[k] += hc->diag[k];
         }
     }
-    s.launches += 1;   // k_resolve
     s.ms_total = ms; s.ms_resolve = ms_resolve;
 }
 
@@ -765,28 +913,41 @@ int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out) {
         CK(cudaEventCreate(&sc->ev0)); CK(cudaEventCreate(&sc->ev1)); CK(cudaEventCreateWithFlags(&sc->ev_start, cudaEventDisableTiming));
         if (const char* e = getenv("RT795_PIPES")) sc->npipes_wanted = std::min(kPipes, std::max(1, atoi(e)));
         {
-            const char* tv = getenv("RT795_TRAVERSAL");
-            sc->persistent = !(tv && std::string(tv) == "classic");
             if (const char* f = getenv("RT795_TRAVERSAL_FLAGS")) sc->trav_flags = sc->trav_flags_shadow = atoi(f);
             if (const char* f = getenv("RT795_FLAGS_CLOSEST")) sc->trav_flags = atoi(f);
             if (const char* f = getenv("RT795_FLAGS_OCCLUSION")) sc->trav_flags_shadow = atoi(f);
             if (const char* g = getenv("RT795_FULL_GRID")) sc->full_grid = atoi(g) != 0;
             if (const char* q = getenv("RT795_QNODES")) sc->quantised_occlusion = atoi(q) != 0;
-            if (const char* q = getenv("RT795_AFFINE_TRIS")) sc->affine_tris = atoi(q) != 0;
+            if (const char* q = getenv("RT795_DEBUG_BVH")) sc->keep_debug_bvh = atoi(q) != 0;
+            if (const char* q = getenv("RT795_SMEM_TLAS")) sc->smem_tlas = atoi(q) != 0;
+            if (const char* q = getenv("RT795_FUSED_RAYGEN")) sc->fused_raygen = atoi(q) != 0;
+            if (const char* q = getenv("RT795_DRIVER")) sc->env_chunked = sc->force_chunked = !strcmp(q, "chunked");
+            sc->k_closest_count = k_trace_persistent<false, true, 0>; sc->k_any_count = k_trace_persistent<true, true, 0>;
+            sc->k_rg_closest_count = k_raygen_trace<true, 0>;
             cudaDeviceProp prop;
             CK(cudaGetDeviceProperties(&prop, device));
-            int be = 1, bs = 1;
-            if (sc->affine_tris) {
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_persistent<false, false, false, true>, kBlock, 0));
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_trace_persistent<true, false, false, true>, kBlock, 0));
-            } else {
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_persistent<false, false>, kBlock, 0));
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, k_trace_persistent<true, false>, kBlock, 0));
-            }
-            sc->grid_extend = prop.multiProcessorCount * std::max(1, be);
-            sc->grid_shadow = prop.multiProcessorCount * std::max(1, bs);
+            sc->sm_count = prop.multiProcessorCount;
         }
         if (!BuildAndUpload(sc, desc, true)) BuildAndUpload(sc, desc, false);
+        {
+            // kernel variants: the top level (TLAS nodes + transform records) is staged in shared memory when it fits
+            int stage_bytes = (sc->d.tlas_nodes * 8 + sc->d.num_objects * 4) * 16;
+            bool smem = sc->smem_tlas && stage_bytes <= kSmemTlasBytes;
+            sc->trace_smem = smem ? stage_bytes : 0;
+            if (smem) {
+                sc->k_closest = k_trace_persistent<false, false, TF_SMEM_TLAS>; sc->k_any = k_trace_persistent<true, false, TF_SMEM_TLAS>;
+                sc->k_rg_closest = k_raygen_trace<false, TF_SMEM_TLAS>;
+            } else {
+                sc->k_closest = k_trace_persistent<false, false, 0>; sc->k_any = k_trace_persistent<true, false, 0>;
+                sc->k_rg_closest = k_raygen_trace<false, 0>;
+            }
+            if (sc->quantised_occlusion) sc->k_any = k_trace_persistent<true, false, TF_QNODES>;
+            int be = 1, bs = 1;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, sc->k_closest, kBlock, sc->trace_smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, sc->k_any, kBlock, sc->quantised_occlusion ? 0 : sc->trace_smem));
+            sc->grid_extend = sc->sm_count * std::max(1, be);
+            sc->grid_shadow = sc->sm_count * std::max(1, bs);
+        }
     });
     if (rcode != RT_OK) { if (sc) rt_scene_destroy(sc); return rcode; }
     *out = sc;
@@ -802,6 +963,7 @@ void rt_scene_destroy(RtScene* sc) {
         if (pp.h_counters) cudaFreeHost(pp.h_counters);
         if (pp.done) cudaEventDestroy(pp.done);
     }
+    if (sc->h_stage) cudaFreeHost(sc->h_stage);
     if (sc->ev_start) cudaEventDestroy(sc->ev_start);
     if (sc->ev0) cudaEventDestroy(sc->ev0);
     if (sc->ev1) cudaEventDestroy(sc->ev1);
@@ -826,14 +988,48 @@ int rt_render(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts, fl
         if (opts && opts->resolve_owned_only) throw Invalid{"resolve_owned_only is for rt_render_device (the host frame of rt_render is written whole)"};
         sc->out_dev.Alloc(n);
         RenderDevice(sc, cam, opts, sc->out_dev.p, nullptr);
-        CK(cudaMemcpyAsync(out_rgb, sc->out_dev.p, n * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
-        CK(cudaStreamSynchronize(sc->stream));
+        // The caller's frame is ordinary pageable memory in the reference (new float[], src/Image.cpp:8): a direct D2H copy into it
+        // goes through the driver's small bounce buffers.  Stage through the library's own pinned buffer in 4 MiB pieces instead,
+        // the host memcpy of one piece overlapping the DMA of the next.
+        {
+            // a caller that already hands over page-locked memory (cudaHostAlloc / cudaHostRegister) gets the plain DMA
+            cudaPointerAttributes pa;
+            if (cudaPointerGetAttributes(&pa, out_rgb) == cudaSuccess && pa.type == cudaMemoryTypeHost) {
+                CK(cudaMemcpyAsync(out_rgb, sc->out_dev.p, n * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
+                CK(cudaStreamSynchronize(sc->stream));
+                return;
+            }
+            cudaGetLastError();
+        }
+        if (sc->h_stage_n < n) {
+            if (sc->h_stage) { cudaFreeHost(sc->h_stage); sc->h_stage = nullptr; sc->h_stage_n = 0; }
+            CK(cudaMallocHost((void**)&sc->h_stage, n * sizeof(float)));
+            sc->h_stage_n = n;
+        }
+        const size_t piece = (size_t)1 << 20;   // floats
+        size_t npieces = (n + piece - 1) / piece;
+        std::vector<cudaEvent_t> evs(npieces);
+        for (size_t k = 0; k < npieces; k++) {
+            size_t off = k * piece, cnt = std::min(piece, n - off);
+            CK(cudaMemcpyAsync(sc->h_stage + off, sc->out_dev.p + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
+            CK(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
+            CK(cudaEventRecord(evs[k], sc->stream));
+        }
+        for (size_t k = 0; k < npieces; k++) {
+            size_t off = k * piece, cnt = std::min(piece, n - off);
+            cudaError_t e = cudaEventSynchronize(evs[k]);
+            cudaEventDestroy(evs[k]);
+            if (e != cudaSuccess) { for (size_t j = k + 1; j < npieces; j++) cudaEventDestroy(evs[j]); CK(e); }
+            memcpy(out_rgb + off, sc->h_stage + off, cnt * sizeof(float));
+        }
     });
 }
 
 int rt_trace_primary(RtScene* sc, const RtCameraDesc* cam, RtHit* out_hits) {
     if (!sc || !cam || !out_hits) { SetLastError("rt_trace_primary: null argument"); return RT_ERR_INVALID; }
     return Guard("rt_trace_primary", [&] {
+        // Same kernels and acceleration structures as a frame: fused raygen (pixel centres) + persistent closest-hit traversal of the
+        // 4-wide BVH over the affine triangle maps, then one record per pixel.
         CK(cudaSetDevice(sc->device));
         cudaStream_t st = sc->stream;
         RtRenderOpts opts; memset(&opts, 0, sizeof opts);
@@ -843,21 +1039,20 @@ int rt_trace_primary(RtScene* sc, const RtCameraDesc* cam, RtHit* out_hits) {
         Pipe* pp = &sc->pipes[0];
         sc->hits_dev.Alloc(npix);
         CK(cudaMemsetAsync(sc->hits_dev.p, 0, npix * sizeof(RtHit), st));
-        DCamera dc; CameraSetup(cam, &dc);
-        DTiling tl = MakeTiling(cam, &opts);
-        RenderConsts rc; memset(&rc, 0, sizeof rc);
+        RaygenArgs rg; memset(&rg, 0, sizeof rg);
+        CameraSetup(cam, &rg.cam);
+        rg.tl = MakeTiling(cam, &opts);
+        rg.center_only = 1;
         int wave = (int)sc->queue_cap / 32 * 32;
-        unsigned long long total = (unsigned long long)tl.local_tiles * tl.tw * tl.th;
+        unsigned long long total = (unsigned long long)rg.tl.local_tiles * rg.tl.tw * rg.tl.th;
         for (unsigned long long base = 0; base < total; base += (unsigned long long)wave) {
             int n = (int)std::min<unsigned long long>((unsigned long long)wave, total - base);
             CK(cudaMemsetAsync(pp->counters.p, 0, sizeof(DCounters), st));
-            k_raygen<<<Blocks(n), kBlock, 0, st>>>(dc, tl, rc, 0, (unsigned)base, 0u, n, pp->levels[0].View(), &pp->counters.p->next_count, 1);
-            CK(cudaMemcpyAsync(pp->h_counters, pp->counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            int n0 = pp->h_counters->next_count;
-            if (n0 <= 0) continue;
-            k_extend<false><<<Blocks(n0), kBlock, 0, st>>>(sc->d, pp->levels[0].View(), 0, n0, pp->counters.p);
-            k_primary_hits<<<Blocks(n0), kBlock, 0, st>>>(sc->d, pp->levels[0].View(), n0, sc->hits_dev.p);
+            rg.base_rest = (unsigned)base; rg.base_sample = 0;
+            TraceIO io{};
+            io.q = pp->levels[0].View(); io.count_ptr = nullptr; io.first = 0; io.limit = n; io.cursor = &pp->counters.p->cursor_extend[0]; io.flags = sc->trav_flags;
+            sc->k_rg_closest<<<std::max(1, std::min(Blocks(n), sc->grid_extend)), kBlock, sc->trace_smem, st>>>(sc->d, io, pp->counters.p, rg);
+            k_primary_hits<<<Blocks(n), kBlock, 0, st>>>(sc->d, pp->levels[0].View(), n, sc->hits_dev.p);
         }
         CK(cudaMemcpyAsync(out_hits, sc->hits_dev.p, npix * sizeof(RtHit), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -917,9 +1112,13 @@ int rt_debug_read_bvh(RtScene* sc, int what, void* out, uint64_t capacity_bytes,
         CK(cudaSetDevice(sc->device));
         const void* src = nullptr; uint64_t bytes = 0; int32_t root = 0;
         switch (what) {
-            case RT_DEBUG_BVH2: src = sc->nodes.p; bytes = (uint64_t)(sc->stats.bvh2_nodes) * 64; root = sc->d.tlas_root; break;
+            case RT_DEBUG_BVH2:
+                if (!sc->keep_debug_bvh) throw Invalid{"the binary BVH is not resident: set RT795_DEBUG_BVH=1 before rt_scene_create"};
+                src = sc->nodes2_debug.p; bytes = (uint64_t)(sc->stats.bvh2_nodes) * 64; root = sc->tlas_base2; break;
             case RT_DEBUG_BVH4: src = sc->nodes4.p; bytes = sc->stats.bvh_nodes * 128; root = sc->d.tlas_root4; break;
-            case RT_DEBUG_BVH4Q: src = sc->nodes4q.p; bytes = sc->stats.bvh_nodes * 64; root = sc->d.tlas_root4; break;
+            case RT_DEBUG_BVH4Q:
+                if (!sc->nodes4q.p) throw Invalid{"the quantised nodes are not resident: set RT795_DEBUG_BVH=1 (or RT795_QNODES=1) before rt_scene_create"};
+                src = sc->nodes4q.p; bytes = sc->stats.bvh_nodes * 64; root = sc->d.tlas_root4; break;
             case RT_DEBUG_TRIS: src = sc->tris.p; bytes = sc->stats.tri_bytes; break;
             case RT_DEBUG_OBJ_ROOT4: src = sc->obj_root4.p; bytes = (uint64_t)std::max(1, sc->d.num_objects) * 4; break;
             default: throw Invalid{"rt_debug_read_bvh: unknown array"};

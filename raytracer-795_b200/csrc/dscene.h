@@ -6,13 +6,16 @@
 
 namespace rt795 {
 
-constexpr int kStackSize = 64;          // traversal stack entries per thread (node, t_entry); core.cu checks both BVHs against it
+constexpr int kStackSize = 64;          // traversal stack entries per thread (node, t_entry); core.cu checks the BVH against it
 constexpr int kMaxLights = 1 << 16;
+constexpr int kMaxLevels = 256;         // ray-tree levels per wave (recursion depth <= 250, core.cu)
+constexpr int kSmemTlasBytes = 8192;    // TLAS nodes (128 B) + top-level transform records (64 B) the traversal kernels stage in shared memory;
+                                        // a larger top level is walked in global memory
 
 // Traversal record of a top-level entry: 64 bytes = the "64-B instance record" of SURVEY §8d.
 struct DObjectXf {
     float4 inv0, inv1, inv2;            // rows of M^-1 (3x4): o' = inv*(o - blur*time, 1), d' = inv*(d, 0)  (src/Helper.cpp:110-133)
-    float4 blur_root;                   // blur.xyz ; w = bits(int): BLAS root node index, or ~sphere index for spheres
+    float4 blur_root;                   // blur.xyz ; w = bits(int): BLAS root in nodes4, or ~sphere index for spheres
 };
 // Shading record of a top-level entry.
 struct DObjectSh {
@@ -29,16 +32,15 @@ struct DImage { const void* pixels; int32_t width, height, format, pad; };
 
 struct DScene {
     // geometry for traversal
-    const uint4* nodes4q;               // BvhNode64Q as 4 x uint4: the same 4-wide tree (same node indices) with 8-bit quantised boxes
-    const float4* nodes4;               // BvhNode128 as 8 x float4 (4-wide collapse of `nodes`; used by k_trace_persistent)
+    const uint4* nodes4q;               // BvhNode64Q as 4 x uint4: the same 4-wide tree (same node indices) with 8-bit quantised boxes; NULL unless RT795_QNODES=1
+    const float4* nodes4;               // BvhNode128 as 8 x float4 (4-wide collapse of the SAH BVH2); every BLAS first, the TLAS nodes last
     const int32_t* obj_root4;           // per top-level entry: BLAS root in nodes4 (spheres: unused)
-    int32_t tlas_root4;
-    const float4* nodes;                // BvhNode64 as 4 x float4 (binary; classic kernels + rt_trace_primary)
-    const float4* tris_w;               // same triangles as ray -> (u, v, w) affine maps, 3 rows x float4 (traverse_pt.cuh tri_test_affine); NULL if off
-    const float4* tris;                 // 3 x float4 per triangle in leaf order: (v0, bits prim), (e1, 0), (e2, 0)
+    int32_t tlas_root4;                 // first TLAS node = its root; nodes [tlas_root4, tlas_root4 + tlas_nodes) are the TLAS
+    int32_t tlas_nodes;
+    const float4* tris_w;               // triangles in leaf order as ray -> (u, v, w) affine maps, 3 rows x float4 (traverse.cuh tri_test_affine)
+    const float4* tris;                 // 3 x float4 per triangle in leaf order: (v0, bits prim), (e1, 0), (e2, 0); read by the shade stage
     const DObjectXf* obj_xf;
     const float4* spheres;              // center.xyz, R
-    int32_t tlas_root;
     // shading data
     const DObjectSh* obj_sh;
     const int32_t* tri_idx;             // 3 ints per triangle (original order)
@@ -83,11 +85,20 @@ struct DShadowQueue {
     float4* c_pixel;                    // contribution rgb (added if unoccluded), bits(pixel)
 };
 
-enum : uint32_t { RAY_PRIMARY = 1u, RAY_BEER_SELF = 2u, RAY_BEER_SIBLING = 4u, RAY_SPECULAR = 8u };
+enum : uint32_t { RAY_PRIMARY = 1u, RAY_BEER_SELF = 2u, RAY_BEER_SIBLING = 4u, RAY_SPECULAR = 8u,
+                  RAY_DEAD = 16u };   // RAY_DEAD: level-0 slot outside the image (fused raygen files one record per work item)
 
+// Per-pipeline device counters.  A wave's queue sizes live ONLY here: every kernel of the wave reads its input count from
+// device memory, so the host enqueues a whole frame without a single round trip (core.cu).
 struct DCounters {
-    int32_t next_count, shadow_count, overflow, ray_cursor;
-    unsigned long long node_visits, prim_tests;                 // closest-hit queries
+    int32_t level_count[kMaxLevels + 1];    // rays in queue level L of the current wave (level 0: written by the host / raygen)
+    int32_t shadow_count[kMaxLevels];       // shadow rays emitted by the shade pass of level L
+    int32_t cursor_extend[kMaxLevels];      // persistent-kernel ray cursors, one per launch of the wave
+    int32_t cursor_shadow[kMaxLevels];
+    int32_t overflow;                       // a queue was full: the frame is redone with smaller waves (never silent)
+    int32_t pad;
+    unsigned long long total_secondary, total_shadow;           // folded in by k_wave_end
+    unsigned long long node_visits, prim_tests;                 // closest-hit queries (COUNT builds)
     unsigned long long node_visits_shadow, prim_tests_shadow;   // occlusion queries
     unsigned long long diag[8];   // COUNT builds: [0/4] node-step warp executions, [1/5] sum of lanes alive (ray unfinished) at those, [2/6] leaf-phase executions, [3/7] lanes in them (closest / occlusion)
 };

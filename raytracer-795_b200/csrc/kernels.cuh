@@ -1,8 +1,10 @@
 // The wavefront kernels K1..K8 for sm_100a.
-//   K1 k_raygen   Camera::getPrimaryRay / PixelLBCorner / getSampleRay / AddDepthOfField (src/Camera.cpp:63-139)
-//   K2 k_extend   closest hit for a ray queue (traverse.cuh)
+//   K1 k_raygen   Camera::getPrimaryRay / PixelLBCorner / getSampleRay / AddDepthOfField (src/Camera.cpp:63-139); raygen.cuh.
+//                 In a frame K1 runs fused into the first closest-hit launch (traverse_pt.cuh k_raygen_trace); the stand-alone
+//                 kernel serves rt_trace_primary and the A/B switch RT795_FUSED_RAYGEN=0
+//   K2 k_trace_persistent<closest>   closest hit for a ray queue (traverse_pt.cuh)
 //   K3 k_shade    surface evaluation + direct-light shadow-ray emission + continuation rays (shade.cuh)
-//   K4 k_shadow   occlusion query + accumulate
+//   K4 k_trace_persistent<any-hit>   occlusion query + accumulate
 //   K5            compaction is fused into K3: warp-ballot slot reservation + one atomicAdd per warp per queue
 //   K6 k_shade<RT_INTEGRATOR_PATH>   path-tracing bounce (NEE + Russian roulette)
 //   K7 k_tonemap_*  photographic tone map (log-average reduction, histogram white point, per-pixel map)
@@ -37,111 +39,45 @@ RT_D int block_reserve(int32_t* counter, int want /*0,1,2*/, int* scratch) {
     return scratch[kBlock / 32] + scratch[warp] + __popc(b1 & lt) + __popc(b2 & lt);
 }
 
-RT_D int meta_pack(int depth, uint32_t flags, int beer_mat) { return (depth & 0xff) | (int)((flags & 0xffu) << 8) | (beer_mat << 16); }
-
-// ---- K1
-// Work item w = work_base + i enumerates (pixel slot, sample) with the sample fastest.  The host hands work_base over as
-// (base_rest, base_sample) = (work_base / spp, work_base % spp) so that every division here is 32-bit (64-bit division by a
-// run-time value is a ~100-instruction subroutine; this kernel had four of them per ray).
-__global__ void __launch_bounds__(kBlock) k_raygen(DCamera cam, DTiling tl, RenderConsts rc, int max_depth, unsigned base_rest, unsigned base_sample, int count,
-                                                   DRayQueue q, int32_t* q_count, int center_only) {
+// ---- K1 (stand-alone; compacting: slots outside the image take no queue entry)
+__global__ void __launch_bounds__(kBlock) k_raygen(RaygenArgs a, int count, DRayQueue q, int32_t* q_count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool active = i < count;
     float3 o = v3(0.f, 0.f, 0.f), d = o;
     float time = 0.f;
     uint32_t pixel = 0, sample = 0;
-    if (active) {
-        int spp = center_only ? 1 : cam.spp;
-        unsigned sw = base_sample + (unsigned)i, sq = sw / (unsigned)spp;
-        sample = sw - sq * (unsigned)spp;
-        unsigned rest = base_rest + sq;
-        unsigned tile_px = (unsigned)(tl.tw * tl.th);
-        int lt = (int)(rest / tile_px);
-        int pit = (int)(rest - (unsigned)lt * tile_px);
-        int k = lt * tl.count + tl.rank;
-        int tx = k % tl.tiles_x, ty = k / tl.tiles_x;
-        int sb = pit >> 5, ln = pit & 31, sbx = tl.tw >> 3;        // 8x4 sub-blocks: one warp = one compact pixel block
-        int x = tx * tl.tw + (sb % sbx) * 8 + (ln & 7), y = ty * tl.th + (sb / sbx) * 4 + (ln >> 3);
-        active = x < cam.nx && y < cam.ny;
-        if (active) {
-            pixel = (uint32_t)(y * cam.nx + x);
-            float3 pos = v3(cam.pos), gaze = v3(cam.gaze), up = v3(cam.up), right = v3(cam.right);
-            if (spp <= 1) {                                          // getPrimaryRay
-                float u = cam.l + (cam.r - cam.l) * (x + 0.5f) * cam.invnx;
-                float v = cam.t - (cam.t - cam.b) * (y + 0.5f) * cam.invny;
-                float3 m = pos + gaze * cam.dist;
-                m = m + u * right;
-                m = m + v * up;
-                o = pos; d = (m - pos) / length(m - pos); time = 0.f;
-            } else {                                                 // PixelLBCorner + getSampleRay (+ AddDepthOfField)
-                float u = cam.l + x * cam.pw;
-                float v = cam.t - (y + 1) * cam.ph;
-                float3 m = pos + gaze * cam.dist;
-                m = m + u * right;
-                m = m + v * up;
-                int si = (int)sample % cam.n, sj = (int)sample / cam.n;
-                float4 r = philox_uniform4(rc.seed, pixel, sample, 0u, DIM_CAMERA);
-                m = m + (si + r.x) * cam.sw * right;
-                m = m + (sj + r.y) * cam.sh * up;
-                o = pos; d = (m - pos) / length(m - pos);
-                if (cam.dof) {
-                    float3 q = pos;
-                    q = q + cam.aperture * (r.z - 0.5f) * right;
-                    q = q + cam.aperture * (r.w - 0.5f) * up;
-                    float3 dir = normalize0(m - pos);
-                    float t_fd = cam.focus / dot(dir, gaze);
-                    float3 p = o + d * t_fd;
-                    o = q; d = normalize0(p - q); time = 0.f;
-                } else time = r.z;
-            }
-        }
-    }
+    bool active = i < count && gen_camera_ray(a, i, o, d, time, pixel, sample);
     __shared__ int s_res[kBlock / 32 + 1];
     int slot = block_reserve(q_count, active ? 1 : 0, s_res);
     if (active) {
         q.o_time[slot] = make_float4(o.x, o.y, o.z, time);
         q.d_tmax[slot] = make_float4(d.x, d.y, d.z, 3.0e38f);
         q.w_pixel[slot] = make_float4(1.f, 1.f, 1.f, __int_as_float((int)pixel));
-        q.meta[slot] = make_int4((int)sample, meta_pack(max_depth, RAY_PRIMARY | RAY_SPECULAR, 0), 1, 0);
+        q.meta[slot] = make_int4((int)sample, meta_pack(a.max_depth, RAY_PRIMARY | RAY_SPECULAR, 0), 1, 0);
     }
 }
 
-// ---- K2
-template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) k_extend(DScene sc, DRayQueue q, int first, int count, DCounters* ctr) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    i += first;
-    float4 ot = q.o_time[i], dt = q.d_tmax[i];
-    HitRec h;
-    float3 o = v3(ot), d = v3(dt);
-    if (any_nan(o) || any_nan(d)) { h.prim = -1; h.obj = -1; h.t = 0.f; h.beta = h.gamma = 0.f; }   // src/Helper.cpp:28-30
-    else {
-        unsigned cn = 0, cp = 0;
-        trace<false, COUNT>(sc, o, d, ot.w, dt.w, h, cn, cp);
-        if (COUNT) { atomicAdd(&ctr->node_visits, (unsigned long long)cn); atomicAdd(&ctr->prim_tests, (unsigned long long)cp); }
+// End of a wave: fold the wave's queue sizes into the frame totals and clear the per-wave counters for the next wave on this
+// pipeline (one thread block; replaces a handful of memsets and the host's bookkeeping).
+__global__ void __launch_bounds__(256) k_wave_end(DCounters* c, int nlevels) {
+    unsigned long long sec = 0, sh = 0;
+    for (int l = threadIdx.x; l < nlevels; l += blockDim.x) {
+        if (l > 0) sec += (unsigned long long)c->level_count[l];
+        sh += (unsigned long long)c->shadow_count[l];
     }
-    q.hit[i] = make_float4(h.t, h.beta, h.gamma, __int_as_float(h.prim));
-    q.hit_obj[i] = h.obj;
-}
-
-// ---- K4
-template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) k_shadow(DScene sc, DShadowQueue sq, int count, float* accum, DCounters* ctr) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    float4 ot = sq.o_time[i], dt = sq.d_tmax[i];
-    HitRec h;
-    float3 o = v3(ot), d = v3(dt);
-    bool occluded = false;
-    if (!(any_nan(o) || any_nan(d))) {
-        unsigned cn = 0, cp = 0;
-        occluded = trace<true, COUNT>(sc, o, d, ot.w, dt.w, h, cn, cp);
-        if (COUNT) { atomicAdd(&ctr->node_visits_shadow, (unsigned long long)cn); atomicAdd(&ctr->prim_tests_shadow, (unsigned long long)cp); }
+    for (int o = 16; o; o >>= 1) { sec += __shfl_xor_sync(0xffffffffu, sec, o); sh += __shfl_xor_sync(0xffffffffu, sh, o); }
+    __shared__ unsigned long long s_sec[8], s_sh[8];
+    if ((threadIdx.x & 31) == 0) { s_sec[threadIdx.x >> 5] = sec; s_sh[threadIdx.x >> 5] = sh; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long a = 0, b = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { a += s_sec[w]; b += s_sh[w]; }
+        c->total_secondary += a;
+        c->total_shadow += b;
     }
-    if (!occluded) {
-        float4 c = sq.c_pixel[i];
-        accum_add(accum, (uint32_t)__float_as_int(c.w), v3(c));
+    __syncthreads();
+    for (int l = threadIdx.x; l <= nlevels; l += blockDim.x) {
+        c->level_count[l] = 0;
+        if (l < nlevels) { c->shadow_count[l] = 0; c->cursor_extend[l] = 0; c->cursor_shadow[l] = 0; }
     }
 }
 
@@ -158,12 +94,37 @@ RT_D void write_ray(const DRayQueue& q, int slot, uint32_t pixel, const RayOut& 
 #ifndef RT795_SHADE_MIN_BLOCKS
 #define RT795_SHADE_MIN_BLOCKS 5
 #endif
-template <int INTEGRATOR>
-__global__ void __launch_bounds__(kBlock, RT795_SHADE_MIN_BLOCKS) k_shade(DScene sc, DCamera cam, RenderConsts rc, DRayQueue in, int first, int count, DRayQueue out, DShadowQueue sq,
-                                                  DCounters* ctr, float* accum) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+// Shade pass over rays [first, first + min(limit, *in_count - first)) of queue level `in`; continuation rays go to `out`
+// (count in *out_count), shadow rays to `sq` (count in *shadow_count).  The ray count is device-resident; the grid covers `limit`.
+struct ShadeIO {
+    DRayQueue in, out;
+    DShadowQueue sq;
+    const int32_t* in_count;   // NULL: exactly `limit` rays
+    int first, limit;
+    int32_t* out_count;
+    int32_t* shadow_count;
+    int32_t* overflow;
+    float* accum;
+};
+
+// LOOP = false: one 128-ray group per CTA, the grid covers `limit` (used when the host knows the ray count: level 0 of a wave, the
+// chunked driver).  LOOP = true: grid-stride over the groups with a small fixed grid, for the deeper levels whose size only the
+// device knows - sizing the grid by what such a level could hold at most (queue capacity = 32 768 CTAs) costs ~60 us of empty
+// CTAs per launch, 10 ms per C2 frame.  ANY loop around this body costs 300 bytes of spills at the 96-register cap (ptxas -v), so
+// the looping variant is compiled for 4 resident CTAs (128 registers, no spills).
+template <int INTEGRATOR, bool LOOP>
+__global__ void __launch_bounds__(kBlock, LOOP ? 4 : RT795_SHADE_MIN_BLOCKS) k_shade(DScene sc, DCamera cam, RenderConsts rc, ShadeIO io) {
+    const DRayQueue& in = io.in;
+    const DRayQueue& out = io.out;
+    const DShadowQueue& sq = io.sq;
+    float* const accum = io.accum;
+    int count = io.limit;
+    if (io.in_count) count = max(0, min(io.limit, *io.in_count - io.first));
+    if ((int)(blockIdx.x * kBlock) >= count) return;
+  for (int group = blockIdx.x * kBlock; group < count; group += LOOP ? (int)(gridDim.x * kBlock) : 0x40000000) {
+    int i = group + threadIdx.x;
     bool active = i < count;
-    i += first;
+    i += io.first;
 
     // per-lane state that survives to the (warp-convergent) queue pushes
     int n_out = 0;
@@ -191,7 +152,9 @@ __global__ void __launch_bounds__(kBlock, RT795_SHADE_MIN_BLOCKS) k_shade(DScene
         HitRec h;
         h.t = hr.x; h.beta = hr.y; h.gamma = hr.z; h.prim = __float_as_int(hr.w); h.obj = in.hit_obj[i];
 
-        if (INTEGRATOR == RT_INTEGRATOR_REFERENCE) {
+        if (flags & RAY_DEAD) {
+            // level-0 slot outside the image (fused raygen): nothing to shade
+        } else if (INTEGRATOR == RT_INTEGRATOR_REFERENCE) {
             // ---- Beer factors whose distance is only known after this ray's (or its sibling's) extend step (src/Scene.cpp:110-115)
             if (flags & (RAY_BEER_SELF | RAY_BEER_SIBLING)) {
                 float t_b = h.t; bool hit_b = h.prim >= 0;
@@ -368,9 +331,9 @@ __global__ void __launch_bounds__(kBlock, RT795_SHADE_MIN_BLOCKS) k_shade(DScene
     // ---- continuation rays -> next queue (pairs stay adjacent: slot, slot+1)
     __shared__ int s_res[kBlock / 32 + 1];
     {
-        int slot = block_reserve(&ctr->next_count, n_out, s_res);
+        int slot = block_reserve(io.out_count, n_out, s_res);
         if (n_out) {
-            if (slot + n_out > rc.queue_cap) atomicExch(&ctr->overflow, 1);
+            if (slot + n_out > rc.queue_cap) atomicExch(io.overflow, 1);
             else { write_ray(out, slot, pixel, r0); if (n_out == 2) write_ray(out, slot + 1, pixel, r1); }
         }
     }
@@ -386,9 +349,9 @@ __global__ void __launch_bounds__(kBlock, RT795_SHADE_MIN_BLOCKS) k_shade(DScene
                 c = W * ls.radiance;
                 emit = !is_zero(c) && !any_nan(c);
             }
-            int slot = block_reserve(&ctr->shadow_count, emit ? 1 : 0, s_res);
+            int slot = block_reserve(io.shadow_count, emit ? 1 : 0, s_res);
             if (emit) {
-                if (slot >= rc.shadow_cap) atomicExch(&ctr->overflow, 1);
+                if (slot >= rc.shadow_cap) atomicExch(io.overflow, 1);
                 else {
                     float3 so = s.P + s.N * sc.shadow_eps;
                     sq.o_time[slot] = make_float4(so.x, so.y, so.z, rtime);
@@ -398,6 +361,9 @@ __global__ void __launch_bounds__(kBlock, RT795_SHADE_MIN_BLOCKS) k_shade(DScene
             }
         }
     }
+    if (!LOOP) break;
+    __syncthreads();                                               // s_res is reused by the next group
+  }
 }
 
 // ---- {v0, e1, e2} records -> affine ray-to-triangle maps (dscene.h tris_w), one thread per triangle, in double for the inverse
@@ -457,6 +423,7 @@ __global__ void k_resolve_owned(const float* __restrict__ accum, float* __restri
 __global__ void k_primary_hits(DScene sc, DRayQueue q, int count, RtHit* out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
+    if ((((uint32_t)q.meta[i].y >> 8) & 0xffu) & RAY_DEAD) return;   // slot outside the image
     float4 ot = q.o_time[i], dt = q.d_tmax[i], hr = q.hit[i];
     uint32_t pixel = (uint32_t)__float_as_int(q.w_pixel[i].w);
     RtHit r;

@@ -28,6 +28,7 @@
 // phases drop 64.6 M -> 23.5 M (occlusion, 4 slots) and their batch rises 2.5 -> 4.3 lanes, but the extra speculative node
 // visits (8.28 -> 8.92 per ray) cost as much: occlusion stage +1.0 ms, closest hit -0.5 ms, frame +1 ms.
 #pragma once
+#include "raygen.cuh"
 #include "shade.cuh"
 #include "traverse.cuh"
 
@@ -35,28 +36,21 @@ namespace rt795 {
 
 constexpr int kFetchThreshold = 20;   // default; TraceIO.flags bits 8..15 override (tuning)
 
-struct TraceIO {
-    const float4* o_time;      // ray queue (read)
-    const float4* d_tmax;
-    int first, count;          // rays [first, first+count)
-    int32_t* cursor;           // global next-ray cursor (zeroed before the launch)
-    // closest-hit outputs
-    float4* hit;
-    int32_t* hit_obj;
-    // shadow outputs
-    const float4* c_pixel;
-    float* accum;
-    int flags;                 // bit 0: dynamic ray fetch, bit 1: postpone leaves (tuning knobs; results do not depend on them)
+// Compile-time variants of the traversal kernel (template parameter FLAGS)
+enum : int {
+    TF_QNODES = 1,      // occlusion only: walk the 8-bit quantised copy of the nodes (DScene.nodes4q)
+    TF_SMEM_TLAS = 2,   // stage the TLAS nodes and the top-level transform records in shared memory (broadcast LDS instead of LDG)
 };
 
-RT_D void pt_accum(float* accum, float4 c) {
-    float* p = accum + (size_t)(uint32_t)__float_as_int(c.w) * 3;
-    if (c.x == c.x && c.y == c.y && c.z == c.z) {
-        if (c.x != 0.f) atomicAdd(p, c.x);
-        if (c.y != 0.f) atomicAdd(p + 1, c.y);
-        if (c.z != 0.f) atomicAdd(p + 2, c.z);
-    }
-}
+struct TraceIO {
+    DRayQueue q;               // closest hit: o_time / d_tmax read, hit / hit_obj written (fused raygen: the whole record is written)
+    DShadowQueue sq;           // occlusion: shadow queue (read)
+    const int32_t* count_ptr;  // device address of the queue size (the producing kernel's counter); NULL: exactly `limit` rays
+    int first, limit;          // rays [first, first + min(limit, *count_ptr - first))
+    int32_t* cursor;           // global next-ray cursor (zero before the launch)
+    float* accum;              // occlusion: pixel accumulator
+    int flags;                 // bit 0: dynamic ray fetch, bit 1: postpone leaves (tuning knobs; results do not depend on them)
+};
 
 // Resident CTAs per SM the compiler must leave room for (A/B knobs).  7 x 128 threads = 72 registers per thread: what the
 // occlusion kernel uses anyway, and 80 -> 72 for closest hit, whose stage drops 17.2 -> 16.65 ms on C4; 8 CTAs (64 registers)
@@ -67,12 +61,36 @@ RT_D void pt_accum(float* accum, float4 c) {
 #ifndef RT795_MINB_CLOSEST
 #define RT795_MINB_CLOSEST 7
 #endif
-template <bool ANY_HIT, bool COUNT, bool QNODES = false, bool AFFINE_TRIS = false>
-__global__ void __launch_bounds__(128, (COUNT || QNODES) ? 0 : (ANY_HIT ? RT795_MINB_ANY : RT795_MINB_CLOSEST)) k_trace_persistent(DScene sc, TraceIO io, DCounters* ctr) {
+
+template <bool ANY_HIT, bool COUNT, int FLAGS, bool RAYGEN>
+RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const RaygenArgs* rg) {
+    constexpr bool QNODES = (FLAGS & TF_QNODES) != 0;
+    constexpr bool SMEM = (FLAGS & TF_SMEM_TLAS) != 0;
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
     const float eps = sc.int_eps;
+    const float4* const q_o = ANY_HIT ? io.sq.o_time : io.q.o_time;
+    const float4* const q_d = ANY_HIT ? io.sq.d_tmax : io.q.d_tmax;
+    int total = io.limit;
+    if (io.count_ptr) total = max(0, min(io.limit, *io.count_ptr - io.first));
+
+    // north_star "BVH top levels staged in shared memory": every ray starts in the TLAS and re-enters it after each instance,
+    // so the TLAS nodes (C4: 6 nodes) and the 64-byte transform records of the top-level entries (C4: 17) are the hottest lines
+    // of the scene.  Staged once per CTA in DYNAMIC shared memory sized to exactly these records (C4: 1.9 KB per CTA; a fixed
+    // 8 KB array took 56 KB per SM out of the L1 and cost 2 ms per C4 frame).  The host selects this variant only when the top
+    // level fits kSmemTlasBytes; otherwise the top level is walked in global memory like the BLASes.
+    extern __shared__ float4 s_stage[];
+    float4* const s_tlas = s_stage;
+    float4* const s_xf = s_stage + (SMEM ? sc.tlas_nodes * 8 : 0);
+    const bool tlas_smem = SMEM;
+    if (SMEM) {
+        const float4* src = sc.nodes4 + (size_t)sc.tlas_root4 * 8;
+        for (int i = threadIdx.x; i < sc.tlas_nodes * 8; i += blockDim.x) s_tlas[i] = __ldg(src + i);
+        const float4* xs = reinterpret_cast<const float4*>(sc.obj_xf);
+        for (int i = threadIdx.x; i < sc.num_objects * 4; i += blockDim.x) s_xf[i] = __ldg(xs + i);
+        __syncthreads();
+    }
 
     // Traversal stack: (node, t_entry) packed into 64 bits (one LDL.64 / STL.64 per entry) with the TOP entry cached in
     // registers, so a pop hands out the cached entry and the reload of the next one overlaps the work on the popped node
@@ -138,11 +156,11 @@ __global__ void __launch_bounds__(128, (COUNT || QNODES) ? 0 : (ANY_HIT ? RT795_
         if (ANY_HIT) {
             bool add = idle && rayidx >= 0 && hprim < 0;   // unoccluded: the light's contribution reaches the pixel
             float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (add) c = __ldg(io.c_pixel + rayidx);
+            if (add) c = __ldg(io.sq.c_pixel + rayidx);
             warp_accum(io.accum, add, (uint32_t)__float_as_int(c.w), v3(c));
             if (idle) rayidx = -1;
         } else if (idle && rayidx >= 0) {
-            io.hit[rayidx] = make_float4(tmax, hb, hg, __int_as_float(hprim)); io.hit_obj[rayidx] = hobj;
+            io.q.hit[rayidx] = make_float4(tmax, hb, hg, __int_as_float(hprim)); io.q.hit_obj[rayidx] = hobj;
             rayidx = -1;
         }
         unsigned m = __ballot_sync(full, idle);
@@ -150,13 +168,26 @@ __global__ void __launch_bounds__(128, (COUNT || QNODES) ? 0 : (ANY_HIT ? RT795_
             int nreq = __popc(m), mine = __popc(m & lt), leader = __ffs(m) - 1, base = 0;
             if ((int)lane == leader) base = atomicAdd(io.cursor, nreq);
             base = __shfl_sync(full, base, leader);
-            if (base + nreq >= io.count) exhausted = true;
-            if (idle && base + mine < io.count) {
+            if (base + nreq >= total) exhausted = true;
+            if (idle && base + mine < total) {
                 rayidx = io.first + base + mine;
-                float4 ot = io.o_time[rayidx], dt = io.d_tmax[rayidx];
-                wo = v3(ot); wd = v3(dt); time = ot.w; tmax = dt.w;
+                bool live = true;
+                if (RAYGEN) {
+                    // K1 fused into K2: the lane generates its next primary ray itself and files the queue record the shade stage
+                    // reads; slot = work item (no compaction: slots outside the image are filed as RAY_DEAD)
+                    uint32_t pixel = 0, sample = 0;
+                    live = gen_camera_ray(*rg, rayidx, wo, wd, time, pixel, sample);
+                    tmax = 3.0e38f;
+                    io.q.o_time[rayidx] = make_float4(wo.x, wo.y, wo.z, time);
+                    io.q.d_tmax[rayidx] = make_float4(wd.x, wd.y, wd.z, 3.0e38f);
+                    io.q.w_pixel[rayidx] = make_float4(1.f, 1.f, 1.f, __int_as_float((int)pixel));
+                    io.q.meta[rayidx] = make_int4((int)sample, meta_pack(rg->max_depth, live ? (RAY_PRIMARY | RAY_SPECULAR) : RAY_DEAD, 0), 1, 0);
+                } else {
+                    float4 ot = q_o[rayidx], dt = q_d[rayidx];
+                    wo = v3(ot); wd = v3(dt); time = ot.w; tmax = dt.w;
+                }
                 hprim = -1; hobj = -1; hb = hg = 0.f;
-                if (any_nan(wo) || any_nan(wd)) { node = kSentinel; if (!ANY_HIT) tmax = 0.f; }   // src/Helper.cpp:28-30: NaN ray = no hit
+                if (!live || any_nan(wo) || any_nan(wd)) { node = kSentinel; if (!ANY_HIT) tmax = 0.f; }   // src/Helper.cpp:28-30: NaN ray = no hit
                 else {
                     RT_SET_RAY(wo, wd);
                     if (COUNT) atomicOr(&s_alive[threadIdx.x >> 5], 1u << lane);
@@ -206,12 +237,18 @@ __global__ void __launch_bounds__(128, (COUNT || QNODES) ? 0 : (ANY_HIT ? RT795_
 #undef RT_SLABQ
 #undef RT_QB
                     } else {
-                    const float4* np = sc.nodes4 + (size_t)node * 8;
                         // near / far planes are picked by the ray's direction signs through the LOAD ADDRESS (lo and hi of an axis are
                         // adjacent float4s of the same 128-byte line), so no min/max per axis is needed: 6 FMA + 2 three-input min/max
                         // + 2 clamps per child instead of 6 FMA + 10 min/max (the ALU pipe is the busiest pipe of this kernel, ncu r01c).
-                        float4 nx4 = ldg4(np + sgx), fx4 = ldg4(np + (1 - sgx)), ny4 = ldg4(np + 2 + sgy), fy4 = ldg4(np + (3 - sgy));
-                        float4 nz4 = ldg4(np + 4 + sgz), fz4 = ldg4(np + (5 - sgz)), cr = ldg4(np + 6);
+                        float4 nx4, fx4, ny4, fy4, nz4, fz4, cr;
+                        if (SMEM && tlas_smem && cur_obj < 0) {
+                            const float4* np = s_tlas + (node - sc.tlas_root4) * 8;
+                            nx4 = np[sgx]; fx4 = np[1 - sgx]; ny4 = np[2 + sgy]; fy4 = np[3 - sgy]; nz4 = np[4 + sgz]; fz4 = np[5 - sgz]; cr = np[6];
+                        } else {
+                            const float4* np = sc.nodes4 + (size_t)node * 8;
+                            nx4 = ldg4(np + sgx); fx4 = ldg4(np + (1 - sgx)); ny4 = ldg4(np + 2 + sgy); fy4 = ldg4(np + (3 - sgy));
+                            nz4 = ldg4(np + 4 + sgz); fz4 = ldg4(np + (5 - sgz)); cr = ldg4(np + 6);
+                        }
 #define RT_SLAB(K, C)                                                                                                                   \
                         {                                                                                                                   \
                             float n_ = fmaxf(fmaxf(nx4.C * id.x - ood.x, ny4.C * id.y - ood.y), fmaxf(nz4.C * id.z - ood.z, 0.f));             \
@@ -251,7 +288,8 @@ __global__ void __launch_bounds__(128, (COUNT || QNODES) ? 0 : (ANY_HIT ? RT795_
                     // TLAS leaf: one top-level entry
                     int obj = (~node) >> 3;
                     float3 oo, od; int root;
-                    xf_ray(sc.obj_xf + obj, wo, wd, time, oo, od, root);
+                    if (SMEM && tlas_smem) xf_ray_rows(s_xf[obj * 4], s_xf[obj * 4 + 1], s_xf[obj * 4 + 2], s_xf[obj * 4 + 3], wo, wd, time, oo, od, root);
+                    else xf_ray(sc.obj_xf + obj, wo, wd, time, oo, od, root);
                     if (root < 0) {
                         if (COUNT) ++cnt_prims;
                         float t;
@@ -264,7 +302,7 @@ __global__ void __launch_bounds__(128, (COUNT || QNODES) ? 0 : (ANY_HIT ? RT795_
                         RT_SET_RAY(oo, od);
                         cur_obj = obj;
                         RT_PUSH(kBlasExit, -1.f);
-                        node = __ldg(sc.obj_root4 + obj);
+                        node = root;                       // the entry's BLAS root in nodes4 (DObjectXf.blur_root.w)
                     }
                 } else {
                     // triangle leaf: postpone the first one, stop at the second
@@ -280,12 +318,12 @@ __global__ void __launch_bounds__(128, (COUNT || QNODES) ? 0 : (ANY_HIT ? RT795_
                 if (COUNT) { unsigned am = __activemask(); if ((int)lane == __ffs(am) - 1) { d_leafexec++; d_leaflanes += __popc(am); } }
                 int payload = ~leaf;
                 int first = payload >> 3, count = (payload & 7) + 1;
-                const float4* tp = (AFFINE_TRIS ? sc.tris_w : sc.tris) + (size_t)first * 3;
+                const float4* tp = sc.tris_w + (size_t)first * 3;
                 bool done = false;
                 for (int i = 0; i < count; i++, tp += 3) {
                     if (COUNT) ++cnt_prims;
-                    float t, u, v; int prim;
-                    if (AFFINE_TRIS ? tri_test_affine(tp, o, d, eps, tmax, t, u, v) : tri_test(tp, o, d, eps, tmax, t, u, v, prim)) {
+                    float t, u, v;
+                    if (tri_test_affine(tp, o, d, eps, tmax, t, u, v)) {
                         tmax = t; hb = u; hg = v; hprim = first + i; hobj = cur_obj;
                         if (ANY_HIT) { done = true; break; }
                     }
@@ -308,6 +346,17 @@ __global__ void __launch_bounds__(128, (COUNT || QNODES) ? 0 : (ANY_HIT ? RT795_
         atomicAdd(&ctr->diag[b + 0], (unsigned long long)d_exec); atomicAdd(&ctr->diag[b + 1], (unsigned long long)d_alive);
         atomicAdd(&ctr->diag[b + 2], (unsigned long long)d_leafexec); atomicAdd(&ctr->diag[b + 3], (unsigned long long)d_leaflanes);
     }
+}
+
+template <bool ANY_HIT, bool COUNT, int FLAGS>
+__global__ void __launch_bounds__(128, (COUNT || (FLAGS & TF_QNODES)) ? 0 : (ANY_HIT ? RT795_MINB_ANY : RT795_MINB_CLOSEST)) k_trace_persistent(DScene sc, TraceIO io, DCounters* ctr) {
+    trace_body<ANY_HIT, COUNT, FLAGS, false>(sc, io, ctr, nullptr);
+}
+
+// K1 + K2 in one launch (level 0 of a wave): work items come from the cursor, rays from the camera.
+template <bool COUNT, int FLAGS>
+__global__ void __launch_bounds__(128, COUNT ? 0 : RT795_MINB_CLOSEST) k_raygen_trace(DScene sc, TraceIO io, DCounters* ctr, RaygenArgs rg) {
+    trace_body<false, COUNT, FLAGS, true>(sc, io, ctr, &rg);
 }
 
 }  // namespace rt795

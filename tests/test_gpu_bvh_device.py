@@ -78,7 +78,8 @@ def _box2(row, k):
 
 
 @pytest.mark.parametrize("builder", ["RT_BVH_DEVICE_PLOC", "RT_BVH_DEVICE_SAH"])
-def test_device_tree_is_a_conservative_partition(rt, scene_dir, builder):
+def test_device_tree_is_a_conservative_partition(rt, scene_dir, builder, monkeypatch):
+    monkeypatch.setenv("RT795_DEBUG_BVH", "1")                           # keep the binary BVH (the collapse's input) resident for rt_debug_read_bvh
     xml = rt.scenes.scene_c3(os.path.join(scene_dir, "c3dev"), res=(96, 54), spp=1, n=96, deterministic=True)   # 18 050 triangles
     hs, (dev,) = _scenes(rt, xml, [getattr(rt, builder)])
     st = dev.stats()

@@ -542,3 +542,39 @@ def test_cli_writes_the_reference_file_formats(rt, scene_dir, tmp_path):
     want = orc.oracle_tonemap(img, key=t.key, burn=t.burn_percent, saturation=t.saturation, gamma=t.gamma).astype(np.int64)   # the CPU statement, not the CUDA path again
     assert (np.abs(ldr - want) <= 1).mean() >= 0.999
     sc2.close(); hs2.close()
+
+
+# ------------------------------------------------------------------------------------------------ route A: the reference's own parser in front of the ABI
+@pytest.mark.parametrize("scene", ["c1", "lights", "brdf", "textures", "textures_jpeg", "c4det"])
+def test_route_a_bridge_reference_parser_plus_librt795(rt, scene_dir, tmp_path, scene):
+    """INTEGRATION.md route A compiled for real (oracle/harness/GpuBridge.cpp -> oracle/_ref/ref_raytracer_gpu): the UNMODIFIED
+    reference sources parse the XML / PLY / images and run their own transform + smooth-normal prologue, then hand their Scene
+    across the C ABI to librt795.so in place of the 8-thread render loop (src/Scene.cpp:336-356).  Its frame must equal the frame
+    of the unmodified reference binary (same parser, CPU render loop) within the C1 tolerance - proving the boundary with the
+    reference's OWN data structures, not this repo's loader.  Deterministic scenes: Whitted C1, every light type, all eight BRDFs,
+    every texture mode (PNG / EXR / JPEG through the reference's decoders), and the C4 features (PLY mesh, 16 instances with scale /
+    rotation, Perlin bump + kd, EXR image texture) at 1 spp."""
+    gpu_exe = os.path.join(ROOT, "oracle", "_ref", "ref_raytracer_gpu")
+    cpu_exe = os.path.join(ROOT, "oracle", "_ref", "ref_raytracer")
+    if not (os.path.exists(gpu_exe) and os.path.exists(cpu_exe)):
+        pytest.skip("oracle/_ref not built")
+    d = os.path.join(scene_dir, "routeA_" + scene)
+    if scene == "c1":
+        xml = rt.scenes.scene_c1(d, res=400)
+    elif scene == "c4det":
+        xml = rt.scenes.scene_c4(d, res=(256, 144), spp=1, n=40, deterministic=True)
+    else:
+        xml = rt.scenes.scene_features(d, scene)
+    hs = rt.HostScene(xml)
+    name = hs.image_name(0)
+    hs.close()
+    outs = []
+    for tag, exe in (("gpu", gpu_exe), ("cpu", cpu_exe)):
+        wd = os.path.join(str(tmp_path), tag)
+        os.makedirs(wd)
+        r = subprocess.run([exe, xml], cwd=wd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(rt.read_f32(os.path.join(wd, name + ".f32")))
+    img, ref = outs
+    assert img.shape == ref.shape and np.isfinite(img).all()
+    assert_pointwise(img, ref, np.ones(img.shape[:2], dtype=bool), f"route A {scene}: reference parser + librt795 vs unmodified reference", outlier_budget=1e-3)
