@@ -279,6 +279,23 @@ int rt_tonemap(RtScene* scene, const float* in_rgb, int nx, int ny, float key, f
 
 int rt_get_stats(RtScene* scene, RtStats* out);
 
+/* ---- multi-GPU inside ONE process: the counterpart of the reference's fan-out inside renderScene (8 std::threads over one
+ * frame, src/Scene.cpp:340-356).  The scene is replicated on `num_devices` CUDA devices (devices[i], NULL = 0..n-1; devices[0]
+ * is the root), one context + one host thread per device.  rt_group_render cuts the frame into interleaved tiles
+ * (tile k -> device k % n), every device's resolve kernel stores its own tiles straight into the ROOT device's frame over
+ * NVLink peer memory (cudaDeviceEnablePeerAccess; a device without peer access to the root is merged by a copy), and the
+ * finished frame is copied to `out_rgb` (host, Image::_data layout) - same result as rt_render on one device, up to the order
+ * of float additions.  opts: as rt_render; tile_rank / tile_count / resolve_owned_only must be 0. */
+typedef struct RtSceneGroup RtSceneGroup;   /* opaque */
+int rt_group_create(const RtSceneDesc* desc, int num_devices, const int* devices, RtSceneGroup** out);
+void rt_group_destroy(RtSceneGroup* group);
+int rt_group_render(RtSceneGroup* group, const RtCameraDesc* cam, const RtRenderOpts* opts, float* out_rgb);
+int rt_group_num_devices(const RtSceneGroup* group);
+/* The replica on devices[index] (owned by the group): for rt_get_stats / rt_tonemap. */
+RtScene* rt_group_scene(RtSceneGroup* group, int index);
+/* 1 if devices[index] stores its tiles into the root's frame directly (peer memory), 0 if it is merged by a copy. */
+int rt_group_uses_peer_memory(const RtSceneGroup* group, int index);
+
 /* Test / diagnostic aid: copies one of the scene's acceleration-structure arrays back to the host so a checker can walk it
  * (tests/test_gpu_bvh_device.py validates the device-built trees this way).  `out` may be NULL to query the size.  Formats:
  * csrc/bvh_build.h (BvhNode64, BvhNode128, BvhNode64Q; triangles as 3 x float4 {v0|global tri id, e1, e2}). */

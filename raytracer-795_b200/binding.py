@@ -118,7 +118,8 @@ HIT_DTYPE = np.dtype([("full", "<i4"), ("object", "<i4"), ("primitive", "<i4"), 
 
 # every symbol include/rt795.h declares (tests/test_abi.py asserts the library exports all of them)
 CORE_SYMBOLS = ["rt_scene_create", "rt_scene_destroy", "rt_render", "rt_render_device", "rt_trace_primary", "rt_tonemap",
-                "rt_get_stats", "rt_debug_read_bvh", "rt_last_error", "rt_abi_version", "rt_device_count", "rt_host_load_scene",
+                "rt_get_stats", "rt_group_create", "rt_group_destroy", "rt_group_render", "rt_group_num_devices", "rt_group_scene",
+                "rt_group_uses_peer_memory", "rt_debug_read_bvh", "rt_last_error", "rt_abi_version", "rt_device_count", "rt_host_load_scene",
                 "rt_host_save_scene_blob", "rt_host_load_scene_blob", "rt_host_load_scene_cached",
                 "rt_host_camera_render_opts", "rt_host_camera_tonemap",
                 "rt_host_free_scene", "rt_host_scene_desc", "rt_host_num_cameras", "rt_host_camera",
@@ -151,6 +152,14 @@ def load_core() -> C.CDLL:
         lib.rt_trace_primary.argtypes = [C.c_void_p, P(RtCameraDesc), C.c_void_p]
         lib.rt_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
         lib.rt_get_stats.argtypes = [C.c_void_p, P(RtStats)]
+        lib.rt_group_create.argtypes = [P(RtSceneDesc), C.c_int, P(C.c_int), P(C.c_void_p)]
+        lib.rt_group_destroy.argtypes = [C.c_void_p]
+        lib.rt_group_destroy.restype = None
+        lib.rt_group_render.argtypes = [C.c_void_p, P(RtCameraDesc), P(RtRenderOpts), C.c_void_p]
+        lib.rt_group_num_devices.argtypes = [C.c_void_p]
+        lib.rt_group_scene.argtypes = [C.c_void_p, C.c_int]
+        lib.rt_group_scene.restype = C.c_void_p
+        lib.rt_group_uses_peer_memory.argtypes = [C.c_void_p, C.c_int]
         lib.rt_debug_read_bvh.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, P(C.c_uint64), P(C.c_int32)]
         lib.rt_last_error.restype = C.c_char_p
         lib.rt_host_load_scene.argtypes = [C.c_char_p, P(C.c_void_p)]
@@ -299,6 +308,45 @@ class Scene:
     def close(self) -> None:
         if self.h:
             self.lib.rt_scene_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SceneGroup:
+    """rt_group_create / rt_group_render: the scene replicated on several CUDA devices of this process, one frame split into
+    interleaved tiles, gathered on devices[0] over peer memory."""
+
+    def __init__(self, desc, devices):
+        self.lib = load_core()
+        self.h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        _check(self.lib.rt_group_create(desc, len(devices), devs, C.byref(self.h)))
+        self.devices = list(devices)
+
+    def render(self, cam: RtCameraDesc, opts: Optional[RtRenderOpts] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
+        opts = opts or default_opts()
+        if out is None:
+            out = np.empty((cam.ny, cam.nx, 3), dtype=np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == cam.nx * cam.ny * 3
+        _check(self.lib.rt_group_render(self.h, C.byref(cam), C.byref(opts), out.ctypes.data))
+        return out
+
+    def stats(self, index: int = 0) -> RtStats:
+        s = RtStats()
+        _check(self.lib.rt_get_stats(self.lib.rt_group_scene(self.h, index), C.byref(s)))
+        return s
+
+    def uses_peer_memory(self, index: int) -> bool:
+        return bool(self.lib.rt_group_uses_peer_memory(self.h, index))
+
+    def close(self) -> None:
+        if self.h:
+            self.lib.rt_group_destroy(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):

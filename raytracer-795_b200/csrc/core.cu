@@ -12,6 +12,8 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -80,6 +82,8 @@ struct Pipe {
     DevBuf<float4> sq_o, sq_d, sq_c;
     DevBuf<DCounters> counters;
     DCounters* h_counters = nullptr;   // pinned
+    DevBuf<int32_t> hist;              // per wave of this pipeline: level / shadow-queue sizes (k_wave_end), read back once per frame
+    int32_t* h_hist = nullptr; size_t h_hist_n = 0;   // pinned
     cudaEvent_t done = nullptr;
 };
 constexpr int kPipes = 4;      // upper bound; RtScene::npipes_wanted (default 2, RT795_PIPES) are used
@@ -117,7 +121,7 @@ struct RtScene {
     int bvh_depth = 0;
     int tlas_base2 = 0;
     // kernel variants (A/B switches, all default to the measured best): RT795_SMEM_TLAS, RT795_FUSED_RAYGEN
-    bool smem_tlas = true, fused_raygen = true;
+    bool smem_tlas = false, fused_raygen = true;   // measured on C4 (profiles/bench/r02_ab_driver.txt): staging 54.4 ms vs 53.7 ms without
     int trace_smem = 0;                    // dynamic shared memory of the traversal launches (staged top level), 0 = not staged
     TraceKernel k_closest = nullptr, k_closest_count = nullptr, k_any = nullptr, k_any_count = nullptr;
     RaygenTraceKernel k_rg_closest = nullptr, k_rg_closest_count = nullptr;
@@ -129,6 +133,13 @@ struct RtScene {
     size_t queue_cap = 0, shadow_cap = 0;
     // Frames are first enqueued optimistically (whole levels, two ping-pong queue buffers); a queue overflow flagged by the device
     // halves `wave_limit` and redoes the frame, and below kMinOptimisticWave the chunked, host-synchronised driver takes over.
+    // Sizes of the deeper levels are known to the device only; what the previous frame saw for the same wave (its level and
+    // shadow-queue sizes, [wave][2 * (nlev + 1)]) sizes this frame's grids.  Only a hint: every launch is correct for any size
+    // (persistent loops, a looping remainder).  RT795_HINTS=0 switches them off (A/B).
+    std::vector<int> hints;
+    int hint_stride = 0, hint_wave = 0;
+    bool use_hints = true;
+    long long hint_key[6] = {0, 0, 0, 0, 0, 0};
     size_t wave_limit = 0;                  // 0 = not limited yet
     size_t learnt_cap = 0;                  // queue capacity wave_limit / force_chunked were learnt with
     bool force_chunked = false, env_chunked = false;   // RT795_DRIVER=chunked, or learnt from overflows
@@ -534,35 +545,48 @@ struct Driver {
     }
 
 
-    void LaunchExtend(const DRayQueue& q, const int32_t* count_ptr, int first, int limit, int32_t* cursor) {
+    // expected size of a device-sized queue: the hint with headroom, capped by what the queue can hold
+    static long long Expect(int hint, long long upper) { return hint >= 0 ? std::min<long long>(upper, (long long)hint + hint / 4 + 2048) : upper; }   // hint < 0: unknown
+
+    void LaunchExtend(const DRayQueue& q, const int32_t* count_ptr, int first, int limit, int32_t* cursor, int hint = -1) {
         TraceIO io{};
         io.q = q; io.count_ptr = count_ptr; io.first = first; io.limit = limit; io.cursor = cursor; io.flags = sc->trav_flags;
-        int grid = sc->full_grid ? Blocks(limit) : std::min(Blocks(limit), sc->grid_extend);
+        int grid = sc->full_grid ? Blocks(limit) : std::min(Blocks(count_ptr ? Expect(hint, limit) : limit), sc->grid_extend);
         (count ? sc->k_closest_count : sc->k_closest)<<<std::max(1, grid), kBlock, count ? 0 : sc->trace_smem, st>>>(sc->d, io, pp->counters.p);
         launches++; n_extend++;
     }
-    void LaunchShadow(const int32_t* count_ptr, int limit, int32_t* cursor) {
+    void LaunchShadow(const int32_t* count_ptr, int limit, int32_t* cursor, int hint = -1) {
         TraceIO io{};
         io.sq = sq; io.count_ptr = count_ptr; io.first = 0; io.limit = limit; io.cursor = cursor; io.accum = accum; io.flags = sc->trav_flags_shadow;
-        int grid = sc->full_grid ? Blocks(limit) : std::min(Blocks(limit), sc->grid_shadow);
+        int grid = sc->full_grid ? Blocks(limit) : std::min(Blocks(count_ptr ? Expect(hint, limit) : limit), sc->grid_shadow);
         (count ? sc->k_any_count : sc->k_any)<<<std::max(1, grid), kBlock, (count || sc->quantised_occlusion) ? 0 : sc->trace_smem, st>>>(sc->d, io, pp->counters.p);
         launches++; n_shadow++;
     }
-    void LaunchShade(const DRayQueue& in, const DRayQueue& out, const int32_t* in_count, int first, int limit, int32_t* out_count, int32_t* shadow_count) {
+    void LaunchShade(const DRayQueue& in, const DRayQueue& out, const int32_t* in_count, int first, int limit, int32_t* out_count, int32_t* shadow_count, int hint = -1) {
         ShadeIO io{};
         io.in = in; io.out = out; io.sq = sq; io.in_count = in_count; io.first = first; io.limit = limit;
         io.out_count = out_count; io.shadow_count = shadow_count; io.overflow = &pp->counters.p->overflow; io.accum = accum;
-        if (in_count) {
-            // size known to the device only: grid-stride variant on a fixed grid (8 CTAs per SM queued: 2 rounds of the 4 resident)
-            int grid = std::max(1, std::min(Blocks(limit), sc->sm_count * 8));
-            if (path) k_shade<RT_INTEGRATOR_PATH, true><<<grid, kBlock, 0, st>>>(sc->d, cam, rc, io);
-            else k_shade<RT_INTEGRATOR_REFERENCE, true><<<grid, kBlock, 0, st>>>(sc->d, cam, rc, io);
-        } else {
-            int grid = std::max(1, Blocks(limit));
-            if (path) k_shade<RT_INTEGRATOR_PATH, false><<<grid, kBlock, 0, st>>>(sc->d, cam, rc, io);
-            else k_shade<RT_INTEGRATOR_REFERENCE, false><<<grid, kBlock, 0, st>>>(sc->d, cam, rc, io);
-        }
-        launches++; n_shade++;
+        auto launch = [&](bool loop, int grid) {
+            if (loop) {
+                if (path) k_shade<RT_INTEGRATOR_PATH, true><<<grid, kBlock, 0, st>>>(sc->d, cam, rc, io);
+                else k_shade<RT_INTEGRATOR_REFERENCE, true><<<grid, kBlock, 0, st>>>(sc->d, cam, rc, io);
+            } else {
+                if (path) k_shade<RT_INTEGRATOR_PATH, false><<<grid, kBlock, 0, st>>>(sc->d, cam, rc, io);
+                else k_shade<RT_INTEGRATOR_REFERENCE, false><<<grid, kBlock, 0, st>>>(sc->d, cam, rc, io);
+            }
+            launches++; n_shade++;
+        };
+        if (!in_count) { launch(false, std::max(1, Blocks(limit))); return; }     // size known to the host: one 128-ray group per CTA
+        // size known to the device only.  With a hint: the one-group-per-CTA variant over the expected size, then the grid-stride
+        // variant on a small grid for whatever lies beyond (its CTAs leave at once when nothing does).  Without: grid-stride only.
+        if (hint >= 0) {
+            int covered = Blocks(Expect(hint, limit)) * kBlock;
+            io.limit = std::min(limit, covered);
+            launch(false, Blocks(io.limit));
+            if (covered >= limit) return;
+            io.first = first + covered; io.limit = limit - covered;
+            launch(true, std::max(1, std::min(Blocks(io.limit), sc->sm_count)));
+        } else launch(true, std::max(1, std::min(Blocks(limit), sc->sm_count * 8)));
     }
     // Camera rays of one wave into level 0 + their closest hits.  Fused: one launch, slot = work item, `n` slots.  Unfused (A/B and
     // the chunked driver): k_raygen compacts into level 0 and counts into level_count[0].
@@ -587,7 +611,7 @@ struct Driver {
 
     // ---- optimistic driver: whole levels, no host round trip.  Level L lives in queue buffer L % 2; its size is only known to
     // the device (level_count[L]); grids are sized by what the level can hold at most.
-    void EnqueueWave(unsigned long long base, int n) {
+    void EnqueueWave(unsigned long long base, int n, const int* hint /* 2 * (nlev + 1) ints or NULL */, int32_t* hist) {
         DCounters* c = pp->counters.p;
         const bool fused = sc->fused_raygen;
         LaunchPrimary(base, n, fused);
@@ -596,15 +620,16 @@ struct Driver {
         for (int lv = 0; lv < nlev; lv++) {
             DRayQueue q = pp->levels[lv % 2].View(), nq = pp->levels[(lv + 1) % 2].View();
             const int32_t* cnt = (lv == 0 && fused) ? nullptr : &c->level_count[lv];
-            if (lv > 0) Timed(1, [&] { LaunchExtend(q, cnt, 0, (int)upper, &c->cursor_extend[lv]); });
-            Timed(2, [&] { LaunchShade(q, nq, cnt, 0, (int)upper, &c->level_count[lv + 1], &c->shadow_count[lv]); });
+            const int hl = hint ? hint[lv] : -1, hs = hint ? hint[nlev + 1 + lv] : -1;
+            if (lv > 0) Timed(1, [&] { LaunchExtend(q, cnt, 0, (int)upper, &c->cursor_extend[lv], hl); });
+            Timed(2, [&] { LaunchShade(q, nq, cnt, 0, (int)upper, &c->level_count[lv + 1], &c->shadow_count[lv], hl); });
             if (sc->d.num_lights > 0 || path) {
                 long long sup = std::min<long long>((long long)rc.shadow_cap, upper * nl);
-                Timed(3, [&] { LaunchShadow(&c->shadow_count[lv], (int)sup, &c->cursor_shadow[lv]); });
+                Timed(3, [&] { LaunchShadow(&c->shadow_count[lv], (int)sup, &c->cursor_shadow[lv], hs); });
             }
             upper = std::min<long long>((long long)rc.queue_cap, branching ? upper * 2 : upper);
         }
-        k_wave_end<<<1, 256, 0, st>>>(c, nlev);
+        k_wave_end<<<1, 256, 0, st>>>(c, nlev, hist);
         launches++;
     }
 
@@ -752,7 +777,9 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
     proto.rc.pt_importance = opts.pt_importance;
     proto.rg.cam = proto.cam; proto.rg.tl = proto.tl; proto.rg.seed = opts.seed; proto.rg.max_depth = max_depth; proto.rg.base_rest = proto.rg.base_sample = 0; proto.rg.center_only = 0;
 
-    struct FrameResult { uint64_t waves = 0, launches = 0, n_extend = 0, n_shade = 0, n_shadow = 0, secondary = 0, shadow = 0; bool overflow = false; int npipe = 1; double ms[4] = {0, 0, 0, 0}; };
+    const long long hint_key[6] = {cam->nx, cam->ny, proto.cam.spp, opts.integrator * 1000 + max_depth, (long long)proto.tl.rank * 65536 + proto.tl.count,
+                                   (long long)opts.queue_capacity * 4 + (opts.pt_nee ? 1 : 0) + (opts.pt_russian_roulette ? 2 : 0)};
+    struct FrameResult { int stride = 0, wave = 0; unsigned long long nwaves = 0; uint64_t waves = 0, launches = 0, n_extend = 0, n_shade = 0, n_shadow = 0, secondary = 0, shadow = 0; bool overflow = false; int npipe = 1; double ms[4] = {0, 0, 0, 0}; };
 
     // One attempt at the frame.  chunked = false: everything is enqueued without a host round trip and the device's overflow flag is
     // read once at the end.
@@ -787,16 +814,31 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
             CK(cudaStreamWaitEvent(dr.st, sc->ev_start, 0));          // after the accumulator was cleared on the caller's stream
             CK(cudaMemsetAsync(dr.pp->counters.p, 0, sizeof(DCounters), dr.st));
         }
+        const unsigned long long nwaves = (total + (unsigned long long)wave - 1) / (unsigned long long)wave;
+        const int stride = 2 * (proto.nlev + 1);
+        const size_t per_pipe = (size_t)((nwaves + npipe - 1) / npipe) * stride;
+        // hints of the previous frame are valid if it had the same shape (camera, options, wave size)
+        const bool hints_ok = !chunked && sc->use_hints && sc->hint_stride == stride && sc->hints.size() == (size_t)nwaves * stride && wave == sc->hint_wave &&
+                              !memcmp(hint_key, sc->hint_key, sizeof hint_key);
+        if (!chunked)
+            for (int p = 0; p < npipe; p++) {
+                Pipe& pp = sc->pipes[p];
+                pp.hist.Alloc(per_pipe);
+                if (pp.h_hist_n < per_pipe) { if (pp.h_hist) cudaFreeHost(pp.h_hist); pp.h_hist = nullptr; CK(cudaMallocHost((void**)&pp.h_hist, per_pipe * sizeof(int32_t))); pp.h_hist_n = per_pipe; }
+            }
         unsigned long long w = 0;
         for (unsigned long long base = 0; base < total; base += (unsigned long long)wave, w++) {
-            Driver& dr = drs[w % (unsigned long long)npipe];
+            const int p = (int)(w % (unsigned long long)npipe);
+            Driver& dr = drs[p];
             int n = (int)std::min<unsigned long long>((unsigned long long)wave, total - base);
-            if (chunked) dr.ChunkedWave(base, n); else dr.EnqueueWave(base, n);
+            if (chunked) dr.ChunkedWave(base, n);
+            else dr.EnqueueWave(base, n, hints_ok ? &sc->hints[(size_t)w * stride] : nullptr, sc->pipes[p].hist.p + (size_t)(w / (unsigned long long)npipe) * stride);
             fr.waves++;
         }
         for (int p = 0; p < npipe; p++) {
             Pipe& pp = sc->pipes[p];
             CK(cudaMemcpyAsync(pp.h_counters, pp.counters.p, sizeof(DCounters), cudaMemcpyDeviceToHost, pp.st));
+            if (!chunked && per_pipe) CK(cudaMemcpyAsync(pp.h_hist, pp.hist.p, per_pipe * sizeof(int32_t), cudaMemcpyDeviceToHost, pp.st));
             CK(cudaEventRecord(pp.done, pp.st));
         }
         for (int p = 0; p < npipe; p++) CK(cudaStreamWaitEvent(st, sc->pipes[p].done, 0));
@@ -809,6 +851,7 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
             if (chunked) { fr.secondary += dr.secondary; fr.shadow += dr.shadow; }
             else { fr.secondary += hc->total_secondary; fr.shadow += hc->total_shadow; }
             if (hc->overflow) fr.overflow = true;
+            fr.stride = stride; fr.nwaves = nwaves; fr.wave = wave;
             for (int k = 0; k < 4; k++)
                 for (auto& e : sev[p].ev[k]) {
                     float ms = 0; CK(cudaEventElapsedTime(&ms, e.first, e.second));
@@ -834,6 +877,16 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
         sc->wave_limit = cur / 2;
         if (sc->wave_limit < kMinOptimisticWave) { sc->force_chunked = true; chunked = true; }
     }
+    if (!chunked) {
+        // this frame's per-wave queue sizes become the next frame's hints (valid while camera / options / wave size repeat)
+        sc->hints.assign((size_t)fr.nwaves * fr.stride, -1);
+        for (unsigned long long w = 0; w < fr.nwaves; w++) {
+            const int32_t* src = sc->pipes[w % (unsigned long long)fr.npipe].h_hist + (size_t)(w / (unsigned long long)fr.npipe) * fr.stride;
+            for (int k = 0; k < fr.stride; k++) sc->hints[(size_t)w * fr.stride + k] = src[k];
+        }
+        sc->hint_stride = fr.stride; sc->hint_wave = fr.wave;
+        memcpy(sc->hint_key, hint_key, sizeof hint_key);
+    } else sc->hints.clear();
     double ms_resolve = 0;
     {
         cudaEvent_t ra = nullptr, rb = nullptr;
@@ -867,6 +920,45 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
         }
     }
     s.ms_total = ms; s.ms_resolve = ms_resolve;
+}
+
+// Device frame -> the caller's host frame.  The caller's frame is ordinary pageable memory in the reference (new float[],
+// src/Image.cpp:8): a direct D2H copy into it goes through the driver's small bounce buffers.  It is staged through the library's
+// own pinned buffer in 4 MiB pieces instead, the host memcpy of one piece overlapping the DMA of the next.  A caller that already
+// hands over page-locked memory (cudaHostAlloc / cudaHostRegister) gets the plain DMA.
+void FrameToHost(RtScene* sc, const float* d_src, float* out_rgb, size_t n) {
+    {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, out_rgb) == cudaSuccess && pa.type == cudaMemoryTypeHost) {
+            CK(cudaMemcpyAsync(out_rgb, d_src, n * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
+            CK(cudaStreamSynchronize(sc->stream));
+            return;
+        }
+        cudaGetLastError();
+    }
+    if (sc->h_stage_n < n) {
+        if (sc->h_stage) { cudaFreeHost(sc->h_stage); sc->h_stage = nullptr; sc->h_stage_n = 0; }
+        CK(cudaMallocHost((void**)&sc->h_stage, n * sizeof(float)));
+        sc->h_stage_n = n;
+    }
+    const size_t piece = (size_t)1 << 20;   // floats
+    size_t npieces = (n + piece - 1) / piece;
+    std::vector<cudaEvent_t> evs(npieces, nullptr);
+    for (size_t k = 0; k < npieces; k++) {
+        size_t off = k * piece, cnt = std::min(piece, n - off);
+        CK(cudaMemcpyAsync(sc->h_stage + off, d_src + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
+        CK(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
+        CK(cudaEventRecord(evs[k], sc->stream));
+    }
+    cudaError_t first_err = cudaSuccess;
+    for (size_t k = 0; k < npieces; k++) {
+        size_t off = k * piece, cnt = std::min(piece, n - off);
+        cudaError_t e = cudaEventSynchronize(evs[k]);
+        cudaEventDestroy(evs[k]);
+        if (e != cudaSuccess && first_err == cudaSuccess) first_err = e;
+        if (first_err == cudaSuccess) memcpy(out_rgb + off, sc->h_stage + off, cnt * sizeof(float));
+    }
+    CK(first_err);
 }
 
 template <typename F>
@@ -921,6 +1013,7 @@ int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out) {
             if (const char* q = getenv("RT795_DEBUG_BVH")) sc->keep_debug_bvh = atoi(q) != 0;
             if (const char* q = getenv("RT795_SMEM_TLAS")) sc->smem_tlas = atoi(q) != 0;
             if (const char* q = getenv("RT795_FUSED_RAYGEN")) sc->fused_raygen = atoi(q) != 0;
+            if (const char* q = getenv("RT795_HINTS")) sc->use_hints = atoi(q) != 0;
             if (const char* q = getenv("RT795_DRIVER")) sc->env_chunked = sc->force_chunked = !strcmp(q, "chunked");
             sc->k_closest_count = k_trace_persistent<false, true, 0>; sc->k_any_count = k_trace_persistent<true, true, 0>;
             sc->k_rg_closest_count = k_raygen_trace<true, 0>;
@@ -961,6 +1054,7 @@ void rt_scene_destroy(RtScene* sc) {
     for (Pipe& pp : sc->pipes) {
         if (pp.st) cudaStreamSynchronize(pp.st);
         if (pp.h_counters) cudaFreeHost(pp.h_counters);
+        if (pp.h_hist) cudaFreeHost(pp.h_hist);
         if (pp.done) cudaEventDestroy(pp.done);
     }
     if (sc->h_stage) cudaFreeHost(sc->h_stage);
@@ -988,41 +1082,170 @@ int rt_render(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts, fl
         if (opts && opts->resolve_owned_only) throw Invalid{"resolve_owned_only is for rt_render_device (the host frame of rt_render is written whole)"};
         sc->out_dev.Alloc(n);
         RenderDevice(sc, cam, opts, sc->out_dev.p, nullptr);
-        // The caller's frame is ordinary pageable memory in the reference (new float[], src/Image.cpp:8): a direct D2H copy into it
-        // goes through the driver's small bounce buffers.  Stage through the library's own pinned buffer in 4 MiB pieces instead,
-        // the host memcpy of one piece overlapping the DMA of the next.
-        {
-            // a caller that already hands over page-locked memory (cudaHostAlloc / cudaHostRegister) gets the plain DMA
-            cudaPointerAttributes pa;
-            if (cudaPointerGetAttributes(&pa, out_rgb) == cudaSuccess && pa.type == cudaMemoryTypeHost) {
-                CK(cudaMemcpyAsync(out_rgb, sc->out_dev.p, n * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
-                CK(cudaStreamSynchronize(sc->stream));
-                return;
-            }
-            cudaGetLastError();
-        }
-        if (sc->h_stage_n < n) {
-            if (sc->h_stage) { cudaFreeHost(sc->h_stage); sc->h_stage = nullptr; sc->h_stage_n = 0; }
-            CK(cudaMallocHost((void**)&sc->h_stage, n * sizeof(float)));
-            sc->h_stage_n = n;
-        }
-        const size_t piece = (size_t)1 << 20;   // floats
-        size_t npieces = (n + piece - 1) / piece;
-        std::vector<cudaEvent_t> evs(npieces);
-        for (size_t k = 0; k < npieces; k++) {
-            size_t off = k * piece, cnt = std::min(piece, n - off);
-            CK(cudaMemcpyAsync(sc->h_stage + off, sc->out_dev.p + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
-            CK(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
-            CK(cudaEventRecord(evs[k], sc->stream));
-        }
-        for (size_t k = 0; k < npieces; k++) {
-            size_t off = k * piece, cnt = std::min(piece, n - off);
-            cudaError_t e = cudaEventSynchronize(evs[k]);
-            cudaEventDestroy(evs[k]);
-            if (e != cudaSuccess) { for (size_t j = k + 1; j < npieces; j++) cudaEventDestroy(evs[j]); CK(e); }
-            memcpy(out_rgb + off, sc->h_stage + off, cnt * sizeof(float));
-        }
+        FrameToHost(sc, sc->out_dev.p, out_rgb, n);
     });
+}
+
+// ---- multi-GPU inside one process: one RtScene, one context and one host thread per device, the frame cut into
+// interleaved 16x16 tiles, every device's resolve kernel storing its own tiles straight into the ROOT device's frame over
+// NVLink peer memory (k_resolve_owned) - the C ABI counterpart of the reference's 8-thread fan-out inside renderScene
+// (src/Scene.cpp:340-356).  A device without peer access to the root resolves into its own memory; its frame is then copied
+// to the root and merged by the same kernel.
+struct RtSceneGroup {
+    std::vector<RtScene*> scenes;
+    std::vector<int> devices;
+    std::vector<char> peer;                       // device i can store into the root's memory
+    DevBuf<float> frame;                          // root device
+    DevBuf<float> stage;                          // root device: landing buffer for frames of non-peer devices
+    std::vector<float*> local;                    // non-peer devices: their own full-size frame (cudaMalloc on that device)
+    size_t frame_n = 0;
+    // workers
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    unsigned long long generation = 0;
+    int pending = 0;
+    bool quit = false;
+    const RtCameraDesc* job_cam = nullptr;
+    RtRenderOpts job_opts{};
+    std::vector<int> rc;
+    std::vector<std::string> err;
+};
+
+namespace {
+void GroupWorker(RtSceneGroup* g, int i) {
+    unsigned long long seen = 0;
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(g->mu);
+            g->cv_go.wait(lk, [&] { return g->quit || g->generation != seen; });
+            if (g->quit) return;
+            seen = g->generation;
+        }
+        RtRenderOpts o = g->job_opts;
+        o.tile_rank = i; o.tile_count = (int)g->scenes.size(); o.resolve_owned_only = 1;
+        float* dst = g->peer[i] ? g->frame.p : g->local[i];
+        int rc = Guard("rt_group_render", [&] { RenderDevice(g->scenes[i], g->job_cam, &o, dst, nullptr); });
+        {
+            std::lock_guard<std::mutex> lk(g->mu);
+            g->rc[i] = rc;
+            if (rc != RT_OK) g->err[i] = rt_last_error();
+            if (--g->pending == 0) g->cv_done.notify_all();
+        }
+    }
+}
+}  // namespace
+
+int rt_group_create(const RtSceneDesc* desc, int num_devices, const int* devices, RtSceneGroup** out) {
+    if (!out) { SetLastError("rt_group_create: null out"); return RT_ERR_INVALID; }
+    *out = nullptr;
+    if (num_devices < 1 || num_devices > 64) { SetLastError("rt_group_create: num_devices must be in 1..64"); return RT_ERR_INVALID; }
+    RtSceneGroup* g = new RtSceneGroup();
+    g->devices.resize(num_devices);
+    for (int i = 0; i < num_devices; i++) g->devices[i] = devices ? devices[i] : i;
+    g->scenes.assign(num_devices, nullptr);
+    g->rc.assign(num_devices, RT_OK); g->err.assign(num_devices, std::string());
+    // the scene is replicated: build every replica on its own host thread (each device builds its BLASes itself)
+    {
+        std::vector<std::thread> th;
+        for (int i = 0; i < num_devices; i++)
+            th.emplace_back([&, i] { g->rc[i] = rt_scene_create(desc, g->devices[i], &g->scenes[i]); if (g->rc[i] != RT_OK) g->err[i] = rt_last_error(); });
+        for (auto& t : th) t.join();
+    }
+    for (int i = 0; i < num_devices; i++)
+        if (g->rc[i] != RT_OK) { int rc = g->rc[i]; SetLastError("rt_group_create: device " + std::to_string(g->devices[i]) + ": " + g->err[i]); rt_group_destroy(g); return rc; }
+    int rcode = Guard("rt_group_create", [&] {
+        const int root = g->devices[0];
+        g->peer.assign(num_devices, 0);
+        g->local.assign(num_devices, nullptr);
+        for (int i = 0; i < num_devices; i++) {
+            int dev = g->devices[i];
+            if (i == 0) { g->peer[i] = 1; continue; }
+            if (getenv("RT795_GROUP_NO_PEER")) continue;                    // test switch: every other replica takes the copy-and-merge path
+            if (dev == root) { g->peer[i] = 1; continue; }
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, dev, root));
+            if (can) {
+                CK(cudaSetDevice(dev));
+                cudaError_t e = cudaDeviceEnablePeerAccess(root, 0);
+                if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) { g->peer[i] = 1; cudaGetLastError(); }
+                else cudaGetLastError();
+            }
+        }
+        for (int i = 0; i < num_devices; i++) g->workers.emplace_back(GroupWorker, g, i);
+    });
+    if (rcode != RT_OK) { rt_group_destroy(g); return rcode; }
+    *out = g;
+    return RT_OK;
+}
+
+void rt_group_destroy(RtSceneGroup* g) {
+    if (!g) return;
+    {
+        std::lock_guard<std::mutex> lk(g->mu);
+        g->quit = true;
+    }
+    g->cv_go.notify_all();
+    for (auto& t : g->workers) t.join();
+    for (size_t i = 0; i < g->local.size(); i++) if (g->local[i]) { cudaSetDevice(g->devices[i]); cudaFree(g->local[i]); }
+    if (!g->devices.empty()) cudaSetDevice(g->devices[0]);
+    g->frame.Free(); g->stage.Free();
+    for (RtScene* s : g->scenes) rt_scene_destroy(s);
+    delete g;
+}
+
+int rt_group_num_devices(const RtSceneGroup* g) { return g ? (int)g->scenes.size() : 0; }
+RtScene* rt_group_scene(RtSceneGroup* g, int index) { return (g && index >= 0 && index < (int)g->scenes.size()) ? g->scenes[index] : nullptr; }
+int rt_group_uses_peer_memory(const RtSceneGroup* g, int index) { return (g && index >= 0 && index < (int)g->peer.size()) ? g->peer[index] : 0; }
+
+int rt_group_render(RtSceneGroup* g, const RtCameraDesc* cam, const RtRenderOpts* opts, float* out_rgb) {
+    if (!g || !cam || !out_rgb) { SetLastError("rt_group_render: null argument"); return RT_ERR_INVALID; }
+    if (opts && (opts->tile_count > 1 || opts->resolve_owned_only)) { SetLastError("rt_group_render: the group partitions the frame itself (leave tile_rank / tile_count / resolve_owned_only 0)"); return RT_ERR_INVALID; }
+    const int n = (int)g->scenes.size();
+    int rcode = Guard("rt_group_render", [&] {
+        if (cam->nx < 1 || cam->ny < 1) throw Invalid{"bad camera resolution"};
+        const size_t npix3 = (size_t)cam->nx * cam->ny * 3;
+        CK(cudaSetDevice(g->devices[0]));
+        g->frame.Alloc(npix3);
+        for (int i = 0; i < n; i++)
+            if (!g->peer[i] && g->frame_n < npix3) {
+                CK(cudaSetDevice(g->devices[i]));
+                if (g->local[i]) { cudaFree(g->local[i]); g->local[i] = nullptr; }
+                CK(cudaMalloc((void**)&g->local[i], npix3 * sizeof(float)));
+            }
+        g->frame_n = std::max(g->frame_n, npix3);
+        CK(cudaSetDevice(g->devices[0]));
+        {
+            std::lock_guard<std::mutex> lk(g->mu);
+            g->job_cam = cam;
+            if (opts) g->job_opts = *opts; else memset(&g->job_opts, 0, sizeof g->job_opts);
+            g->pending = n;
+            g->generation++;
+        }
+        g->cv_go.notify_all();
+        {
+            std::unique_lock<std::mutex> lk(g->mu);
+            g->cv_done.wait(lk, [&] { return g->pending == 0; });
+        }
+        for (int i = 0; i < n; i++) if (g->rc[i] != RT_OK) throw Invalid{"device " + std::to_string(g->devices[i]) + ": " + g->err[i]};
+        // every worker returned after its device finished (RenderDevice waits for its last kernel): peer stores have landed.
+        RtScene* root = g->scenes[0];
+        CK(cudaSetDevice(root->device));
+        for (int i = 0; i < n; i++) {
+            if (g->peer[i]) continue;
+            g->stage.Alloc(npix3);
+            CK(cudaMemcpyPeer(g->stage.p, root->device, g->local[i], g->devices[i], npix3 * sizeof(float)));
+            RtRenderOpts o; memset(&o, 0, sizeof o);
+            if (opts) o = *opts;
+            o.tile_rank = i; o.tile_count = n;
+            DTiling tl = MakeTiling(cam, &o);
+            long long m = (long long)tl.local_tiles * tl.th * (tl.tw >> 2);
+            if (m > 0) k_resolve_owned<<<Blocks(m), kBlock, 0, root->stream>>>(g->stage.p, g->frame.p, tl, cam->nx, cam->ny, 1.0f);
+            CK(cudaStreamSynchronize(root->stream));
+        }
+        FrameToHost(root, g->frame.p, out_rgb, npix3);
+    });
+    return rcode;
 }
 
 int rt_trace_primary(RtScene* sc, const RtCameraDesc* cam, RtHit* out_hits) {

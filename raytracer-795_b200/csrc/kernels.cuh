@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(kBlock) k_raygen(RaygenArgs a, int count, DRay
 
 // End of a wave: fold the wave's queue sizes into the frame totals and clear the per-wave counters for the next wave on this
 // pipeline (one thread block; replaces a handful of memsets and the host's bookkeeping).
-__global__ void __launch_bounds__(256) k_wave_end(DCounters* c, int nlevels) {
+// `hist` (2 * (nlevels + 1) ints, may be NULL) receives the wave's level and shadow-queue sizes: the next frame's grid hints.
+__global__ void __launch_bounds__(256) k_wave_end(DCounters* c, int nlevels, int32_t* hist) {
     unsigned long long sec = 0, sh = 0;
     for (int l = threadIdx.x; l < nlevels; l += blockDim.x) {
         if (l > 0) sec += (unsigned long long)c->level_count[l];
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(256) k_wave_end(DCounters* c, int nlevels) {
     }
     __syncthreads();
     for (int l = threadIdx.x; l <= nlevels; l += blockDim.x) {
+        if (hist) { hist[l] = c->level_count[l]; hist[nlevels + 1 + l] = l < nlevels ? c->shadow_count[l] : 0; }
         c->level_count[l] = 0;
         if (l < nlevels) { c->shadow_count[l] = 0; c->cursor_extend[l] = 0; c->cursor_shadow[l] = 0; }
     }

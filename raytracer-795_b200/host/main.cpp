@@ -1,6 +1,7 @@
 // CLI with the reference's contract (src/main.cpp:7-14): `raytracer scene.xml` renders every camera of the scene
 // and writes each camera's <ImageName> (P3 PPM for "*.png*" names, half-float EXR otherwise, src/Image.cpp:26-34).
 // Extra, optional knobs after the scene path:  --f32 (also dump <ImageName>.f32 raw floats)  --device N
+// --gpus N (one frame split over devices N0..N0+N-1 of this process: rt_group_render, the in-process fan-out of src/Scene.cpp:340-356)
 // A camera's <Renderer>/<RendererParams>/<Tonemap> elements (extensions) are honoured unless --integrator / --tonemap override them.
 // --cache (keep / reuse <scene.xml>.rt795blob, the prepared scene, while its sources are unchanged)
 // --integrator path|reference  --bvh auto|host|ploc|sah (per-mesh BVH builder)  --seed S  --tonemap KEY BURN SAT GAMMA (writes <ImageName>.tm.ppm)
@@ -13,9 +14,9 @@
 #include <vector>
 
 int main(int argc, char* argv[]) {
-    if (argc < 2) { fprintf(stderr, "usage: %s scene.xml [--f32] [--cache] [--device N] [--integrator path|reference] [--bvh auto|host|ploc|sah] [--seed S] [--tonemap key burn sat gamma]\n", argv[0]); return 2; }
+    if (argc < 2) { fprintf(stderr, "usage: %s scene.xml [--f32] [--cache] [--device N] [--gpus N] [--integrator path|reference] [--bvh auto|host|ploc|sah] [--seed S] [--tonemap key burn sat gamma]\n", argv[0]); return 2; }
     bool f32 = false, tonemap = false, cache = false, cli_integrator = false, cli_seed = false;
-    int device = 0, bvh = RT_BVH_AUTO;
+    int device = 0, gpus = 1, bvh = RT_BVH_AUTO;
     float tm[4] = {0.18f, 1.0f, 1.0f, 2.2f};
     RtRenderOpts opts;
     memset(&opts, 0, sizeof opts);
@@ -24,6 +25,7 @@ int main(int argc, char* argv[]) {
         if (!strcmp(argv[i], "--f32")) f32 = true;
         else if (!strcmp(argv[i], "--cache")) cache = true;
         else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--seed") && i + 1 < argc) { opts.seed = strtoull(argv[++i], nullptr, 10); cli_seed = true; }
         else if (!strcmp(argv[i], "--integrator") && i + 1 < argc) { opts.integrator = !strcmp(argv[++i], "path") ? RT_INTEGRATOR_PATH : RT_INTEGRATOR_REFERENCE; cli_integrator = true; }
         else if (!strcmp(argv[i], "--bvh") && i + 1 < argc) { const char* b = argv[++i]; bvh = !strcmp(b, "host") ? RT_BVH_HOST_SAH : !strcmp(b, "device") || !strcmp(b, "ploc") ? RT_BVH_DEVICE_PLOC : !strcmp(b, "sah") ? RT_BVH_DEVICE_SAH : RT_BVH_AUTO; }
@@ -34,7 +36,7 @@ int main(int argc, char* argv[]) {
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     // One process renders on one GPU: hide the others before the CUDA runtime starts, so its initialisation touches a single
     // device (on an 8-GPU box the start-up of the runtime is the largest part of a one-frame run).
-    if (!getenv("CUDA_VISIBLE_DEVICES")) { setenv("CUDA_VISIBLE_DEVICES", std::to_string(device).c_str(), 1); device = 0; }
+    if (gpus <= 1 && !getenv("CUDA_VISIBLE_DEVICES")) { setenv("CUDA_VISIBLE_DEVICES", std::to_string(device).c_str(), 1); device = 0; }
     auto t0 = now();
     RtHostScene* hs = nullptr;
     int hit = 0;
@@ -44,9 +46,16 @@ int main(int argc, char* argv[]) {
     auto t1b = now();
     if (ndev <= 0) { fprintf(stderr, "no CUDA device: %s\n", rt_last_error()); return 1; }
     RtScene* sc = nullptr;
+    RtSceneGroup* group = nullptr;
     RtSceneDesc desc = *rt_host_scene_desc(hs);
     desc.bvh_builder = bvh;
-    if (rt_scene_create(&desc, device, &sc) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }
+    if (gpus > 1) {
+        if (device + gpus > ndev) { fprintf(stderr, "--gpus %d from device %d: only %d CUDA device(s)\n", gpus, device, ndev); return 1; }
+        std::vector<int> devs(gpus);
+        for (int i = 0; i < gpus; i++) devs[i] = device + i;
+        if (rt_group_create(&desc, gpus, devs.data(), &group) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }
+        sc = rt_group_scene(group, 0);                                    // the root replica: statistics, tone map
+    } else if (rt_scene_create(&desc, device, &sc) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }
     auto t2 = now();
     printf("BVH construction complete.\n");
     {
@@ -65,10 +74,18 @@ int main(int argc, char* argv[]) {
             if (rt_host_camera_render_opts(hs, c, &xo) == RT_OK) { uint64_t seed = cli_seed ? opts.seed : xo.seed; co = xo; co.seed = seed; }
         }
         auto r0 = now();
-        if (rt_render(sc, cam, &co, img.data()) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }
+        if ((group ? rt_group_render(group, cam, &co, img.data()) : rt_render(sc, cam, &co, img.data())) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }
         auto r1 = now();
         RtStats st;
         rt_get_stats(sc, &st);
+        if (group) {                                                      // whole-frame totals over the replicas; time = the slowest device
+            for (int i = 1; i < rt_group_num_devices(group); i++) {
+                RtStats si;
+                rt_get_stats(rt_group_scene(group, i), &si);
+                st.rays_primary += si.rays_primary; st.rays_secondary += si.rays_secondary; st.rays_shadow += si.rays_shadow;
+                if (si.ms_total > st.ms_total) st.ms_total = si.ms_total;
+            }
+        }
         double rays = (double)(st.rays_primary + st.rays_secondary + st.rays_shadow);
         fprintf(stderr, "camera %d: %.3f ms, %.1f Mrays/s (%llu primary, %llu secondary, %llu shadow)\n", c, st.ms_total, rays / st.ms_total * 1e-3,
                 (unsigned long long)st.rays_primary, (unsigned long long)st.rays_secondary, (unsigned long long)st.rays_shadow);
@@ -97,7 +114,7 @@ int main(int argc, char* argv[]) {
         if (rt_host_save_image(name, img.data(), cam->nx, cam->ny) != RT_OK) { fprintf(stderr, "%s\n", rt_last_error()); return 1; }
         fprintf(stderr, "camera %d: rt_render call %.1f ms (first call allocates the ray queues), image write %.1f ms\n", c, ms(r0, r1), ms(w0, now()));
     }
-    rt_scene_destroy(sc);
+    if (group) rt_group_destroy(group); else rt_scene_destroy(sc);
     rt_host_free_scene(hs);
     return 0;
 }

@@ -71,3 +71,55 @@ def test_two_gpu_p2p_gather_matches_single_gpu(rt, scene_dir, tmp_path):
         got = np.load(tmp_path / f)
         assert np.isfinite(got).all(), f
         assert np.allclose(got, alone, rtol=1e-5, atol=1e-5), f
+
+
+# ------------------------------------------------------------------------------------------------ multi-GPU behind the C ABI (rt_group_*)
+def _group_test_exe():
+    return os.path.join(ROOT, "raytracer-795_b200", "bin", "group_render_test")
+
+
+@pytest.mark.parametrize("no_peer", [False, True])
+def test_group_render_c_program(rt, scene_dir, no_peer):
+    """tests/cpp/group_render_test.cpp (plain C ABI, no Python / torch): rt_group_render over every device of the box (on a one-GPU
+    box: two replicas on device 0, which still exercises the worker threads, the tile partition and the owned-tile stores into one
+    frame) equals rt_render on one device to 1e-5; per-rank tile options are rejected.  no_peer: every replica but the root takes
+    the copy-and-merge path a device without peer access gets."""
+    import subprocess
+    exe = _group_test_exe()
+    assert os.path.exists(exe), "build it: make -C raytracer-795_b200"
+    import torch
+    ndev = torch.cuda.device_count()
+    devs = [str(i) for i in range(ndev)] if ndev >= 2 else ["0", "0"]
+    xml = rt.scenes.scene_c2(os.path.join(scene_dir, "c2grp"), res=203, spp=4)      # ragged tiles + branching rays
+    env = dict(os.environ)
+    if no_peer:
+        env["RT795_GROUP_NO_PEER"] = "1"
+    r = subprocess.run([exe, xml] + devs, capture_output=True, text=True, env=env)
+    print(r.stdout.strip())
+    assert r.returncode == 0, (r.stdout, r.stderr[-2000:])
+    assert f"devices={len(devs)}" in r.stdout and "rejected_tile_opts=1" in r.stdout
+    if no_peer:
+        assert "peer=1 " in r.stdout              # only the root writes directly
+
+
+def test_group_render_binding_matches_single_device(rt, scene_dir):
+    """The same through the ctypes binding, three replicas (or every GPU of the box), C4-style instanced scene with motion blur."""
+    import torch
+    ndev = torch.cuda.device_count()
+    devs = list(range(ndev)) if ndev >= 2 else [0, 0, 0]
+    xml = rt.scenes.scene_c4(os.path.join(scene_dir, "c4grp"), res=(256, 144), spp=4, n=40)
+    hs = rt.HostScene(xml)
+    cam = hs.camera(0)
+    sc = rt.Scene(hs.desc, 0)
+    alone = sc.render(cam)
+    sc.close()
+    g = rt.SceneGroup(hs.desc, devs)
+    a = g.render(cam)
+    b = g.render(cam)                                                          # a second frame reuses workers, frame and queues
+    assert np.allclose(a, alone, rtol=1e-5, atol=1e-5) and np.allclose(b, alone, rtol=1e-5, atol=1e-5)
+    st = [g.stats(i) for i in range(len(devs))]
+    assert sum(s.rays_primary for s in st) == cam.nx * cam.ny * cam.num_samples     # the replicas partition the frame exactly
+    assert all(s.rays_primary > 0 for s in st)
+    with pytest.raises(rt.RtError):
+        g.render(cam, rt.default_opts(tile_rank=0, tile_count=2))
+    g.close(); hs.close()
