@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RT795_ABI_VERSION 1
+#define RT795_ABI_VERSION 2
 
 typedef enum RtStatus {
     RT_OK = 0,
@@ -57,7 +57,11 @@ enum { RT_TEX_IMAGE = 0, RT_TEX_PERLIN = 1 };
 /* NoiseConversion, src/defs.h:11 */
 enum { RT_NC_ABSVAL = 0, RT_NC_LINEAR = 1, RT_NC_NONE = 2 };
 /* LightType, src/Light.h:12 */
-enum { RT_LIGHT_POINT = 0, RT_LIGHT_AREA = 1, RT_LIGHT_DIRECTIONAL = 2, RT_LIGHT_SPOT = 3, RT_LIGHT_ENVIRONMENT = 4 };
+enum { RT_LIGHT_POINT = 0, RT_LIGHT_AREA = 1, RT_LIGHT_DIRECTIONAL = 2, RT_LIGHT_SPOT = 3, RT_LIGHT_ENVIRONMENT = 4,
+       /* object lights (course HW7, pages/Page7.md:9-13; no code in the reference snapshot): a top-level object that emits.  Rays that
+        * hit it see its radiance; next-event estimation samples its surface: a mesh by triangle area then uniformly on the triangle,
+        * a sphere uniformly over the cone of directions it subtends */
+       RT_LIGHT_MESH = 5, RT_LIGHT_SPHERE = 6 };
 /* top-level entry kinds */
 enum { RT_OBJ_SPHERE = 0, RT_OBJ_MESH = 1 };
 /* image pixel formats (what the reference's texture loaders produce, src/Texture.cpp:41-74) */
@@ -127,6 +131,7 @@ typedef struct RtObject {
     float inv[12];           /* rows 0..2 of M^-1 (3x4)                             */
     float inv_t[9];          /* upper 3x3 of (M^-1)^T, row-major (normal matrix)    */
     float blur[3];           /* MotionBlur translation (world units per unit time)  */
+    float radiance[3];       /* object lights (<LightMesh> / <LightSphere> <Radiance>): emitted radiance, front side; 0 0 0 = not a light */
 } RtObject;
 
 /* Light, src/Light.h + constructors in src/Light.cpp.  Fields unused by a type are ignored. */
@@ -139,6 +144,7 @@ typedef struct RtLight {
     float coverage_deg;      /* spot: CoverageAngle (full angle, degrees)           */
     float falloff_deg;       /* spot: FalloffAngle (full angle, degrees)            */
     int32_t image;           /* environment: 0-based index into images[]            */
+    int32_t object;          /* mesh / sphere light: index of the emitting top-level entry in objects[] (its radiance = `intensity`) */
 } RtLight;
 
 /* Per-mesh acceleration-structure builder (csrc/bvh_device.cu, csrc/bvh_build.cpp).  All produce the same node formats; any

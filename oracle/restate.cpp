@@ -104,6 +104,9 @@ struct Ctx {
     int nx, ny, spp, n;
     float invnx, invny, pw, ph, sw, sh;
     bool dof; float focus, aperture;
+    // object lights (RT_LIGHT_MESH / RT_LIGHT_SPHERE; no reference code - DESIGN.md §7): world-space sampling records per light
+    struct LightGeom { V3 c; float R = 0; std::vector<V3> tri; std::vector<float> cdf; float area = 0; };
+    std::vector<LightGeom> lgeom;
 };
 
 V3 TriCenter(const RtSceneDesc* s, int tri) {   // Triangle::GetCenter, src/Shape.cpp:179-190
@@ -611,6 +614,50 @@ V3 LightShading(const Ctx& cx, int li, const Ray& ray, const Hit& ret, const RtM
             V3 E = ld3(L.intensity) * ((L.size * L.size) * (cosTheta / dsq));
             return shade(normalized(sp - p), E);
         }
+        case RT_LIGHT_SPHERE: case RT_LIGHT_MESH: {                                              // object lights: twin of csrc/shade.cuh light_eval
+            const Ctx::LightGeom& g = cx.lgeom[li];
+            const float pi = 3.14159265358979323846f;
+            Rng4 r = philox(cx.seed, pixel, sample, node, DIM_LIGHT0 + li * DIM_LIGHT_STRIDE);
+            V3 target, E;
+            if (L.type == RT_LIGHT_SPHERE) {
+                V3 pc = g.c - p;
+                float R = g.R, d2 = dot(pc, pc);
+                if (!(d2 > R * R * 1.0002f)) return V3(0, 0, 0);
+                float d = std::sqrt(d2), cosmax = std::sqrt(std::max(0.f, 1.f - R * R / d2));
+                float ct = 1.f - r.u[0] * (1.f - cosmax), st = std::sqrt(std::max(0.f, 1.f - ct * ct));
+                float ph = 2.0f * pi * r.u[1];
+                V3 w = pc / d, u = OrthonormalU(w), v = cross(w, u);
+                V3 dir = normalized(u * (st * std::cos(ph)) + v * (st * std::sin(ph)) + w * ct);
+                float th = d * ct - std::sqrt(std::max(0.f, R * R - d2 * st * st));
+                target = p + dir * th;
+                E = ld3(L.intensity) * (2.0f * pi * (1.f - cosmax));
+            } else {
+                int ntri = (int)g.cdf.size();
+                if (ntri <= 0 || !(g.area > 0.f)) return V3(0, 0, 0);
+                int lo = 0, hi = ntri - 1;
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (r.u[0] < g.cdf[mid]) hi = mid; else lo = mid + 1; }
+                V3 a = g.tri[3 * lo], b = g.tri[3 * lo + 1], c = g.tri[3 * lo + 2];
+                float su = std::sqrt(r.u[1]), b1 = 1.f - su, b2 = r.u[2] * su;
+                target = a * b1 + b * b2 + c * (1.f - b1 - b2);
+                V3 ln = normalized(cross(c - b, a - b));
+                V3 dv = p - target;
+                float dsq = dot(dv, dv);
+                float cosl = dot(ln, dv) / std::sqrt(std::max(dsq, 1e-30f));
+                if (!(cosl > 0.f)) return V3(0, 0, 0);
+                E = ld3(L.intensity) * (g.area * cosl / dsq);
+            }
+            V3 dv = target - p;
+            float D = norm(dv);
+            V3 wi = dv / D;
+            float eps = s->shadow_ray_eps, sdot = dot(n, wi);
+            float tmax = (-eps * sdot + std::sqrt(std::max(0.f, eps * eps * sdot * sdot - eps * eps + D * D))) * 0.9998f;
+            V3 rad = shade(wi, E);
+            if (rad.x == 0 && rad.y == 0 && rad.z == 0) return rad;
+            Ray sr{origin, wi, ray.time};
+            Hit h = FindIntersection(cx, sr);
+            if (h.full && dot(h.point - origin, wi) < tmax) return V3(0, 0, 0);                 // something before the emitter's own surface
+            return rad;
+        }
         case RT_LIGHT_ENVIRONMENT: {                                                             // src/Light.cpp:551-660
             V3 u = OrthonormalU(n), w = cross(n, u);
             V3 dir = n;
@@ -668,12 +715,24 @@ Spawn MirrorReflectance(const Ctx& cx, const Ray& ray, const Hit& ret, const RtM
 
 V3 RecursiveShading(const Ctx& cx, const Ray& ray, const Hit& ret, int depth, uint32_t pixel, uint32_t sample, uint32_t node);
 
+// Radiance an object light (<LightMesh> / <LightSphere>) sends back along the ray that hit its front side (extension).
+inline V3 Emitted(const Ctx& cx, const Ray& ray, const Hit& ret) {
+    if (!ret.full || ret.object < 0) return V3(0, 0, 0);
+    V3 le = ld3(cx.s->objects[ret.object].radiance);
+    if ((le.x != 0 || le.y != 0 || le.z != 0) && dot(ret.normal, ray.d) < 0) return le;
+    return V3(0, 0, 0);
+}
+V3 RecursiveShadingCore(const Ctx& cx, const Ray& ray, const Hit& ret, int depth, uint32_t pixel, uint32_t sample, uint32_t node);
+V3 RecursiveShading(const Ctx& cx, const Ray& ray, const Hit& ret, int depth, uint32_t pixel, uint32_t sample, uint32_t node) {
+    return RecursiveShadingCore(cx, ray, ret, depth, pixel, sample, node) + Emitted(cx, ray, ret);
+}
+
 inline V3 Recurse(const Ctx& cx, const Spawn& sp, int depth, uint32_t pixel, uint32_t sample, uint32_t node) {
     return RecursiveShading(cx, sp.ray, sp.ret, depth, pixel, sample, node);
 }
 
 // Scene::RecursiveShading, src/Scene.cpp:148-219 (+ DielectricRefraction :57-118, FresnelReflectance :120-128, BeerLaw :130-133)
-V3 RecursiveShading(const Ctx& cx, const Ray& ray, const Hit& ret, int depth, uint32_t pixel, uint32_t sample, uint32_t node) {
+V3 RecursiveShadingCore(const Ctx& cx, const Ray& ray, const Hit& ret, int depth, uint32_t pixel, uint32_t sample, uint32_t node) {
     if (!ret.full) return V3(0, 0, 0);
     const RtSceneDesc* s = cx.s;
     const RtMaterial& mat = s->materials[ret.matIndex - 1];
@@ -744,7 +803,7 @@ V3 RecursiveShading(const Ctx& cx, const Ray& ray, const Hit& ret, int depth, ui
 
 // Scene::Shading, src/Scene.cpp:230-241
 V3 Shading(const Ctx& cx, const Ray& ray, const Hit& ret, uint32_t pixel, uint32_t sample) {
-    if (ret.dm == RT_DM_REPLACE_ALL) return ret.textureColor;
+    if (ret.dm == RT_DM_REPLACE_ALL) return ret.textureColor + Emitted(cx, ray, ret);
     return RecursiveShading(cx, ray, ret, cx.s->max_recursion_depth, pixel, sample, 1);
 }
 
@@ -863,7 +922,7 @@ V3 PathTrace(const Ctx& cx, Ray ray, uint32_t pixel, uint32_t sample, int row, i
             break;
         }
         const RtMaterial& mat = s->materials[h.matIndex - 1];
-        V3 Le = ld3(mat.emission);
+        V3 Le = ld3(mat.emission) + (h.object >= 0 ? ld3(s->objects[h.object].radiance) : V3(0, 0, 0));
         if ((Le.x > 0 || Le.y > 0 || Le.z > 0) && (count_emission || !cx.opts.pt_nee) && dot(h.normal, ray.d) < 0) L = L + cmul(beta, Le);
         if ((int)node == max_depth + 1) break;
         V3 n = h.normal;
@@ -954,6 +1013,46 @@ void BuildCtx(Ctx& cx, const RtSceneDesc* s, const RtCameraDesc* cam, const RtRe
         BuildNode(s, bv, 0, s->meshes[m].tri_count, 0, 0);
     }
     SetupCamera(cx, cam);
+    // object lights: world-space sampling records (forward transform = inverse of the stored M^-1, in double; a sphere's radius scales
+    // with the cube root of |det M|), as csrc/core.cu builds them
+    cx.lgeom.assign(std::max(1, s->num_lights), Ctx::LightGeom());
+    for (int li = 0; li < s->num_lights; li++) {
+        const RtLight& L = s->lights[li];
+        if (L.type != RT_LIGHT_MESH && L.type != RT_LIGHT_SPHERE) continue;
+        const RtObject& o = s->objects[L.object];
+        double A[3][3], t[3], M[3][3], T[3];
+        for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) A[r][c] = o.inv[r * 4 + c]; t[r] = o.inv[r * 4 + 3]; }
+        double det = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) + A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+        M[0][0] = (A[1][1] * A[2][2] - A[1][2] * A[2][1]) / det; M[0][1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) / det; M[0][2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) / det;
+        M[1][0] = (A[1][2] * A[2][0] - A[1][0] * A[2][2]) / det; M[1][1] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) / det; M[1][2] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) / det;
+        M[2][0] = (A[1][0] * A[2][1] - A[1][1] * A[2][0]) / det; M[2][1] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) / det; M[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) / det;
+        for (int r = 0; r < 3; r++) T[r] = -(M[r][0] * t[0] + M[r][1] * t[1] + M[r][2] * t[2]);
+        auto xf = [&](const float* p) { double q[3]; for (int r = 0; r < 3; r++) q[r] = M[r][0] * p[0] + M[r][1] * p[1] + M[r][2] * p[2] + T[r]; return V3((float)q[0], (float)q[1], (float)q[2]); };
+        Ctx::LightGeom& g = cx.lgeom[li];
+        if (L.type == RT_LIGHT_SPHERE) {
+            const RtSphere& sp = s->spheres[o.geom];
+            double detM = M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) + M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+            g.c = xf(sp.center); g.R = (float)(sp.radius * std::cbrt(std::fabs(detM)));
+        } else {
+            const RtMesh& me = s->meshes[o.geom];
+            std::vector<double> areas(me.tri_count);
+            double total = 0;
+            for (int k = 0; k < me.tri_count; k++) {
+                const int* ix = s->tri_indices + 3 * (size_t)(me.first_tri + k);
+                double P[3][3];
+                for (int v = 0; v < 3; v++) for (int r = 0; r < 3; r++) { const float* p = s->vertices + 3 * (size_t)ix[v]; P[v][r] = M[r][0] * p[0] + M[r][1] * p[1] + M[r][2] * p[2] + T[r]; }
+                double e1[3] = {P[1][0] - P[0][0], P[1][1] - P[0][1], P[1][2] - P[0][2]}, e2[3] = {P[2][0] - P[0][0], P[2][1] - P[0][1], P[2][2] - P[0][2]};
+                double nn[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+                areas[k] = 0.5 * std::sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+                total += areas[k];
+                for (int v = 0; v < 3; v++) g.tri.push_back(V3((float)P[v][0], (float)P[v][1], (float)P[v][2]));
+            }
+            double run = 0;
+            g.cdf.resize(me.tri_count);
+            for (int k = 0; k < me.tri_count; k++) { run += areas[k]; g.cdf[k] = k == me.tri_count - 1 ? 1.0f : (float)(total > 0 ? run / total : 1.0); }
+            g.area = (float)total;
+        }
+    }
 }
 
 }  // namespace

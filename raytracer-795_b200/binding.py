@@ -54,12 +54,12 @@ class RtSphere(C.Structure):
 
 class RtObject(C.Structure):
     _fields_ = [("kind", C.c_int32), ("geom", C.c_int32), ("mat_index", C.c_int32), ("tex", C.c_int32 * 2),
-                ("tex_offset", C.c_int32), ("inv", C.c_float * 12), ("inv_t", C.c_float * 9), ("blur", f3)]
+                ("tex_offset", C.c_int32), ("inv", C.c_float * 12), ("inv_t", C.c_float * 9), ("blur", f3), ("radiance", f3)]
 
 
 class RtLight(C.Structure):
     _fields_ = [("type", C.c_int32), ("position", f3), ("direction", f3), ("intensity", f3), ("size", C.c_float),
-                ("coverage_deg", C.c_float), ("falloff_deg", C.c_float), ("image", C.c_int32)]
+                ("coverage_deg", C.c_float), ("falloff_deg", C.c_float), ("image", C.c_int32), ("object", C.c_int32)]
 
 
 class RtSceneDesc(C.Structure):

@@ -116,6 +116,8 @@ struct RtScene {
     DevBuf<DImage> images;
     std::vector<DevBuf<unsigned char>> image_px;
     DevBuf<RtLight> lights;
+    DevBuf<DLightGeom> light_geom;
+    DevBuf<float4> light_tris;
     bool has_dielectric = false;
     bool has_specular = false;             // some material spawns continuation rays (mirror / conductor / dielectric)
     int bvh_depth = 0;
@@ -220,8 +222,12 @@ void Validate(const RtSceneDesc* s) {
     }
     for (int i = 0; i < s->num_lights; i++) {
         const RtLight& l = s->lights[i];
-        if (l.type < RT_LIGHT_POINT || l.type > RT_LIGHT_ENVIRONMENT) bad("unknown light type");
+        if (l.type < RT_LIGHT_POINT || l.type > RT_LIGHT_SPHERE) bad("unknown light type");
         if (l.type == RT_LIGHT_ENVIRONMENT && (l.image < 0 || l.image >= s->num_images)) bad("environment light image index out of range");
+        if (l.type == RT_LIGHT_MESH || l.type == RT_LIGHT_SPHERE) {
+            if (l.object < 0 || l.object >= s->num_objects) bad("object light: object index out of range");
+            if (s->objects[l.object].kind != (l.type == RT_LIGHT_MESH ? RT_OBJ_MESH : RT_OBJ_SPHERE)) bad("object light: the object is not of the light's kind");
+        }
     }
     if (s->bvh_builder < RT_BVH_AUTO || s->bvh_builder > RT_BVH_DEVICE_SAH) bad("bvh_builder must be one of RT_BVH_*");
     if (s->env_light_index < -1 || s->env_light_index >= s->num_lights) bad("env_light_index out of range");
@@ -346,6 +352,8 @@ bool BuildAndUpload(RtScene* sc, const RtSceneDesc* s, bool allow_device) {
     for (int i = 0; i < s->num_spheres; i++) spheres[i] = make_float4(s->spheres[i].center[0], s->spheres[i].center[1], s->spheres[i].center[2], s->spheres[i].radius);
     int max_blas_depth = 0, max_blas_stack4 = 0;
     std::vector<int32_t> root4(std::max(1, s->num_objects), 0);
+    struct Fwd { double M[3][3], T[3]; };
+    std::vector<Fwd> fwd(s->num_objects);                                // forward (object -> world) transforms, for the object lights
     for (int i = 0; i < s->num_objects; i++) {
         const RtObject& o = s->objects[i];
         DObjectXf& x = oxf[i];
@@ -374,6 +382,7 @@ bool BuildAndUpload(RtScene* sc, const RtSceneDesc* s, bool allow_device) {
         M[2][0] = (A[1][0] * A[2][1] - A[1][1] * A[2][0]) / det; M[2][1] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) / det; M[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) / det;
         double T[3];
         for (int r = 0; r < 3; r++) T[r] = -(M[r][0] * t[0] + M[r][1] * t[1] + M[r][2] * t[2]);
+        memcpy(fwd[i].M, M, sizeof M); memcpy(fwd[i].T, T, sizeof T);
         Aabb wb; wb.Reset();
         for (int corner = 0; corner < 8; corner++) {
             double p[3] = {corner & 1 ? ob.hi[0] : ob.lo[0], corner & 2 ? ob.hi[1] : ob.lo[1], corner & 4 ? ob.hi[2] : ob.lo[2]};
@@ -395,6 +404,46 @@ bool BuildAndUpload(RtScene* sc, const RtSceneDesc* s, bool allow_device) {
         h.kind = o.kind; h.geom = o.geom;
         h.smooth = o.kind == RT_OBJ_MESH ? s->meshes[o.geom].smooth : 0;
         h.first_tri = o.kind == RT_OBJ_MESH ? s->meshes[o.geom].first_tri : 0;
+        memcpy(h.radiance, o.radiance, 12); h.pad = 0;
+    }
+    // ---- object lights: world-space sampling records (a sphere light keeps its shape under a similarity transform only: its
+    // radius is scaled by the cube root of |det M|; motion blur does not move emitters)
+    std::vector<DLightGeom> lgeom(std::max(1, s->num_lights));
+    std::vector<float4> ltris;
+    memset(lgeom.data(), 0, lgeom.size() * sizeof(DLightGeom));
+    for (int li = 0; li < s->num_lights; li++) {
+        const RtLight& L = s->lights[li];
+        if (L.type != RT_LIGHT_MESH && L.type != RT_LIGHT_SPHERE) continue;
+        const RtObject& o = s->objects[L.object];
+        const Fwd& f = fwd[L.object];
+        auto xf = [&](const float* p, double* q) { for (int r = 0; r < 3; r++) q[r] = f.M[r][0] * p[0] + f.M[r][1] * p[1] + f.M[r][2] * p[2] + f.T[r]; };
+        DLightGeom& g = lgeom[li];
+        if (L.type == RT_LIGHT_SPHERE) {
+            const RtSphere& sp = s->spheres[o.geom];
+            double c[3]; xf(sp.center, c);
+            double det = f.M[0][0] * (f.M[1][1] * f.M[2][2] - f.M[1][2] * f.M[2][1]) - f.M[0][1] * (f.M[1][0] * f.M[2][2] - f.M[1][2] * f.M[2][0]) + f.M[0][2] * (f.M[1][0] * f.M[2][1] - f.M[1][1] * f.M[2][0]);
+            g.sphere = make_float4((float)c[0], (float)c[1], (float)c[2], (float)(sp.radius * std::cbrt(std::fabs(det))));
+        } else {
+            const RtMesh& me = s->meshes[o.geom];
+            g.first_tri = (int)ltris.size() / 3; g.tri_count = me.tri_count;
+            double total = 0;
+            std::vector<double> areas(me.tri_count);
+            for (int t = 0; t < me.tri_count; t++) {
+                const int* ix = s->tri_indices + 3 * (size_t)(me.first_tri + t);
+                double a[3], b[3], c[3];
+                xf(s->vertices + 3 * (size_t)ix[0], a); xf(s->vertices + 3 * (size_t)ix[1], b); xf(s->vertices + 3 * (size_t)ix[2], c);
+                double e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+                double n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+                areas[t] = 0.5 * std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+                total += areas[t];
+                ltris.push_back(make_float4((float)a[0], (float)a[1], (float)a[2], 0.f));
+                ltris.push_back(make_float4((float)b[0], (float)b[1], (float)b[2], 0.f));
+                ltris.push_back(make_float4((float)c[0], (float)c[1], (float)c[2], 0.f));
+            }
+            double run = 0;
+            for (int t = 0; t < me.tri_count; t++) { run += areas[t]; ltris[(size_t)(g.first_tri + t) * 3].w = t == me.tri_count - 1 ? 1.0f : (float)(total > 0 ? run / total : 1.0); }
+            g.area = (float)total;
+        }
     }
     BuiltBvh tl;
     BuildSahBvh(obounds.data(), s->num_objects, 1, &tl);
@@ -467,6 +516,9 @@ bool BuildAndUpload(RtScene* sc, const RtSceneDesc* s, bool allow_device) {
     sc->textures.Upload(s->textures, s->num_textures, st);
     std::vector<RtLight> lights(s->lights, s->lights + s->num_lights);
     sc->lights.Upload(lights.data(), lights.size(), st);
+    sc->light_geom.Upload(lgeom.data(), lgeom.size(), st);
+    if (ltris.empty()) ltris.push_back(make_float4(0.f, 0.f, 0.f, 1.f));
+    sc->light_tris.Upload(ltris.data(), ltris.size(), st);
     std::vector<DImage> dimg(s->num_images);
     sc->image_px.resize(s->num_images);
     for (int i = 0; i < s->num_images; i++) {
@@ -492,6 +544,7 @@ bool BuildAndUpload(RtScene* sc, const RtSceneDesc* s, bool allow_device) {
     d.tris = sc->tris.p; d.obj_xf = sc->obj_xf.p; d.spheres = sc->spheres.p; sc->tlas_base2 = tlas_base;
     d.obj_sh = sc->obj_sh.p; d.tri_idx = sc->tri_idx.p; d.vertices = sc->vertices.p; d.normals = sc->normals.p; d.texcoords = sc->texcoords.p;
     d.materials = sc->materials.p; d.textures = sc->textures.p; d.images = sc->images.p; d.lights = sc->lights.p;
+    d.light_geom = sc->light_geom.p; d.light_tris = sc->light_tris.p;
     d.num_lights = s->num_lights; d.num_objects = s->num_objects; d.max_depth = s->max_recursion_depth;
     d.shadow_eps = s->shadow_ray_eps; d.int_eps = s->int_test_eps;
     memcpy(d.background, s->background_color, 12); memcpy(d.ambient, s->ambient_light, 12);

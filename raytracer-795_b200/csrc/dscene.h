@@ -27,6 +27,15 @@ struct DObjectSh {
     int32_t first_tri;                  // mesh first triangle (global numbering), for primitive ids
     int32_t kind;                       // RT_OBJ_*
     int32_t geom;
+    float radiance[3];                  // object light: emitted radiance (front side), else 0
+    int32_t pad;
+};
+// Sampling record of an object light (RT_LIGHT_MESH / RT_LIGHT_SPHERE), indexed like DScene.lights; world space.
+struct DLightGeom {
+    float4 sphere;                      // sphere light: centre, radius
+    int32_t first_tri, tri_count;       // mesh light: its triangles in DScene.light_tris
+    float area;                         // mesh light: total world-space area
+    int32_t pad;
 };
 struct DImage { const void* pixels; int32_t width, height, format, pad; };
 
@@ -51,6 +60,8 @@ struct DScene {
     const struct RtTexture* textures;
     const DImage* images;
     const struct RtLight* lights;
+    const DLightGeom* light_geom;       // per light (zeros for the analytic light types)
+    const float4* light_tris;           // mesh lights: 3 x float4 per triangle, world space: (a, cdf), (b, 0), (c, 0); cdf = cumulative area fraction
     int32_t num_lights, num_objects;
     int32_t max_depth;
     float shadow_eps, int_eps;

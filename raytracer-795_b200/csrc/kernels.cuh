@@ -174,8 +174,10 @@ __global__ void __launch_bounds__(kBlock, LOOP ? 4 : RT795_SHADE_MIN_BLOCKS) k_s
             } else {
                 s = eval_surface(sc, ro, rd, rtime, h);
                 mat = sc.materials[s.mat_index - 1];
+                float3 Le = v3(0.f, 0.f, 0.f);
+                if (!is_zero(s.Le) && dot(s.N, rd) < 0.f) Le = W * s.Le;                               // object light seen by this ray (extension; the reference snapshot has none)
                 if ((flags & RAY_PRIMARY) && s.dm == RT_DM_REPLACE_ALL) {                              // Scene::Shading, src/Scene.cpp:232-234
-                    pend = W * s.tex_color; has_pend = true;
+                    pend = W * s.tex_color + Le; has_pend = true;
                 } else {
                     const float eps = sc.shadow_eps;
                     auto reflect_ray = [&](float3 weight, uint32_t fl, int bmat, float bs) {            // MirrorReflectance, src/Scene.cpp:32-55
@@ -245,6 +247,7 @@ __global__ void __launch_bounds__(kBlock, LOOP ? 4 : RT795_SHADE_MIN_BLOCKS) k_s
                         }
                     }
                     if (lit) { pend = W * (v3(sc.ambient) * v3(mat.ambient)); has_pend = true; }       // Scene::ambient, src/Scene.cpp:22-30
+                    if (!is_zero(Le)) { pend = pend + Le; has_pend = true; }
                 }
             }
         } else {
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(kBlock, LOOP ? 4 : RT795_SHADE_MIN_BLOCKS) k_s
             } else {
                 s = eval_surface(sc, ro, rd, rtime, h);
                 mat = sc.materials[s.mat_index - 1];
-                float3 Le = v3(mat.emission);
+                float3 Le = v3(mat.emission) + s.Le;
                 if ((Le.x > 0.f || Le.y > 0.f || Le.z > 0.f) && (count_emission || !rc.pt_nee) && dot(s.N, rd) < 0.f) { pend = W * Le; has_pend = true; }
                 if ((int)node < max_depth + 1) {
                     const float eps = sc.shadow_eps;

@@ -119,7 +119,7 @@ RT_D bool light_eval(const DScene& sc, int li, const RtMaterial& m, const Surfac
     const float eps = sc.shadow_eps;
     float3 P = s.P, N = s.N;
     float3 target;
-    bool finite = true;
+    bool finite = true, object_light = false;
     float falloff = 1.f;
     float3 E;
     switch (L.type) {
@@ -154,6 +154,43 @@ RT_D bool light_eval(const DScene& sc, int li, const RtMaterial& m, const Surfac
             float dsq = length(P - target); dsq = dsq * dsq;
             E = v3(L.intensity) * ((L.size * L.size) * (cosT / dsq));
         } break;
+        case RT_LIGHT_SPHERE: {
+            // object light, sphere: a direction uniform over the cone the sphere subtends from P (pdf = 1 / (2 pi (1 - cos theta_max)));
+            // the shadow interval ends just before the sphere's own surface.  (No reference code: pages/Page7.md:9-13, 137-153.)
+            const DLightGeom g = sc.light_geom[li];
+            float3 pc = v3(g.sphere) - P;
+            float R = g.sphere.w, d2 = dot(pc, pc);
+            if (!(d2 > R * R * 1.0002f)) return false;                                 // P on / inside the emitter: no cone
+            float d = sqrtf(d2), cosmax = sqrtf(fmaxf(0.f, 1.f - R * R / d2));
+            float4 r = philox_uniform4(seed, pixel, sample, node, DIM_LIGHT0 + li * DIM_LIGHT_STRIDE);
+            float ct = 1.f - r.x * (1.f - cosmax), st = sqrtf(fmaxf(0.f, 1.f - ct * ct)), sp_, cp_;
+            sincosf(2.0f * pi * r.y, &sp_, &cp_);
+            float3 w = pc / d, u = orthonormal_u(w), v = cross(w, u);
+            float3 dir = normalize0(u * (st * cp_) + v * (st * sp_) + w * ct);
+            float th = d * ct - sqrtf(fmaxf(0.f, R * R - d2 * st * st));              // first intersection of P + t dir with the sphere
+            target = P + dir * th;
+            E = v3(L.intensity) * (2.0f * pi * (1.f - cosmax));
+            object_light = true;
+        } break;
+        case RT_LIGHT_MESH: {
+            // object light, mesh: a triangle with probability proportional to its area, a uniform point on it; only the front side emits
+            const DLightGeom g = sc.light_geom[li];
+            if (g.tri_count <= 0 || !(g.area > 0.f)) return false;
+            float4 r = philox_uniform4(seed, pixel, sample, node, DIM_LIGHT0 + li * DIM_LIGHT_STRIDE);
+            const float4* lt = sc.light_tris + (size_t)g.first_tri * 3;
+            int lo = 0, hi = g.tri_count - 1;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (r.x < __ldg(lt + 3 * (size_t)mid).w) hi = mid; else lo = mid + 1; }
+            float4 a4 = __ldg(lt + 3 * (size_t)lo), b4 = __ldg(lt + 3 * (size_t)lo + 1), c4 = __ldg(lt + 3 * (size_t)lo + 2);
+            float su = sqrtf(r.y), b1 = 1.f - su, b2 = r.z * su;
+            target = v3(a4) * b1 + v3(b4) * b2 + v3(c4) * (1.f - b1 - b2);
+            float3 ln = normalize0(cross(v3(c4) - v3(b4), v3(a4) - v3(b4)));          // the reference's face normal, (c-b) x (a-b)
+            float3 dv = P - target;
+            float dsq = dot(dv, dv);
+            float cosl = dot(ln, dv) * rsqrtf(fmaxf(dsq, 1e-30f));
+            if (!(cosl > 0.f)) return false;                                          // P behind the emitting side
+            E = v3(L.intensity) * (g.area * cosl / dsq);
+            object_light = true;
+        } break;
         default: {   // RT_LIGHT_ENVIRONMENT
             float3 u = orthonormal_u(N), w = cross(N, u);
             float3 dir = N;
@@ -179,6 +216,7 @@ RT_D bool light_eval(const DScene& sc, int li, const RtMaterial& m, const Surfac
         float sdot = dot(N, out.wi);
         // occluded iff the closest hit h satisfies |P-h| < |P-target| with h = P + N*eps + t*wi  
         out.tmax = -eps * sdot + sqrtf(fmaxf(0.f, eps * eps * sdot * sdot - eps * eps + D * D));
+        if (object_light) out.tmax *= 0.9998f;     // the emitter is geometry: the occluding interval ends just before its own surface
     } else out.tmax = 3.0e38f;
     // the reference normalises (target - P) again for wi (e.g. src/Light.cpp:243); same vector
     out.radiance = surface_response(m, s, ray_d, out.wi, E) * falloff;

@@ -24,6 +24,7 @@ struct Surface {
     int dm;              // ReturnVal::dm
     int mat_index;       // 1-based
     int prim_in_mesh;    // triangle index within its mesh (face order); 0 for spheres
+    float3 Le;           // emitted radiance of an object light (<LightMesh> / <LightSphere>), else 0
 };
 
 // Perlin tables of the reference (src/Perlin.cpp:4-25) packed into immediates: no constant-memory lookups with
@@ -142,6 +143,7 @@ RT_D Surface eval_surface(const DScene& sc, float3 o, float3 d, float time, cons
     s.tex_normalizer = 1.0f;
     const DObjectSh& ob = sc.obj_sh[h.obj];
     s.mat_index = ob.mat_index;
+    s.Le = v3(ob.radiance);
     float3 oo, od; int root;
     xf_ray(sc.obj_xf + h.obj, o, d, time, oo, od, root);
     float3 p_obj = oo + od * h.t;      // object-space hit point (the reference textures in object space)

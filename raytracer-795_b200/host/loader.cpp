@@ -101,6 +101,8 @@ struct ParsedObject {
     bool reset_transform = false;
     int base_object = -1;     // instances: index (into objects_) of the base mesh object
     bool is_mesh_elem = false;
+    bool is_light = false;    // <LightSphere> / <LightMesh>
+    float radiance[3] = {0, 0, 0};
     Mat4 model;
 };
 
@@ -492,9 +494,13 @@ private:
     bool Objects(std::string* err) {
         auto objs = root_->FirstChildElement("Objects");
         if (!objs) return Fail(err, "<Objects> missing");
-        for (auto o = objs->FirstChildElement("Sphere"); o; o = o->NextSiblingElement("Sphere")) {
+        // <LightSphere> / <LightMesh> (course HW7 object lights, pages/Page7.md:9-13; not parsed by the reference snapshot): a <Sphere> /
+        // <Mesh> with a <Radiance> child.  They follow the plain elements of their kind in the top-level order.
+        for (const char* tag : {"Sphere", "LightSphere"})
+        for (auto o = objs->FirstChildElement(tag); o; o = o->NextSiblingElement(tag)) {
             ParsedObject po; po.kind = RT_OBJ_SPHERE;
             if (!CommonObject(o, &po, true, err)) return false;
+            if (tag[0] == 'L' && (!Vec3(o->FirstChildElement("Radiance"), po.radiance) || !(po.is_light = true))) return Fail(err, "LightSphere needs <Radiance>");
             int c = 0; float R = 0;
             auto ce = o->FirstChildElement("Center"); auto re = o->FirstChildElement("Radius");
             if (!ce || !ce->QueryIntText(&c) || !re || !re->QueryFloatText(&R)) return Fail(err, "Sphere needs Center and Radius");
@@ -517,9 +523,11 @@ private:
             objects_.push_back(po);
         }
         mesh_start_ = (int)objects_.size();
-        for (auto o = objs->FirstChildElement("Mesh"); o; o = o->NextSiblingElement("Mesh")) {
-            ParsedObject po; po.kind = RT_OBJ_MESH; po.is_mesh_elem = true;
+        for (const char* tag : {"Mesh", "LightMesh"})
+        for (auto o = objs->FirstChildElement(tag); o; o = o->NextSiblingElement(tag)) {
+            ParsedObject po; po.kind = RT_OBJ_MESH; po.is_mesh_elem = tag[0] == 'M';    // MeshInstance looks its base up among <Mesh> elements only
             if (!CommonObject(o, &po, true, err)) return false;
+            if (tag[0] == 'L' && (!Vec3(o->FirstChildElement("Radiance"), po.radiance) || !(po.is_light = true))) return Fail(err, "LightMesh needs <Radiance>");
             bool smooth = false;
             if (auto a = o->FindAttributePrefix("shadingMode")) smooth = StartsWith(a->value.c_str(), "smooth");
             auto fe = o->FirstChildElement("Faces");
@@ -574,7 +582,7 @@ private:
             o->QueryIntAttribute("baseMeshId", &base_id);
             o->QueryBoolAttribute("resetTransform", &po.reset_transform);
             for (int i = mesh_start_; i < (int)objects_.size(); i++)               // last match wins (no break), Parser.h:1184-1188
-                if (objects_[i].id == base_id) po.base_object = i;
+                if (objects_[i].id == base_id && objects_[i].is_mesh_elem) po.base_object = i;
             if (po.base_object < 0) return Fail(err, "MeshInstance baseMeshId does not name a <Mesh>");
             const ParsedObject& base = objects_[po.base_object];
             po.geom = base.geom;
@@ -697,6 +705,13 @@ private:
             for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) o.inv[r * 4 + c] = inv.m[r][c];
             for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) o.inv_t[r * 3 + c] = inv.m[c][r];
             memcpy(o.blur, po.blur, 12);
+            if (po.is_light) {
+                memcpy(o.radiance, po.radiance, 12);
+                RtLight l; memset(&l, 0, sizeof l);
+                l.type = po.kind == RT_OBJ_SPHERE ? RT_LIGHT_SPHERE : RT_LIGHT_MESH; l.image = -1;
+                l.object = (int)hs_->objects.size(); memcpy(l.intensity, po.radiance, 12);
+                hs_->lights.push_back(l);                                          // after the <Lights> elements, in top-level order
+            }
             if (o.mat_index < 1 || o.mat_index > (int)hs_->materials.size()) return Fail(err, "object Material index out of range");
             for (int k = 0; k < 2; k++) if (o.tex[k] < 0 || o.tex[k] > (int)hs_->textures.size()) return Fail(err, "object Textures id out of range");
             hs_->objects.push_back(o);

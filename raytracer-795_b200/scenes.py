@@ -664,6 +664,103 @@ def scene_c5(outdir: str, res=(3840, 2160), spp: int = 1024, name: str = "c5", d
     return path
 
 
+def scene_object_lights(outdir: str, variant: str = "cornell", res=(160, 120), spp: int = 16, name: str = "olights", depth: int = 6) -> str:
+    """Object lights (<LightMesh> / <LightSphere>, the course's HW7 elements; extensions of the reference grammar), for the path tracer.
+    variant "cornell": closed Cornell box, a <LightMesh> lamp under the ceiling (rotated and translated by object transformations),
+        a scaled + translated <LightSphere>, a diffuse and a mirror sphere; every surface a normalised BRDF (kd / pi).
+    variant "furnace": the inside of a closed box that IS the only light: <LightMesh> of 12 triangles facing inwards, radiance 1,
+        albedo 0.5 (normalised modified Blinn-Phong with ks = 0, so f = kd / pi exactly).  Every ray sees radiance
+        sum_k 0.5^k over the bounces the depth allows, with next-event estimation on or off - the estimator's pdf / area /
+        cosine factors all have to be right for that."""
+    os.makedirs(outdir, exist_ok=True)
+    if variant == "furnace":
+        L = 4.0
+        verts = [(-L, -L, L), (L, -L, L), (L, -L, -L), (-L, -L, -L), (-L, L, L), (L, L, L), (L, L, -L), (-L, L, -L)]
+        faces = (_quad_faces(verts, (0, 1, 2, 3), (0, 1, 0)) + _quad_faces(verts, (4, 5, 6, 7), (0, -1, 0)) + _quad_faces(verts, (3, 2, 6, 7), (0, 0, 1)) +
+                 _quad_faces(verts, (0, 1, 5, 4), (0, 0, -1)) + _quad_faces(verts, (0, 3, 7, 4), (1, 0, 0)) + _quad_faces(verts, (1, 2, 6, 5), (-1, 0, 0)))
+        mats = _material(1, (0, 0, 0), (0.5, 0.5, 0.5), (0, 0, 0), 1, brdf=1)
+        cam = "<Position>0.3 -0.4 0.9</Position><Gaze>0.2 0.1 -1</Gaze><Up>0 1 0</Up><FovY>70</FovY>"
+        objects = f"""    <LightMesh id="1"><Material>1</Material><Radiance>1 1 1</Radiance><Faces>
+{_faces_text(faces)}
+    </Faces></LightMesh>"""
+        lights = "    <AmbientLight>0 0 0</AmbientLight>"
+        transforms = ""
+    else:
+        X, Y, Z0, Z1 = 10.0, 20.0, -10.0, 10.0
+        verts = [(-X, 0, Z1), (X, 0, Z1), (X, 0, Z0), (-X, 0, Z0), (-X, Y, Z1), (X, Y, Z1), (X, Y, Z0), (-X, Y, Z0),
+                 (-1, 0, 1), (1, 0, 1), (1, 0, -1), (-1, 0, -1),          # unit lamp quad 8-11 (scaled / rotated / moved by transformations)
+                 (-4.5, 4.0, 1.0), (4.5, 3.0, 3.5), (0, 0, 0)]             # spheres 12, 13; light sphere centre 14 (moved by a transformation)
+        white = (_quad_faces(verts, (0, 1, 2, 3), (0, 1, 0)) + _quad_faces(verts, (4, 5, 6, 7), (0, -1, 0)) + _quad_faces(verts, (3, 2, 6, 7), (0, 0, 1)) +
+                 _quad_faces(verts, (0, 1, 5, 4), (0, 0, -1)))
+        red = _quad_faces(verts, (0, 3, 7, 4), (1, 0, 0))
+        green = _quad_faces(verts, (1, 2, 6, 5), (-1, 0, 0))
+        lamp = _quad_faces(verts, (8, 9, 10, 11), (0, -1, 0))
+        mats = (_material(1, (0, 0, 0), (0.75, 0.75, 0.75), (0.1, 0.1, 0.1), 1, brdf=1) + _material(2, (0, 0, 0), (0.75, 0.1, 0.08), (0.05, 0.05, 0.05), 1, brdf=1) +
+                _material(3, (0, 0, 0), (0.1, 0.65, 0.12), (0.05, 0.05, 0.05), 1, brdf=1) + _material(4, (0, 0, 0), (0.6, 0.6, 0.3), (0.2, 0.2, 0.2), 1, brdf=1) +
+                _material(5, (0, 0, 0), (0, 0, 0), (0, 0, 0), 1, "mirror", (0.9, 0.9, 0.9)) + _material(6, (0, 0, 0), (0.3, 0.3, 0.3), (0, 0, 0), 1, brdf=1))
+        cam = "<Position>0.4 10.2 9.5</Position><Gaze>-0.011 -0.017 -1</Gaze><Up>0 1 0</Up><FovY>75</FovY>"
+        objects = f"""    <Sphere id="1"><Material>4</Material><Center>13</Center><Radius>4.0</Radius></Sphere>
+    <Sphere id="2"><Material>5</Material><Center>14</Center><Radius>3.0</Radius></Sphere>
+    <LightSphere id="3"><Material>6</Material><Center>15</Center><Radius>1.0</Radius><Transformations>s2 t2</Transformations><Radiance>90 80 60</Radiance></LightSphere>
+    <Mesh id="4"><Material>1</Material><Faces>
+{_faces_text(white)}
+    </Faces></Mesh>
+    <Mesh id="5"><Material>2</Material><Faces>
+{_faces_text(red)}
+    </Faces></Mesh>
+    <Mesh id="6"><Material>3</Material><Faces>
+{_faces_text(green)}
+    </Faces></Mesh>
+    <LightMesh id="7"><Material>6</Material><Transformations>s1 r1 t1</Transformations><Radiance>60 56 50</Radiance><Faces>
+{_faces_text(lamp)}
+    </Faces></LightMesh>"""
+        lights = "    <AmbientLight>0 0 0</AmbientLight>"
+        transforms = """  <Transformations>
+    <Scaling id="1">3 1 2.5</Scaling>
+    <Scaling id="2">1.5 1.5 1.5</Scaling>
+    <Rotation id="1">12 0 0 1</Rotation>
+    <Translation id="1">-1 19.2 0.5</Translation>
+    <Translation id="2">6.5 12 -5</Translation>
+  </Transformations>
+"""
+    xml = f"""<Scene>
+  <MaxRecursionDepth>{depth}</MaxRecursionDepth>
+  <BackgroundColor>0 0 0</BackgroundColor>
+  <ShadowRayEpsilon>1e-3</ShadowRayEpsilon>
+  <IntersectionTestEpsilon>1e-6</IntersectionTestEpsilon>
+  <Cameras>
+    <Camera id="1">
+      {cam}
+      <NearDistance>1</NearDistance>
+      <ImageResolution>{res[0]} {res[1]}</ImageResolution>
+      <NumSamples>{spp}</NumSamples>
+      <ImageName>{name}.exr</ImageName>
+      <Renderer>PathTracing</Renderer>
+      <RendererParams>NextEventEstimation ImportanceSampling</RendererParams>
+    </Camera>
+  </Cameras>
+  <BRDFs>
+    <ModifiedBlinnPhong id="1" normalized="true"><Exponent>20</Exponent></ModifiedBlinnPhong>
+  </BRDFs>
+  <Lights>
+{lights}
+  </Lights>
+  <Materials>
+{mats}  </Materials>
+{transforms}  <VertexData>
+{chr(10).join("    " + _fmt(p) for p in verts)}
+  </VertexData>
+  <Objects>
+{objects}
+  </Objects>
+</Scene>
+"""
+    path = os.path.join(outdir, f"{name}.xml")
+    with open(path, "w") as fh:
+        fh.write(xml)
+    return path
+
+
 CONFIGS = {
     "c1": dict(gen=scene_c1, label="C1 Whitted: 5 spheres + 4 triangles, 1 point light, 800x800, 1 spp, depth 6"),
     "c2": dict(gen=scene_c2, label="C2 Cornell box, dielectric + conductor spheres, area light, glossy, 1024x1024, 100 spp"),

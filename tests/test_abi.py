@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(rt):
     for n in names:
         assert hasattr(lib, n), f"librt795.so does not export {n}"
     assert sorted(rt.binding.CORE_SYMBOLS) == names
-    assert lib.rt_abi_version() == 1
+    assert lib.rt_abi_version() == 2
 
 
 def test_struct_layouts_match_header(rt, tmp_path):
