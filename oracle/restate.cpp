@@ -619,6 +619,7 @@ V3 LightShading(const Ctx& cx, int li, const Ray& ray, const Hit& ret, const RtM
             const float pi = 3.14159265358979323846f;
             Rng4 r = philox(cx.seed, pixel, sample, node, DIM_LIGHT0 + li * DIM_LIGHT_STRIDE);
             V3 target, E;
+            float object_tmax = 3.0e38f;                          // where the shadow ray (from p + n eps) meets the emitter's own surface
             if (L.type == RT_LIGHT_SPHERE) {
                 V3 pc = g.c - p;
                 float R = g.R, d2 = dot(pc, pc);
@@ -631,6 +632,9 @@ V3 LightShading(const Ctx& cx, int li, const Ray& ray, const Hit& ret, const RtM
                 float th = d * ct - std::sqrt(std::max(0.f, R * R - d2 * st * st));
                 target = p + dir * th;
                 E = ld3(L.intensity) * (2.0f * pi * (1.f - cosmax));
+                V3 oc = origin - g.c;
+                float bq = dot(oc, dir), cq = dot(oc, oc) - R * R, dq = bq * bq - cq;
+                object_tmax = dq > 0.f ? std::max(0.f, -bq - std::sqrt(dq)) : 3.0e38f;
             } else {
                 int ntri = (int)g.cdf.size();
                 if (ntri <= 0 || !(g.area > 0.f)) return V3(0, 0, 0);
@@ -645,12 +649,16 @@ V3 LightShading(const Ctx& cx, int li, const Ray& ray, const Hit& ret, const RtM
                 float cosl = dot(ln, dv) / std::sqrt(std::max(dsq, 1e-30f));
                 if (!(cosl > 0.f)) return V3(0, 0, 0);
                 E = ld3(L.intensity) * (g.area * cosl / dsq);
+                V3 wdir = -dv / std::sqrt(std::max(dsq, 1e-30f));
+                float den = dot(ln, wdir);
+                object_tmax = den < 0.f ? dot(ln, a - origin) / den : 3.0e38f;
             }
             V3 dv = target - p;
             float D = norm(dv);
             V3 wi = dv / D;
             float eps = s->shadow_ray_eps, sdot = dot(n, wi);
-            float tmax = (-eps * sdot + std::sqrt(std::max(0.f, eps * eps * sdot * sdot - eps * eps + D * D))) * 0.9998f;
+            float tmax = -eps * sdot + std::sqrt(std::max(0.f, eps * eps * sdot * sdot - eps * eps + D * D));
+            tmax = std::min(tmax * 1.0002f, object_tmax) * 0.9998f;
             V3 rad = shade(wi, E);
             if (rad.x == 0 && rad.y == 0 && rad.z == 0) return rad;
             Ray sr{origin, wi, ray.time};

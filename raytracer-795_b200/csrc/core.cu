@@ -739,10 +739,10 @@ struct Driver {
 };
 
 size_t QueueCapacity(const RtRenderOpts* opts) {
-    // default 4 Mi rays per wave.  Every launch ends in a tail where the last rays finish on a mostly idle GPU; measured on C4
-    // with ONE pipeline: 1 Mi 83.7 ms, 2 Mi 73.6, 4 Mi 67.6, 8 Mi 65.2, 16 Mi 64.9 per frame.  With two pipelines the tails
-    // overlap with the other wave and the size matters little: 2 x 4 Mi 61.8, 2 x 8 Mi 62.9, 4 x 4 Mi 61.6, 3 x 16 Mi 63.7.
-    size_t cap = opts->queue_capacity > 0 ? (size_t)opts->queue_capacity : ((size_t)1 << 22);
+    // default 8 Mi rays per wave.  Every launch ends in a tail where the last rays finish on a mostly idle GPU, and the deeper levels
+    // of a wave are sparse; bigger waves amortise both.  Round 2, two pipelines, ms per frame at 4 / 8 / 16 Mi (profiles/bench/
+    // r02_queue_capacity.txt): C2 34.3 / 31.6 / 31.1, C4 53.8 / 53.4 / 53.5, C5 (32 spp) 140.8 / 137.5 / 135.9.
+    size_t cap = opts->queue_capacity > 0 ? (size_t)opts->queue_capacity : ((size_t)1 << 23);
     if (opts->queue_capacity <= 0) if (const char* e = getenv("RT795_QUEUE_CAP")) { long long v = atoll(e); if (v > 0) cap = (size_t)v; }   // tuning override of the default
     return std::min<size_t>(std::max<size_t>(cap, 64), (size_t)1 << 28);
 }

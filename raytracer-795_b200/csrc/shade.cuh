@@ -120,6 +120,7 @@ RT_D bool light_eval(const DScene& sc, int li, const RtMaterial& m, const Surfac
     float3 P = s.P, N = s.N;
     float3 target;
     bool finite = true, object_light = false;
+    float object_tmax = 3.0e38f;
     float falloff = 1.f;
     float3 E;
     switch (L.type) {
@@ -170,6 +171,10 @@ RT_D bool light_eval(const DScene& sc, int li, const RtMaterial& m, const Surfac
             float th = d * ct - sqrtf(fmaxf(0.f, R * R - d2 * st * st));              // first intersection of P + t dir with the sphere
             target = P + dir * th;
             E = v3(L.intensity) * (2.0f * pi * (1.f - cosmax));
+            // where the SHADOW ray (origin P + N eps) meets the sphere: the offset moves that point a lot for grazing directions
+            float3 oc = P + N * eps - v3(g.sphere);
+            float bq = dot(oc, dir), cq = dot(oc, oc) - R * R, dq = bq * bq - cq;
+            object_tmax = dq > 0.f ? fmaxf(0.f, -bq - sqrtf(dq)) : 3.0e38f;           // the offset ray passes the sphere by: nothing of its own to avoid
             object_light = true;
         } break;
         case RT_LIGHT_MESH: {
@@ -189,6 +194,11 @@ RT_D bool light_eval(const DScene& sc, int li, const RtMaterial& m, const Surfac
             float cosl = dot(ln, dv) * rsqrtf(fmaxf(dsq, 1e-30f));
             if (!(cosl > 0.f)) return false;                                          // P behind the emitting side
             E = v3(L.intensity) * (g.area * cosl / dsq);
+            {   // where the shadow ray (origin P + N eps) meets the emitting triangle's plane
+                float3 wdir = -dv * rsqrtf(fmaxf(dsq, 1e-30f));
+                float den = dot(ln, wdir);
+                object_tmax = den < 0.f ? dot(ln, v3(a4) - (P + N * eps)) / den : 3.0e38f;
+            }
             object_light = true;
         } break;
         default: {   // RT_LIGHT_ENVIRONMENT
@@ -216,7 +226,8 @@ RT_D bool light_eval(const DScene& sc, int li, const RtMaterial& m, const Surfac
         float sdot = dot(N, out.wi);
         // occluded iff the closest hit h satisfies |P-h| < |P-target| with h = P + N*eps + t*wi  
         out.tmax = -eps * sdot + sqrtf(fmaxf(0.f, eps * eps * sdot * sdot - eps * eps + D * D));
-        if (object_light) out.tmax *= 0.9998f;     // the emitter is geometry: the occluding interval ends just before its own surface
+        // the emitter is geometry: the occluding interval ends just before the shadow ray reaches the emitter's own surface
+        if (object_light) out.tmax = fminf(out.tmax * 1.0002f, object_tmax) * 0.9998f;
     } else out.tmax = 3.0e38f;
     // the reference normalises (target - P) again for wi (e.g. src/Light.cpp:243); same vector
     out.radiance = surface_response(m, s, ray_d, out.wi, E) * falloff;

@@ -82,7 +82,10 @@ bool LoadPng(const std::string& path, LoadedImage* out, std::string* err) {
         if (pos + 12 + len > file.size()) { *err = "truncated PNG: " + path; return false; }
         const unsigned char* type = &file[pos + 4];
         const unsigned char* d = &file[pos + 8];
-        if (!memcmp(type, "IHDR", 4)) { w = BE32(d); h = BE32(d + 4); depth = d[8]; ctype = d[9]; interlace = d[12]; }
+        if (!memcmp(type, "IHDR", 4)) {
+            if (len != 13) { *err = "PNG: bad IHDR length: " + path; return false; }
+            w = BE32(d); h = BE32(d + 4); depth = d[8]; ctype = d[9]; interlace = d[12];
+        }
         else if (!memcmp(type, "PLTE", 4)) plte.assign(d, d + len);
         else if (!memcmp(type, "tRNS", 4)) trns.assign(d, d + len);
         else if (!memcmp(type, "IDAT", 4)) idat.insert(idat.end(), d, d + len);

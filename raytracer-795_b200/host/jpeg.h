@@ -182,6 +182,7 @@ inline bool DecodeJpeg(const std::vector<uint8_t>& file, int* width, int* height
             case 0xc2: progressive = true;   // SOF2: same frame header; coefficients arrive spread over several scans
             // fall through
             case 0xc0: case 0xc1: {   // SOF0 / SOF1
+                if (have_frame) return fail("JPEG: second frame header");     // a later SOF would re-size the planes under scans already decoded
                 if (se - s < 6) return fail("JPEG: truncated SOF");
                 if (s[0] != 8) return fail("JPEG: only 8-bit samples are supported");
                 H = (s[1] << 8) | s[2]; W = (s[3] << 8) | s[4];

@@ -136,6 +136,9 @@ inline bool LoadPly(const std::string& path, PlyMesh* out, std::string* err) {
                     size_t cnt;
                     if (ascii) { double c; if (!(as >> c)) { *err = "PLY truncated"; return false; } cnt = (size_t)c; }
                     else { int cs = SizeOf(pr.cty); if (cs == 0 || p + cs > end) { *err = "PLY truncated"; return false; } cnt = (size_t)(swap ? ReadBin(p, pr.count_type, true) : ReadLE(p, pr.cty)); p += cs; }
+                    // a list cannot be longer than what is left of the file (1 byte / 1 token per item at least): checked BEFORE allocating
+                    if (!ascii && cnt > (size_t)(end - p)) { *err = "PLY truncated"; return false; }
+                    if (ascii && cnt > (size_t)1 << 24) { *err = "PLY: unreasonable list length"; return false; }
                     std::vector<int64_t> lst(cnt);
                     int ts = SizeOf(pr.ty);
                     if (!ascii && (ts == 0 || p + (size_t)ts * cnt > end)) { *err = "PLY truncated"; return false; }

@@ -453,6 +453,62 @@ def test_mutated_inputs_never_crash(rt, tmp_path):
     assert outcomes["loaded"] > 0 and outcomes["rejected"] > 0
 
 
+def test_targeted_corruptions_are_rejected(rt, tmp_path):
+    """The three structural corruptions a byte-flip fuzzer rarely hits: a SECOND frame header after the first progressive scan (it
+    would re-size the coefficient planes under scans already decoded), an IHDR chunk shorter than 13 bytes, and a PLY face list whose
+    count field is far larger than the file."""
+    import struct
+    import zlib
+    from PIL import Image
+    d = str(tmp_path / "tc")
+    os.makedirs(d)
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, size=(40, 56, 3)).astype(np.uint8)
+    # (1) progressive JPEG with its SOF2 segment repeated (smaller dimensions the second time) right before the second scan
+    Image.fromarray(img).save(os.path.join(d, "p.jpg"), quality=85, progressive=True)
+    data = open(os.path.join(d, "p.jpg"), "rb").read()
+    sof = data.index(b"\xff\xc2")
+    seglen = struct.unpack(">H", data[sof + 2:sof + 4])[0]
+    seg = bytearray(data[sof:sof + 2 + seglen])
+    seg[5:9] = struct.pack(">HH", 8, 8)                                       # H, W of the forged frame
+    sos = [i for i in range(len(data) - 1) if data[i] == 0xff and data[i + 1] == 0xda]
+    assert len(sos) >= 2
+    forged = data[:sos[1]] + bytes(seg) + data[sos[1]:]
+    with open(os.path.join(d, "dup.jpg"), "wb") as f:
+        f.write(forged)
+    with pytest.raises(rt.RtError) as e:
+        _load_image_texture(rt, d, "dup.jpg")
+    assert "second frame header" in str(e.value)
+    # (2) PNG whose IHDR chunk is 9 bytes long
+    def chunk(t, body):
+        c = struct.pack(">I", len(body)) + t + body
+        return c + struct.pack(">I", zlib.crc32(t + body) & 0xffffffff)
+    raw = b"".join(b"\x00" + img[y].tobytes() for y in range(img.shape[0]))
+    short = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIB", 56, 40, 8)) + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+    with open(os.path.join(d, "short.png"), "wb") as f:
+        f.write(short)
+    with pytest.raises(rt.RtError) as e:
+        _load_image_texture(rt, d, "short.png")
+    assert "IHDR" in str(e.value)
+    # (3) binary PLY: the first face claims 2^31 - 1 indices
+    xml = rt.scenes.scene_c4(d, res=(32, 18), spp=1, n=10, deterministic=True)
+    ply = os.path.join(d, "c4_mesh.ply")
+    b = bytearray(open(ply, "rb").read())
+    hdr_end = b.index(b"end_header\n") + len(b"end_header\n")
+    header = bytes(b[:hdr_end]).decode()
+    assert "property list uchar int" in header
+    patched = header.replace("property list uchar int", "property list int int")
+    nverts = int(header.split("element vertex ")[1].split()[0])
+    nprops = header.split("element face")[0].count("property float")
+    body = bytes(b[hdr_end:])
+    faces_at = nverts * nprops * 4
+    forged = patched.encode() + body[:faces_at] + struct.pack("<i", 2 ** 31 - 1) + body[faces_at + 1:]
+    with open(ply, "wb") as f:
+        f.write(forged)
+    with pytest.raises(rt.RtError):
+        rt.HostScene(xml)
+
+
 def test_camera_renderer_and_tonemap_extensions(rt, tmp_path):
     """<Renderer> / <RendererParams> / <Tonemap> in a camera (course vocabulary; not parsed by the reference snapshot, SURVEY
     App. B) -> rt_host_camera_render_opts / rt_host_camera_tonemap, and they survive the scene blob."""
