@@ -31,6 +31,11 @@ import __graft_entry__ as ge  # noqa: E402
 
 # ALGORITHMIC bytes per ray, SURVEY.md §8d:  B_ray = 48 + 32*(ceil(log2 N_top) + ceil(log2(N_tri/4))) + 48*4 + 64*[instanced]
 B_RAY = {"c1": 224, "c2": 400, "c3": 784, "c4": 1040, "c5": 416}
+# ALGORITHMIC lane-ops per ray, SURVEY.md §8d ("ALGORITHMIC flops"): ~40 lane-ops per inner-node visit of the ideal binary descent
+# (two child slabs) and ~50 per triangle test: OPS_ray = 40*(ceil(log2 N_top) + ceil(log2(N_tri/4))) + 50*4  (C1: one primitive).
+# The traversal kernels are bound by the SM issue rate (instructions x active lanes), not by HBM: this is the roofline that binds.
+OPS_RAY = {"c1": 40 * 4 + 50, "c2": 40 * 5 + 200, "c3": 40 * 17 + 200, "c4": 40 * 23 + 200, "c5": 40 * 5 + 200}
+SM_COUNT, LANES_PER_SM = 148, 128            # B200: 148 SMs x 4 schedulers x 32 lanes, one warp instruction per scheduler and clock
 
 WORKLOADS = {
     # name: (generator kwargs for the full configuration, kwargs for the bounded CPU sample).  The CPU sample keeps the full
@@ -127,6 +132,15 @@ def measured_peaks() -> tuple[float, str]:
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_kernel(config: str, kernel: str):
+    """issue-slot utilisation / active lanes per instruction / pipe utilisation of `kernel` from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(config, {}).get(f"k_{kernel}_ncu")
+    return None
 
 
 def ncu_traffic(config: str, kernel: str):
@@ -258,7 +272,15 @@ def run_ours(args, rt):
     cam = hs.camera(0)
     # library default (AUTO): big meshes get the host builder's binned-SAH tree, built on the GPU (profiles/bench/r01_bvh_builders_c4.json)
     builder = {"host": rt.RT_BVH_HOST_SAH, "ploc": rt.RT_BVH_DEVICE_PLOC, "sah": rt.RT_BVH_DEVICE_SAH, "auto": rt.RT_BVH_AUTO}[args.bvh]
-    sc = rt.Scene(hs.desc, local, bvh_builder=builder)
+    # the first rt_scene_create of a process pays module load + first-use allocations of the device builder (cub temporaries): build
+    # three times, report every build and keep the last scene
+    build_ms = []
+    sc = None
+    for _ in range(3 if not args.small else 1):
+        if sc is not None:
+            sc.close()
+        sc = rt.Scene(hs.desc, local, bvh_builder=builder)
+        build_ms.append(float(sc.stats().ms_bvh_build))
     integrator = rt.RT_INTEGRATOR_PATH if args.config == "c5" else rt.RT_INTEGRATOR_REFERENCE
     npix = cam.nx * cam.ny
     # N>1: every rank's resolve kernel stores its tiles into rank 0's framebuffer over NVLink peer memory (multigpu.FrameGather;
@@ -392,18 +414,43 @@ def run_ours(args, rt):
     stage = {"ms_extend": st.ms_extend, "ms_shade": st.ms_shade, "ms_shadow": st.ms_shadow, "ms_raygen": st.ms_raygen, "ms_resolve": st.ms_resolve,
              "launches_extend": int(st.launches_extend), "launches_shadow": int(st.launches_shadow)}
 
-    def kernel_roofline(name, label, rays, ms, launches):
-        a = rays * b_ray / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        return {"kernel": label, "achieved": a, "frac": a / peak, "traffic": ncu_traffic(args.config, name), "rays_per_launch": rays / max(1, launches),
-                "avg_launch_ms": ms / max(1, launches), "stage_ms": ms}
+    # one more frame with the per-ray counters build: measured node visits / triangle tests and SIMT lane counts of the two traversal kernels
+    co = rt.default_opts(integrator=integrator, tile_rank=rank, tile_count=world, collect_counters=2, resolve_owned_only=gather.resolve_owned_only)
+    render_step(co)
+    torch.cuda.synchronize()
+    cs = sc.stats()
+    ops_ray = OPS_RAY[args.config]
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    issue_peak = SM_COUNT * LANES_PER_SM * sm_mhz * 1e6 / 1e9             # G lane-ops/s at the clock observed under load
+    issue_src = f"{SM_COUNT} SMs x {LANES_PER_SM} lanes x {sm_mhz:.0f} MHz (SM clock sampled during the timed region)"
 
-    k2 = kernel_roofline("extend", "k_trace_persistent<closest-hit> (K2 extend)", ext_rays, st.ms_extend, int(st.launches_extend))
-    k4 = kernel_roofline("shadow", "k_trace_persistent<any-hit> (K4 occlusion)", int(st.rays_shadow), st.ms_shadow, int(st.launches_shadow))
+    def kernel_roofline(name, label, rays, ms, launches, visits, prims, diag):
+        hbm = rays * b_ray / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        alg = rays * ops_ray / (ms * 1e-3) / 1e9 if ms > 0 else 0.0      # G lane-ops/s, algorithmic
+        # measured work of the 4-wide tree: a 4-wide node visit tests four child slabs (2 x the binary visit's 40), a triangle test 50
+        work = (visits * 80 + prims * 50) / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        extra = ncu_kernel(args.config, name)
+        return {"kernel": label, "issue": {"achieved": alg, "peak": issue_peak, "unit": "Glaneops/s", "frac": alg / issue_peak, "measured_work_glaneops": work,
+                                           "measured_work_frac": work / issue_peak, "node_visits_per_ray": visits / max(1, rays), "prim_tests_per_ray": prims / max(1, rays),
+                                           "leaf_phase_lanes": (diag[3] / diag[2]) if diag[2] else None, "ncu": extra},
+                "hbm": {"achieved": hbm, "peak": peak, "unit": "GB/s", "frac": hbm / peak, "traffic": ncu_traffic(args.config, name)},
+                "rays_per_launch": rays / max(1, launches), "avg_launch_ms": ms / max(1, launches), "stage_ms": ms}
+
+    k2 = kernel_roofline("extend", "k_raygen_trace / k_trace_persistent<closest-hit> (K1+K2 extend)", ext_rays, st.ms_extend, int(st.launches_extend),
+                         int(cs.node_visits), int(cs.prim_tests), list(cs.diag)[0:4])
+    k4 = kernel_roofline("shadow", "k_trace_persistent<any-hit> (K4 occlusion)", int(st.rays_shadow), st.ms_shadow, int(st.launches_shadow),
+                         int(cs.node_visits_shadow), int(cs.prim_tests_shadow), list(cs.diag)[4:8])
     dom, other = (k4, k2) if st.ms_shadow >= st.ms_extend else (k2, k4)      # the dominant kernel = the traversal kernel with the larger stage time
-    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": dom["traffic"],
-                "peak_source": peak_src, "algorithmic_bytes_per_ray": b_ray, "rays_per_launch": dom["rays_per_launch"], "avg_launch_ms": dom["avg_launch_ms"],
-                "stage_ms": stage, "other_traversal_kernel": other,
-                "note": "scene (tris+BVH) fits the 126 MB L2, so the HBM roofline is a reference line, not the binding limit; see DESIGN.md"}
+    roofline = {"bound": "issue", "kernel": dom["kernel"], "achieved": dom["issue"]["achieved"], "peak": issue_peak, "unit": "Glaneops/s", "frac": dom["issue"]["frac"],
+                "traffic": dom["hbm"]["traffic"], "peak_source": issue_src, "algorithmic_laneops_per_ray": ops_ray,
+                "measured_work_frac": dom["issue"]["measured_work_frac"], "node_visits_per_ray": dom["issue"]["node_visits_per_ray"],
+                "prim_tests_per_ray": dom["issue"]["prim_tests_per_ray"], "ncu": dom["issue"]["ncu"],
+                "rays_per_launch": dom["rays_per_launch"], "avg_launch_ms": dom["avg_launch_ms"], "stage_ms": stage,
+                "secondary": {"bound": "hbm", "achieved": dom["hbm"]["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["hbm"]["frac"], "peak_source": peak_src,
+                              "algorithmic_bytes_per_ray": b_ray, "traffic": dom["hbm"]["traffic"],
+                              "note": "the scene (BVH + triangles) is L2-resident: DRAM carries the ray queues only (ncu: DRAM throughput a few % of peak), so this line does not bind"},
+                "other_traversal_kernel": other,
+                "note": "software BVH traversal = divergent FP32 SIMT: the binding roofline is the SM issue rate (lane-ops/s); achieved = rays/s x algorithmic lane-ops per ray (SURVEY 8d)"}
     sstats = sc.stats()
 
     cpu_baseline = None
@@ -420,7 +467,7 @@ def run_ours(args, rt):
                 "config": {"workload": rt.scenes.CONFIGS[args.config]["label"] + (" [--small sample]" if args.small else "") + (f" [--spp {args.spp}]" if args.spp else ""),
                            "resolution": [cam.nx, cam.ny], "spp": cam.num_samples, "rays_per_frame": {"primary": rays[0], "secondary": rays[1], "shadow": rays[2]},
                            "integrator": "path" if integrator else "reference", "parallelism": f"tiles16x16-interleaved-x{world}", "gather": {"mode": gather.mode, "fallback_reason": gather.why_not_p2p, "ms_render_max": ms_render_max, "ms_gather_max": ms_gather_max, "check": gather_check}, "l2": "flushed between steps (256 MB write)",
-                           "scene_bytes": {"bvh": int(sstats.bvh_bytes), "triangles": int(sstats.tri_bytes)}, "bvh_build_ms": sstats.ms_bvh_build,
+                           "scene_bytes": {"bvh": int(sstats.bvh_bytes), "triangles": int(sstats.tri_bytes)}, "bvh_build_ms": {"first_in_process": build_ms[0], "min": min(build_ms), "median": float(np.median(build_ms)), "all": build_ms},
                            "bvh_builder": args.bvh, "bvh_device_meshes": int(sstats.bvh_device_meshes)},
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(cam_host.numel()), "d2h_bytes_per_step": int(npix * 12),
                         "api": "rt_render (host camera/options in, host framebuffer out)" if world == 1 else ("rt_render_device (K8 stores owned tiles into rank 0's frame over NVLink peer memory) + device barrier" if gather.mode == "p2p" else "rt_render_device + NCCL reduce") + " + D2H on rank 0",

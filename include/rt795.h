@@ -224,6 +224,12 @@ typedef struct RtRenderOpts {
                                  a SUM reduce gathers exactly).  1: the resolve stores ONLY this rank's tiles and leaves every other
                                  pixel of `out` untouched - `out` may then be a peer (NVLink) mapping of the root GPU's
                                  framebuffer and the resolve kernel itself is the gather (rt_render_device only) */
+    int32_t parity_exact;     /* 1: every closest-hit query (camera, reflection, refraction AND shadow rays) follows the reference's
+                                 per-object rules the fast path drops: inside an object the nearest accepted
+                                 primitive by |t| wins, triangles are accepted from t >= -eps, the object counts only if Ray::gett
+                                 (x-quotient, src/Ray.cpp:21-36) of that point lies in (0, best) - a hit just behind the origin masks the
+                                 whole object - and shadow rays are full closest-hit queries (src/Light.cpp:188-204).  Slower (no any-hit
+                                 early out, one pipeline); a debug / parity mode.  Ties still resolve in traversal order. */
 } RtRenderOpts;
 
 /* Primary-hit record for parity/debug (rt_trace_primary); mirrors what the oracle hit harness dumps. */

@@ -89,7 +89,7 @@ class RtRenderOpts(C.Structure):
     _fields_ = [("integrator", C.c_int32), ("seed", C.c_uint64), ("tile_rank", C.c_int32), ("tile_count", C.c_int32),
                 ("tile_w", C.c_int32), ("tile_h", C.c_int32), ("pt_max_depth", C.c_int32), ("pt_nee", C.c_int32),
                 ("pt_russian_roulette", C.c_int32), ("pt_importance", C.c_int32), ("wave_rays", C.c_int32),
-                ("queue_capacity", C.c_int32), ("collect_counters", C.c_int32), ("resolve_owned_only", C.c_int32)]
+                ("queue_capacity", C.c_int32), ("collect_counters", C.c_int32), ("resolve_owned_only", C.c_int32), ("parity_exact", C.c_int32)]
 
 
 class RtTonemap(C.Structure):

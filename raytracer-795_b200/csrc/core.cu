@@ -80,6 +80,7 @@ struct Pipe {
     cudaStream_t st = nullptr;
     std::vector<QueueBufs> levels;
     DevBuf<float4> sq_o, sq_d, sq_c;
+    DevBuf<float4> sq_hit; DevBuf<int32_t> sq_hit_obj;   // RtRenderOpts.parity_exact only: closest hits of the shadow rays
     DevBuf<DCounters> counters;
     DCounters* h_counters = nullptr;   // pinned
     DevBuf<int32_t> hist;              // per wave of this pipeline: level / shadow-queue sizes (k_wave_end), read back once per frame
@@ -578,6 +579,7 @@ struct Driver {
     bool count;        // node / primitive-test counters (collect_counters & 2)
     bool stage_time;   // per-stage CUDA-event timing (collect_counters & 1)
     bool path;
+    bool exact;        // RtRenderOpts.parity_exact
     int nlev;          // ray-tree levels a wave can have (level 0 = camera rays)
     int nbuf;          // queue buffers per pipeline (2 = ping-pong)
     bool branching;
@@ -605,13 +607,25 @@ struct Driver {
         TraceIO io{};
         io.q = q; io.count_ptr = count_ptr; io.first = first; io.limit = limit; io.cursor = cursor; io.flags = sc->trav_flags;
         int grid = sc->full_grid ? Blocks(limit) : std::min(Blocks(count_ptr ? Expect(hint, limit) : limit), sc->grid_extend);
-        (count ? sc->k_closest_count : sc->k_closest)<<<std::max(1, grid), kBlock, count ? 0 : sc->trace_smem, st>>>(sc->d, io, pp->counters.p);
+        if (exact) k_trace_persistent<false, false, TF_EXACT><<<std::max(1, grid), kBlock, 0, st>>>(sc->d, io, pp->counters.p);
+        else (count ? sc->k_closest_count : sc->k_closest)<<<std::max(1, grid), kBlock, count ? 0 : sc->trace_smem, st>>>(sc->d, io, pp->counters.p);
         launches++; n_extend++;
     }
     void LaunchShadow(const int32_t* count_ptr, int limit, int32_t* cursor, int hint = -1) {
         TraceIO io{};
         io.sq = sq; io.count_ptr = count_ptr; io.first = 0; io.limit = limit; io.cursor = cursor; io.accum = accum; io.flags = sc->trav_flags_shadow;
         int grid = sc->full_grid ? Blocks(limit) : std::min(Blocks(count_ptr ? Expect(hint, limit) : limit), sc->grid_shadow);
+        if (exact) {
+            // the reference's IsShadow is a full closest-hit query (src/Light.cpp:188-204): same exact kernel over the shadow queue, then
+            // the contributions of the rays that hit nothing inside their interval are added
+            pp->sq_hit.Alloc(sc->shadow_cap); pp->sq_hit_obj.Alloc(sc->shadow_cap);
+            io.q = DRayQueue{sq.o_time, sq.d_tmax, nullptr, nullptr, pp->sq_hit.p, pp->sq_hit_obj.p};
+            io.flags = sc->trav_flags;
+            k_trace_persistent<false, false, TF_EXACT><<<std::max(1, grid), kBlock, 0, st>>>(sc->d, io, pp->counters.p);
+            k_shadow_resolve<<<std::max(1, Blocks(limit)), kBlock, 0, st>>>(sq, pp->sq_hit.p, count_ptr, limit, accum);
+            launches += 2; n_shadow++;
+            return;
+        }
         (count ? sc->k_any_count : sc->k_any)<<<std::max(1, grid), kBlock, (count || sc->quantised_occlusion) ? 0 : sc->trace_smem, st>>>(sc->d, io, pp->counters.p);
         launches++; n_shadow++;
     }
@@ -666,7 +680,7 @@ struct Driver {
     // the device (level_count[L]); grids are sized by what the level can hold at most.
     void EnqueueWave(unsigned long long base, int n, const int* hint /* 2 * (nlev + 1) ints or NULL */, int32_t* hist) {
         DCounters* c = pp->counters.p;
-        const bool fused = sc->fused_raygen;
+        const bool fused = sc->fused_raygen && !exact;
         LaunchPrimary(base, n, fused);
         long long upper = n;
         const int nl = std::max(1, sc->d.num_lights);
@@ -815,6 +829,7 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
     proto.stage_time = (opts.collect_counters & 1) != 0;
     bool path = opts.integrator == RT_INTEGRATOR_PATH;
     proto.path = path;
+    proto.exact = opts.parity_exact != 0;
     int max_depth = path ? (opts.pt_max_depth > 0 ? opts.pt_max_depth : sc->d.max_depth) : sc->d.max_depth;
     if (max_depth < 0) max_depth = 0;
     if (max_depth > 250) throw Invalid{"recursion depth above 250 is not supported"};
@@ -841,7 +856,7 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
         unsigned long long wave_hint = opts.wave_rays > 0 ? (unsigned long long)opts.wave_rays : (unsigned long long)cap_hint;
         if (!chunked && sc->wave_limit) wave_hint = std::min<unsigned long long>(wave_hint, sc->wave_limit);
         // one pipeline when stages are timed / counted (clean per-stage numbers), in the chunked driver, or when the frame is a single wave
-        int npipe = (proto.stage_time || proto.count || chunked) ? 1 : (int)std::min<unsigned long long>((unsigned long long)sc->npipes_wanted, (total + wave_hint - 1) / std::max<unsigned long long>(1, wave_hint));
+        int npipe = (proto.stage_time || proto.count || chunked || proto.exact) ? 1 : (int)std::min<unsigned long long>((unsigned long long)sc->npipes_wanted, (total + wave_hint - 1) / std::max<unsigned long long>(1, wave_hint));
         npipe = std::max(1, npipe);
         const int nbuf = chunked ? ((proto.branching || sc->d.num_lights > 8) ? proto.nlev + 1 : 2) : 2;
         EnsureRenderBuffers(sc, &opts, nbuf, npix3, npipe);
@@ -959,7 +974,7 @@ void RenderDevice(RtScene* sc, const RtCameraDesc* cam, const RtRenderOpts* opts
     float ms = 0; CK(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1));
     RtStats& s = sc->stats;
     s.rays_primary = owned; s.rays_secondary = fr.secondary; s.rays_shadow = fr.shadow; s.launches = fr.launches + 1 /* k_resolve */; s.waves = fr.waves;
-    const bool fused_used = sc->fused_raygen && !chunked;         // K1 ran inside the first closest-hit launch of each wave
+    const bool fused_used = sc->fused_raygen && !chunked && !proto.exact;         // K1 ran inside the first closest-hit launch of each wave
     s.ms_raygen = fused_used ? 0.0 : fr.ms[0]; s.ms_extend = fr.ms[1] + (fused_used ? fr.ms[0] : 0.0); s.ms_shade = fr.ms[2]; s.ms_shadow = fr.ms[3];
     s.launches_extend = fr.n_extend; s.launches_shade = fr.n_shade; s.launches_shadow = fr.n_shadow;
     s.node_visits = s.prim_tests = s.node_visits_shadow = s.prim_tests_shadow = 0;

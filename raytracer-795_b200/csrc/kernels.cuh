@@ -392,6 +392,18 @@ __global__ void k_make_affine_tris(const float4* __restrict__ tris, int n, float
     o[2] = make_float4((float)rw[0], (float)rw[1], (float)rw[2], (float)-(rw[0] * A[0] + rw[1] * A[1] + rw[2] * A[2]));
 }
 
+// ---- RtRenderOpts.parity_exact: shadow rays were traced as full closest-hit queries (hits in `hit`); a light's contribution reaches
+// the pixel iff nothing was hit inside the ray's interval (src/Light.cpp:188-204: occluded iff |p - L| > |p - hit|)
+__global__ void __launch_bounds__(kBlock) k_shadow_resolve(DShadowQueue sq, const float4* __restrict__ hit, const int32_t* count_ptr, int limit, float* accum) {
+    int count = limit;
+    if (count_ptr) count = max(0, min(limit, *count_ptr));
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool add = i < count && __float_as_int(hit[i].w) < 0;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (add) c = sq.c_pixel[i];
+    warp_accum(accum, add, (uint32_t)__float_as_int(c.w), v3(c));
+}
+
 // ---- K8
 __global__ void k_resolve(const float* __restrict__ accum, float* __restrict__ out, int n3, float inv_spp) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

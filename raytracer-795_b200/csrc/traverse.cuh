@@ -60,6 +60,17 @@ RT_D bool tri_test_affine(const float4* __restrict__ rows, float3 o, float3 d, f
     return (t > 0.f) && (t < tmax) && (u >= -eps) && (v >= -eps) && (u + v <= 1.0f);   // NaN (degenerate triangle or parallel ray) fails every test
 }
 
+// TF_EXACT (traverse_pt.cuh): the reference's acceptance from t >= -eps, candidates ordered by |t| (`best` = the object's current |t|).
+RT_D bool tri_test_affine_exact(const float4* __restrict__ rows, float3 o, float3 d, float eps, float best, float& t, float& u, float& v) {
+    float4 rw = ldg4(rows + 2), ru = ldg4(rows), rv = ldg4(rows + 1);
+    float ow = rw.x * o.x + rw.y * o.y + rw.z * o.z + rw.w, dw = rw.x * d.x + rw.y * d.y + rw.z * d.z;
+    t = -ow / dw;
+    float ou = ru.x * o.x + ru.y * o.y + ru.z * o.z + ru.w, du = ru.x * d.x + ru.y * d.y + ru.z * d.z;
+    float ov = rv.x * o.x + rv.y * o.y + rv.z * o.z + rv.w, dv = rv.x * d.x + rv.y * d.y + rv.z * d.z;
+    u = ou + t * du; v = ov + t * dv;
+    return (t >= -eps) && (fabsf(t) < best) && (u >= -eps) && (v >= -eps) && (u + v <= 1.0f);
+}
+
 // Sphere::bvhIntersect, src/Shape.cpp:347-398, in object space with the un-normalised direction.
 RT_D bool sphere_test(float4 cr, float3 o, float3 d, float eps, float& t) {
     float3 oc = o - v3(cr);

@@ -40,7 +40,18 @@ constexpr int kFetchThreshold = 20;   // default; TraceIO.flags bits 8..15 overr
 enum : int {
     TF_QNODES = 1,      // occlusion only: walk the 8-bit quantised copy of the nodes (DScene.nodes4q)
     TF_SMEM_TLAS = 2,   // stage the TLAS nodes and the top-level transform records in shared memory (broadcast LDS instead of LDG)
+    TF_EXACT = 4,       // closest hit only, RtRenderOpts.parity_exact: the reference's per-object rules, see below
 };
+
+// TF_EXACT - the reference's closest-hit rules the fast path deliberately drops (deviations 1 and 2):
+//  * inside one object the winner is the accepted primitive nearest by |t|, and a triangle is accepted from t >= -eps
+//    (src/Shape.cpp:330-331, src/BVH.cpp:165-171, 193-203): a hit just BEHIND the origin wins and then
+//  * the object counts only if Ray::gett of the winner's point (the x-quotient (p.x - o.x) / d.x, y then z on NaN,
+//    src/Ray.cpp:21-36) lies in (0, best) (src/Helper.cpp:41-43) - so that winner masks the whole object;
+//  * the hit's t IS that quotient (the world point is o + t' d, src/Helper.cpp:47), rounding noise of the x-quotient included.
+// While a lane is inside an object, (tmax, hprim, ...) hold the OBJECT's running winner (tmax = |t|, tsig = t) and the best hit
+// over the earlier objects is parked in (g_t, g_prim, ...); leaving the object merges the two by the reference's rule.
+// Ties (equal |t| inside an object, equal t' between objects) still resolve in traversal order, not the reference's BVH order.
 
 struct TraceIO {
     DRayQueue q;               // closest hit: o_time / d_tmax read, hit / hit_obj written (fused raygen: the whole record is written)
@@ -66,6 +77,8 @@ template <bool ANY_HIT, bool COUNT, int FLAGS, bool RAYGEN>
 RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const RaygenArgs* rg) {
     constexpr bool QNODES = (FLAGS & TF_QNODES) != 0;
     constexpr bool SMEM = (FLAGS & TF_SMEM_TLAS) != 0;
+    constexpr bool EXACT = (FLAGS & TF_EXACT) != 0 && !ANY_HIT;
+    const float tnear_min = EXACT ? -sc.int_eps : 0.f;      // EXACT: primitives up to eps behind the origin are candidates
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
@@ -110,6 +123,8 @@ RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const 
     float time = 0.f, tmax = 0.f;
     float hb = 0.f, hg = 0.f;
     int hprim = -1, hobj = -1;
+    float g_t = 0.f, g_b = 0.f, g_g = 0.f, tsig = 0.f;      // EXACT: parked best over earlier objects; signed t of the object's winner
+    int g_prim = -1, g_obj = -1;
     bool exhausted = false;
     const int fetch_threshold = (io.flags >> 8) & 0xff ? (io.flags >> 8) & 0xff : kFetchThreshold;
     unsigned cnt_nodes = 0, cnt_prims = 0;
@@ -148,6 +163,23 @@ RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const 
         top_n = (int)(unsigned)e_; top_t = __uint_as_float((unsigned)(e_ >> 32));                      \
         more_ = !(node == kBlasExit || tt_ < tmax);                                                    \
       } } } while (0)
+
+    // EXACT: Ray::gett on the object-space ray (src/Ray.cpp:21-36); products and sums rounded separately like the reference's build
+    auto gett = [&](float3 oo_, float3 dd_, float t_) {
+        float px = __fadd_rn(oo_.x, __fmul_rn(dd_.x, t_)), py = __fadd_rn(oo_.y, __fmul_rn(dd_.y, t_)), pz = __fadd_rn(oo_.z, __fmul_rn(dd_.z, t_));
+        float q = __fdiv_rn(__fsub_rn(px, oo_.x), dd_.x);
+        if (q != q) q = __fdiv_rn(__fsub_rn(py, oo_.y), dd_.y);
+        if (q != q) q = __fdiv_rn(__fsub_rn(pz, oo_.z), dd_.z);
+        return q;
+    };
+    // EXACT: leaving an object - its winner (if any) against the parked best, src/Helper.cpp:41-49
+#define RT_MERGE_OBJECT()                                                                              \
+    do {                                                                                               \
+        bool take_ = false; float tq_ = 0.f;                                                           \
+        if (hprim >= 0) { tq_ = gett(o, d, tsig); take_ = tq_ < g_t && tq_ > 0.f; }                    \
+        if (take_) { tmax = tq_; }                                                                     \
+        else { tmax = g_t; hprim = g_prim; hobj = g_obj; hb = g_b; hg = g_g; }                         \
+    } while (0)
 
     while (true) {
         // ---------------- retire finished rays, fetch new ones
@@ -216,6 +248,7 @@ RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const 
                 if (node == kSentinel) break;
                 if (node == kBlasExit) {
                     if (leaf < 0) break;   // the pending leaf lives in this instance's object space: test it before leaving
+                    if (EXACT) RT_MERGE_OBJECT();
                     RT_SET_RAY(wo, wd);
                     cur_obj = -1;
                     RT_POP();
@@ -262,7 +295,7 @@ RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const 
                         }
 #define RT_SLAB(K, C)                                                                                                                   \
                         {                                                                                                                   \
-                            float n_ = fmaxf(fmaxf(nx4.C * id.x - ood.x, ny4.C * id.y - ood.y), fmaxf(nz4.C * id.z - ood.z, 0.f));             \
+                            float n_ = fmaxf(fmaxf(nx4.C * id.x - ood.x, ny4.C * id.y - ood.y), fmaxf(nz4.C * id.z - ood.z, tnear_min));       \
                             float f_ = fminf(fminf(fx4.C * id.x - ood.x, fy4.C * id.y - ood.y), fminf(fz4.C * id.z - ood.z, tmax));            \
                             rf[K] = __float_as_int(cr.C);                                                                                   \
                             tn[K] = (n_ <= f_ && rf[K] != kNoChildDev) ? n_ : 3.0e38f;                                                      \
@@ -304,7 +337,13 @@ RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const 
                     if (root < 0) {
                         if (COUNT) ++cnt_prims;
                         float t;
-                        if (sphere_test(ldg4(sc.spheres + (~root)), oo, od, eps, t) && t > 0.f && t < tmax) {
+                        if (EXACT) {
+                            // Sphere::bvhIntersect returns its non-negative root; the object then counts iff gett of that point is in (0, best)
+                            if (sphere_test(ldg4(sc.spheres + (~root)), oo, od, eps, t)) {
+                                float tq = gett(oo, od, t);
+                                if (tq < tmax && tq > 0.f) { tmax = tq; hprim = 0; hobj = obj; hb = hg = 0.f; }
+                            }
+                        } else if (sphere_test(ldg4(sc.spheres + (~root)), oo, od, eps, t) && t > 0.f && t < tmax) {
                             tmax = t; hprim = 0; hobj = obj; hb = hg = 0.f;
                             if (ANY_HIT) { node = kSentinel; leaf = 0; break; }
                         }
@@ -312,6 +351,7 @@ RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const 
                     } else {
                         RT_SET_RAY(oo, od);
                         cur_obj = obj;
+                        if (EXACT) { g_t = tmax; g_prim = hprim; g_obj = hobj; g_b = hb; g_g = hg; hprim = -1; }   // park the best so far; tmax keeps bounding the search
                         RT_PUSH(kBlasExit, -1.f);
                         node = root;                       // the entry's BLAS root in nodes4 (DObjectXf.blur_root.w)
                     }
@@ -334,7 +374,9 @@ RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const 
                 for (int i = 0; i < count; i++, tp += 3) {
                     if (COUNT) ++cnt_prims;
                     float t, u, v;
-                    if (tri_test_affine(tp, o, d, eps, tmax, t, u, v)) {
+                    if (EXACT) {
+                        if (tri_test_affine_exact(tp, o, d, eps, tmax, t, u, v)) { tmax = fabsf(t); tsig = t; hb = u; hg = v; hprim = first + i; hobj = cur_obj; }
+                    } else if (tri_test_affine(tp, o, d, eps, tmax, t, u, v)) {
                         tmax = t; hb = u; hg = v; hprim = first + i; hobj = cur_obj;
                         if (ANY_HIT) { done = true; break; }
                     }
@@ -346,6 +388,7 @@ RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const 
             if ((io.flags & 1) && !exhausted && __popc(__activemask()) < fetch_threshold) break;
         }
     }
+#undef RT_MERGE_OBJECT
 #undef RT_POP
 #undef RT_POP1
 #undef RT_PUSH
