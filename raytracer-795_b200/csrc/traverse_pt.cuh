@@ -49,9 +49,11 @@ enum : int {
 //  * the object counts only if Ray::gett of the winner's point (the x-quotient (p.x - o.x) / d.x, y then z on NaN,
 //    src/Ray.cpp:21-36) lies in (0, best) (src/Helper.cpp:41-43) - so that winner masks the whole object;
 //  * the hit's t IS that quotient (the world point is o + t' d, src/Helper.cpp:47), rounding noise of the x-quotient included.
-// While a lane is inside an object, (tmax, hprim, ...) hold the OBJECT's running winner (tmax = |t|, tsig = t) and the best hit
-// over the earlier objects is parked in (g_t, g_prim, ...); leaving the object merges the two by the reference's rule.
-// Ties (equal |t| inside an object, equal t' between objects) still resolve in traversal order, not the reference's BVH order.
+// The best hit over the objects visited so far lives in (g_t, g_prim, g_obj, ...); (tmax, hprim, ...) hold the running winner of the
+// object the lane is inside (tmax = |t|, tsig = t) and are +inf / none in the TLAS: like the reference, one object's search is not
+// bounded by another object's hit (its t is a different, noisier quantity).  Leaving an object merges by the reference's rule; a tie
+// between objects goes to the earlier top-level entry.  Equal |t| INSIDE an object still resolves in traversal order, not in the
+// order of the reference's own median-split BVH.
 
 struct TraceIO {
     DRayQueue q;               // closest hit: o_time / d_tmax read, hit / hit_obj written (fused raygen: the whole record is written)
@@ -175,10 +177,14 @@ RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const 
     // EXACT: leaving an object - its winner (if any) against the parked best, src/Helper.cpp:41-49
 #define RT_MERGE_OBJECT()                                                                              \
     do {                                                                                               \
-        bool take_ = false; float tq_ = 0.f;                                                           \
-        if (hprim >= 0) { tq_ = gett(o, d, tsig); take_ = tq_ < g_t && tq_ > 0.f; }                    \
-        if (take_) { tmax = tq_; }                                                                     \
-        else { tmax = g_t; hprim = g_prim; hobj = g_obj; hb = g_b; hg = g_g; }                         \
+        if (hprim >= 0) {                                                                              \
+            float tq_ = gett(o, d, tsig);                                                              \
+            /* strict <: the EARLIER top-level entry keeps a tie (the reference loops over entries in order) */ \
+            if (tq_ > 0.f && (tq_ < g_t || (tq_ == g_t && g_prim >= 0 && cur_obj < g_obj))) {          \
+                g_t = tq_; g_prim = hprim; g_obj = cur_obj; g_b = hb; g_g = hg;                        \
+            }                                                                                          \
+        }                                                                                              \
+        tmax = 3.0e38f; hprim = -1;                                                                    \
     } while (0)
 
     while (true) {
@@ -192,7 +198,8 @@ RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const 
             warp_accum(io.accum, add, (uint32_t)__float_as_int(c.w), v3(c));
             if (idle) rayidx = -1;
         } else if (idle && rayidx >= 0) {
-            io.q.hit[rayidx] = make_float4(tmax, hb, hg, __int_as_float(hprim)); io.q.hit_obj[rayidx] = hobj;
+            if (EXACT) { io.q.hit[rayidx] = make_float4(g_t, g_b, g_g, __int_as_float(g_prim)); io.q.hit_obj[rayidx] = g_obj; }
+            else { io.q.hit[rayidx] = make_float4(tmax, hb, hg, __int_as_float(hprim)); io.q.hit_obj[rayidx] = hobj; }
             rayidx = -1;
         }
         unsigned m = __ballot_sync(full, idle);
@@ -230,7 +237,8 @@ RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const 
                     wo = v3(ot); wd = v3(dt); time = ot.w; tmax = dt.w;
                 }
                 hprim = -1; hobj = -1; hb = hg = 0.f;
-                if (!live || any_nan(wo) || any_nan(wd)) { node = kSentinel; if (!ANY_HIT) tmax = 0.f; }   // src/Helper.cpp:28-30: NaN ray = no hit
+                if (EXACT) { g_t = tmax; g_prim = -1; g_obj = -1; g_b = g_g = 0.f; tmax = 3.0e38f; }   // the ray's own bound applies at the merges only
+                if (!live || any_nan(wo) || any_nan(wd)) { node = kSentinel; if (!ANY_HIT) { tmax = 0.f; g_t = 0.f; } }   // src/Helper.cpp:28-30: NaN ray = no hit
                 else {
                     RT_SET_RAY(wo, wd);
                     if (COUNT) atomicOr(&s_alive[threadIdx.x >> 5], 1u << lane);
@@ -341,7 +349,7 @@ RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const 
                             // Sphere::bvhIntersect returns its non-negative root; the object then counts iff gett of that point is in (0, best)
                             if (sphere_test(ldg4(sc.spheres + (~root)), oo, od, eps, t)) {
                                 float tq = gett(oo, od, t);
-                                if (tq < tmax && tq > 0.f) { tmax = tq; hprim = 0; hobj = obj; hb = hg = 0.f; }
+                                if (tq > 0.f && (tq < g_t || (tq == g_t && g_prim >= 0 && obj < g_obj))) { g_t = tq; g_prim = 0; g_obj = obj; g_b = g_g = 0.f; }
                             }
                         } else if (sphere_test(ldg4(sc.spheres + (~root)), oo, od, eps, t) && t > 0.f && t < tmax) {
                             tmax = t; hprim = 0; hobj = obj; hb = hg = 0.f;
@@ -351,7 +359,7 @@ RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const 
                     } else {
                         RT_SET_RAY(oo, od);
                         cur_obj = obj;
-                        if (EXACT) { g_t = tmax; g_prim = hprim; g_obj = hobj; g_b = hb; g_g = hg; hprim = -1; }   // park the best so far; tmax keeps bounding the search
+                        if (EXACT) { tmax = 3.0e38f; hprim = -1; }     // this object's own search, unbounded by the others' hits
                         RT_PUSH(kBlasExit, -1.f);
                         node = root;                       // the entry's BLAS root in nodes4 (DObjectXf.blur_root.w)
                     }
