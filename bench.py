@@ -296,11 +296,13 @@ def run_ours(args, rt):
 
     mid_events = []
 
-    def render_step(o, mid=None):
+    def render_step(o, mid=None, release=True):
         sc.render_device(cam, o, gather.out_ptr, stream.cuda_stream)
         if mid is not None:
             mid.record(stream)
         gather.finish()                                       # p2p: device barrier after the peer stores; nccl: SUM reduce to rank 0
+        if release:
+            gather.release()                                  # p2p: nobody starts the next frame's stores before rank 0 is done with this one
 
     host_np = host_frame.numpy().reshape(cam.ny, cam.nx, 3)
     pageable_np = np.empty((cam.ny, cam.nx, 3), dtype=np.float32)   # what the reference hands over: new float[] (src/Image.cpp:8)
@@ -316,9 +318,10 @@ def run_ours(args, rt):
             sc.render(cam, o, out=host_np)
             return
         cam_dev.copy_(cam_host, non_blocking=True)            # this step's inputs (camera + options) from pinned host memory
-        render_step(o)
+        render_step(o, release=False)
         if rank == 0:
             host_frame.copy_(frame, non_blocking=True)        # the step's result: the gathered framebuffer
+        gather.release()                                      # after rank 0's read of the frame is on the stream
         torch.cuda.synchronize()
 
     launches = 0

@@ -699,6 +699,9 @@ V3 BasicShading(const Ctx& cx, const Ray& ray, const Hit& ret, const RtMaterial&
     return raw;
 }
 
+// Ray-tree node ids of the RNG counter (root 1, reflected 2n, refracted 2n + 1; hashed on beyond 30 bounces) - twin of csrc/kernels.cuh child_node
+inline uint32_t ChildNode(uint32_t node, uint32_t branch) { return node < 0x40000000u ? node * 2u + branch : node * 2654435761u + 0x9E3779B9u + branch; }
+
 V3 NanCheck(V3 v) { return isnan3(v) ? V3(0, 0, 0) : v; }                                       // src/Scene.cpp:221-228
 
 struct Spawn { Ray ray; Hit ret; };
@@ -747,7 +750,7 @@ V3 RecursiveShadingCore(const Ctx& cx, const Ray& ray, const Hit& ret, int depth
     if (mat.type == RT_MAT_NORMAL || depth <= 0) return BasicShading(cx, ray, ret, mat, pixel, sample, node);
     if (mat.type == RT_MAT_MIRROR) {
         Spawn sc = MirrorReflectance(cx, ray, ret, mat, pixel, sample, node);
-        V3 refl = Recurse(cx, sc, depth - 1, pixel, sample, node * 2);
+        V3 refl = Recurse(cx, sc, depth - 1, pixel, sample, ChildNode(node, 0));
         refl = cmul(ld3(mat.mirror), refl);
         return BasicShading(cx, ray, ret, mat, pixel, sample, node) + refl;
     }
@@ -776,25 +779,25 @@ V3 RecursiveShadingCore(const Ctx& cx, const Ray& ray, const Hit& ret, int depth
         float beerDistance = tr.ret.full ? norm(tr.ret.point - ret.point) : 0.0f;
         V3 beer(exp(-mat.absorption_coeff[0] * beerDistance), exp(-mat.absorption_coeff[1] * beerDistance), exp(-mat.absorption_coeff[2] * beerDistance));
         if (entering) {
-            V3 inside = Recurse(cx, tr, depth - 1, pixel, sample, node * 2 + 1);
+            V3 inside = Recurse(cx, tr, depth - 1, pixel, sample, ChildNode(node, 1));
             inside = (1 - fresnel) * inside;
             inside = cmul(beer, inside);
             Spawn sc = MirrorReflectance(cx, ray, ret, mat, pixel, sample, node);
-            V3 refl = Recurse(cx, sc, depth - 1, pixel, sample, node * 2);
+            V3 refl = Recurse(cx, sc, depth - 1, pixel, sample, ChildNode(node, 0));
             refl = fresnel * refl;
             inside = NanCheck(inside); refl = NanCheck(refl);
             return BasicShading(cx, ray, ret, mat, pixel, sample, node) + inside + refl;
         }
         if (tir) {
             Spawn sc = MirrorReflectance(cx, ray, ret, mat, pixel, sample, node);
-            V3 ir = Recurse(cx, sc, depth - 1, pixel, sample, node * 2);
+            V3 ir = Recurse(cx, sc, depth - 1, pixel, sample, ChildNode(node, 0));
             ir = cmul(beer, ir);
             return NanCheck(ir);
         }
-        V3 outside = Recurse(cx, tr, depth - 1, pixel, sample, node * 2 + 1);
+        V3 outside = Recurse(cx, tr, depth - 1, pixel, sample, ChildNode(node, 1));
         outside = (1 - fresnel) * outside;
         Spawn sc = MirrorReflectance(cx, ray, ret, mat, pixel, sample, node);
-        V3 refl = Recurse(cx, sc, depth - 1, pixel, sample, node * 2);
+        V3 refl = Recurse(cx, sc, depth - 1, pixel, sample, ChildNode(node, 0));
         refl = fresnel * refl;
         refl = cmul(beer, refl);
         outside = NanCheck(outside); refl = NanCheck(refl);
@@ -803,7 +806,7 @@ V3 RecursiveShadingCore(const Ctx& cx, const Ray& ray, const Hit& ret, int depth
     // conductor
     float fresnel = ConductorFresnel(mat.refraction_index, mat.absorption_index, ray.d, ret.normal);
     Spawn sc = MirrorReflectance(cx, ray, ret, mat, pixel, sample, node);
-    V3 refl = Recurse(cx, sc, depth - 1, pixel, sample, node * 2);
+    V3 refl = Recurse(cx, sc, depth - 1, pixel, sample, ChildNode(node, 0));
     refl = fresnel * refl;
     refl = cmul(ld3(mat.mirror), refl);
     return BasicShading(cx, ray, ret, mat, pixel, sample, node) + refl;

@@ -83,6 +83,13 @@ __global__ void __launch_bounds__(256) k_wave_end(DCounters* c, int nlevels, int
     }
 }
 
+// Ray-tree node ids for the RNG counter: root 1, reflected child 2n, refracted child 2n + 1 - unique while they fit 32 bits (30
+// bounces); deeper nodes continue with a multiplicative hash instead of shifting the id out (which would hand every node below
+// depth 32 the same stream).  oracle/restate.cpp ChildNode is the twin.
+RT_D uint32_t child_node(uint32_t node, uint32_t branch) {
+    return node < 0x40000000u ? node * 2u + branch : node * 2654435761u + 0x9E3779B9u + branch;
+}
+
 // ---- K3 / K6
 struct RayOut { float3 o, d, w; float time; int sample, meta, node; float beer_s; };
 
@@ -191,7 +198,7 @@ __global__ void __launch_bounds__(kBlock, LOOP ? 4 : RT795_SHADE_MIN_BLOCKS) k_s
                         }
                         RayOut r;
                         r.o = s.P + s.N * eps; r.d = wr; r.w = weight; r.time = rtime; r.sample = (int)sample;
-                        r.meta = meta_pack(depth - 1, fl, bmat); r.node = (int)(node * 2u); r.beer_s = bs;
+                        r.meta = meta_pack(depth - 1, fl, bmat); r.node = (int)child_node(node, 0u); r.beer_s = bs;
                         return r;
                     };
                     if (mat.type == RT_MAT_NORMAL || depth <= 0) lit = true;
@@ -221,7 +228,7 @@ __global__ void __launch_bounds__(kBlock, LOOP ? 4 : RT795_SHADE_MIN_BLOCKS) k_s
                         float rper = (n_i * cos_i - n_t * cos_t) / (n_i * cos_i + n_t * cos_t);
                         float F = 0.5f * (rpar * rpar + rper * rper);
                         RayOut tr;
-                        tr.o = s.P - eps * nn; tr.d = tdir; tr.time = rtime; tr.sample = (int)sample; tr.node = (int)(node * 2u + 1u);
+                        tr.o = s.P - eps * nn; tr.d = tdir; tr.time = rtime; tr.sample = (int)sample; tr.node = (int)child_node(node, 1u);
                         // offset.dir for the Beer distance: origin - p = -eps*nn
                         tr.beer_s = -dot(nn, tdir);
                         if (entering) {

@@ -818,8 +818,10 @@ int rt_host_load_scene(const char* xml_path, RtHostScene** out) {
 void rt_host_free_scene(RtHostScene* hs) { delete hs; }
 int rt_host_save_scene_blob(const RtHostScene* hs, const char* blob_path) {
     if (!hs || !blob_path) { SetLastError("rt_host_save_scene_blob: null argument"); return RT_ERR_INVALID; }
+    FILE* f = nullptr;
+    try {
     std::string tmp = std::string(blob_path) + ".tmp";
-    FILE* f = fopen(tmp.c_str(), "wb");
+    f = fopen(tmp.c_str(), "wb");
     if (!f) { SetLastError(std::string("rt_host_save_scene_blob: cannot write ") + tmp); return RT_ERR_IO; }
     BlobWriter w{f};
     w.Raw(kBlobMagic, 8); w.U64(LayoutStamp());
@@ -829,7 +831,12 @@ int rt_host_save_scene_blob(const RtHostScene* hs, const char* blob_path) {
         StatFile(d, &size, &mt);
         w.Str(d); w.U64(size); w.U64((uint64_t)mt);
     }
-    w.Raw(&hs->desc, sizeof(RtSceneDesc));                               // scalars; the pointer fields are rebound on load
+    {   // scalars only: the pointer fields are rebound on load, so they are written as NULL (blobs are byte-reproducible and carry no addresses)
+        RtSceneDesc d = hs->desc;
+        d.vertices = nullptr; d.vertex_normals = nullptr; d.texcoords = nullptr; d.tri_indices = nullptr; d.meshes = nullptr; d.spheres = nullptr;
+        d.objects = nullptr; d.materials = nullptr; d.textures = nullptr; d.images = nullptr; d.lights = nullptr;
+        w.Raw(&d, sizeof(RtSceneDesc));
+    }
     w.Vec(hs->vertices); w.Vec(hs->normals); w.Vec(hs->texcoords); w.Vec(hs->tris);
     w.Vec(hs->meshes); w.Vec(hs->spheres); w.Vec(hs->objects); w.Vec(hs->materials); w.Vec(hs->textures); w.Vec(hs->lights); w.Vec(hs->cameras); w.Vec(hs->cam_opts); w.Vec(hs->cam_tonemap);
     w.U64(hs->image_names.size());
@@ -839,8 +846,14 @@ int rt_host_save_scene_blob(const RtHostScene* hs, const char* blob_path) {
     w.Raw(kBlobMagic, 8);                                                // trailer: a truncated file is rejected
     bool ok = w.ok;
     if (fclose(f) != 0) ok = false;
+    f = nullptr;
     if (!ok || rename(tmp.c_str(), blob_path) != 0) { remove(tmp.c_str()); SetLastError(std::string("rt_host_save_scene_blob: write failed for ") + blob_path); return RT_ERR_IO; }
     return RT_OK;
+    } catch (const std::exception& e) {                                    // e.g. bad_alloc building a path string: never across the C boundary
+        if (f) fclose(f);
+        SetLastError(std::string("rt_host_save_scene_blob: ") + e.what());
+        return RT_ERR_OOM;
+    }
 }
 
 int rt_host_load_scene_blob(const char* blob_path, int check_sources, RtHostScene** out) {
@@ -851,9 +864,11 @@ int rt_host_load_scene_blob(const char* blob_path, int check_sources, RtHostScen
     uint64_t fsize = 0; int64_t fmt = 0;
     StatFile(blob_path, &fsize, &fmt);
     BlobReader r{f, true, fsize};
-    RtHostScene* hs = new RtHostScene();
+    RtHostScene* hs = nullptr;
+    bool f_open = true;
     try {
-    auto fail = [&](const std::string& why) { fclose(f); delete hs; SetLastError(std::string("rt_host_load_scene_blob: ") + blob_path + ": " + why); return RT_ERR_PARSE; };
+    hs = new RtHostScene();
+    auto fail = [&](const std::string& why) { fclose(f); f_open = false; delete hs; hs = nullptr; SetLastError(std::string("rt_host_load_scene_blob: ") + blob_path + ": " + why); return RT_ERR_PARSE; };
     char magic[8];
     r.Raw(magic, 8);
     if (!r.ok || memcmp(magic, kBlobMagic, 8) != 0) return fail("not a scene blob");
@@ -888,12 +903,13 @@ int rt_host_load_scene_blob(const char* blob_path, int check_sources, RtHostScen
     }
     r.Raw(magic, 8);
     if (!r.ok || memcmp(magic, kBlobMagic, 8) != 0) return fail("truncated");
-    fclose(f);
+    fclose(f); f_open = false;
     if (hs->cameras.size() != hs->image_names.size() || hs->cam_opts.size() != hs->cameras.size() || hs->cam_tonemap.size() != hs->cameras.size() || hs->vertices.size() % 3 || hs->tris.size() % 3 || hs->texcoords.size() % 2 ||
         (!hs->normals.empty() && hs->normals.size() != hs->vertices.size())) { delete hs; SetLastError(std::string("rt_host_load_scene_blob: ") + blob_path + ": inconsistent arrays"); return RT_ERR_PARSE; }
     hs->desc.abi_version = RT795_ABI_VERSION;
     BindDesc(hs);                                                         // rt_scene_create validates every index range again
     } catch (const std::exception& e) {
+        if (f_open) fclose(f);
         delete hs;
         SetLastError(std::string("rt_host_load_scene_blob: ") + blob_path + ": " + e.what());
         return RT_ERR_PARSE;

@@ -73,8 +73,19 @@ class FrameGather:
         return 1 if self.mode == "p2p" else 0
 
     def finish(self):
-        """Enqueue, on the current stream, whatever completes the gather after this rank's rt_render_device returned."""
+        """Enqueue, on the current stream, whatever completes the gather after this rank's rt_render_device returned.
+        Contract (p2p): after finish() rank 0 may READ the frame on this stream; before ANY rank renders the next frame into it, every
+        rank must call release() after rank 0 has enqueued its reads (copy to the host, tone map ...) on the stream - otherwise a fast
+        peer's stores of frame n+1 land in a frame rank 0 is still reading (write after read; invisible only while consecutive frames
+        are identical)."""
         if self.mode == "p2p":
             self.hdl.barrier()                        # device-side signal-pad barrier: all ranks' peer stores have landed
         elif self.mode == "nccl":
             self.dist.reduce(self.local, dst=0, op=self.dist.ReduceOp.SUM)
+
+    def release(self):
+        """Second half of the frame hand-over: enqueued by every rank after rank 0's reads of the gathered frame were enqueued on
+        its stream.  p2p: a second device barrier, so no rank's next resolve starts storing into the root's frame before rank 0's reads
+        are done.  nccl / local: nothing to do (every rank writes only its own buffer, stream order covers it)."""
+        if self.mode == "p2p":
+            self.hdl.barrier()

@@ -47,6 +47,32 @@ def _worker(rank, world, port, xml, out_dir):
         torch.cuda.synchronize(); dist.barrier()
         if rank == 0:
             np.save(os.path.join(out_dir, f"{mode}_{g.mode}.npy"), g.frame.cpu().numpy().reshape(cam.ny, cam.nx, 3))
+    # two DIFFERENT frames back to back, rank 0 reading each with a non-blocking copy: FrameGather.release() must keep frame n+1's peer
+    # stores out of the buffer until frame n has been read (write-after-read across ranks)
+    import copy
+    cams = [cam, copy.copy(cam)]
+    cams[1] = rt.RtCameraDesc.from_buffer_copy(cam)
+    cams[1].position[0] += 1.5; cams[1].position[1] += 0.7
+    g = rt.multigpu.FrameGather(cam.nx * cam.ny * 3, dev, mode="p2p")
+    host = [torch.empty(cam.nx * cam.ny * 3, dtype=torch.float32).pin_memory() for _ in cams]
+    o = rt.default_opts(tile_rank=rank, tile_count=world, resolve_owned_only=g.resolve_owned_only)
+    for rep in range(3):
+        for k, c in enumerate(cams):
+            if g.mode == "nccl":
+                g.frame.zero_()
+            sc.render_device(c, o, g.out_ptr, stream.cuda_stream)
+            g.finish()
+            if rank == 0:
+                host[k].copy_(g.frame, non_blocking=True)
+            g.release()
+    torch.cuda.synchronize(); dist.barrier()
+    if rank == 0:
+        for k, c in enumerate(cams):
+            np.save(os.path.join(out_dir, f"seq{k}.npy"), host[k].numpy().reshape(cam.ny, cam.nx, 3))
+            alone_k = torch.empty(cam.nx * cam.ny * 3, dtype=torch.float32, device=dev)
+            sc.render_device(c, rt.default_opts(), alone_k.data_ptr(), stream.cuda_stream)
+            torch.cuda.synchronize()
+            np.save(os.path.join(out_dir, f"seq{k}_alone.npy"), alone_k.cpu().numpy().reshape(cam.ny, cam.nx, 3))
     if rank == 0:
         alone = torch.empty(cam.nx * cam.ny * 3, dtype=torch.float32, device=dev)
         sc.render_device(cam, rt.default_opts(), alone.data_ptr(), stream.cuda_stream)
@@ -65,7 +91,10 @@ def test_two_gpu_p2p_gather_matches_single_gpu(rt, scene_dir, tmp_path):
     xml = rt.scenes.scene_c3(os.path.join(scene_dir, "c3p2p"), res=(203, 117), spp=4, n=48)
     mp.start_processes(_worker, args=(2, _free_port(), xml, str(tmp_path)), nprocs=2, join=True, start_method="spawn")
     alone = np.load(tmp_path / "alone.npy")
-    files = sorted(f for f in os.listdir(tmp_path) if f.endswith(".npy") and f != "alone.npy")
+    for k in range(2):
+        assert np.allclose(np.load(tmp_path / f"seq{k}.npy"), np.load(tmp_path / f"seq{k}_alone.npy"), rtol=1e-5, atol=1e-5), k
+    assert not np.allclose(np.load(tmp_path / "seq0.npy"), np.load(tmp_path / "seq1.npy"), rtol=1e-2, atol=1e-2)
+    files = sorted(f for f in os.listdir(tmp_path) if f.endswith(".npy") and f != "alone.npy" and not f.startswith("seq"))
     assert any(f.startswith("p2p_") for f in files) and "nccl_nccl.npy" in files
     for f in files:
         got = np.load(tmp_path / f)

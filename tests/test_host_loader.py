@@ -270,6 +270,8 @@ def test_scene_blob_round_trip_staleness_and_corruption(rt, tmp_path):
     a = rt.HostScene(xml)
     blob = os.path.join(d, "scene.blob")
     a.save_blob(blob)
+    a.save_blob(blob + ".again")                                             # byte-reproducible: no host addresses inside
+    assert open(blob, "rb").read() == open(blob + ".again", "rb").read()
     b = rt.HostScene(blob=blob)
     assert _desc_bytes(rt, a) == _desc_bytes(rt, b)                                   # bit-identical prepared scene
     b.close()
