@@ -275,9 +275,10 @@ void rt_scene_destroy(RtScene* scene);
  * Replaces the thread spawn/join block src/Scene.cpp:336-356 (ThreadedRendering :269-292). */
 int rt_render(RtScene* scene, const RtCameraDesc* cam, const RtRenderOpts* opts, float* out_rgb);
 
-/* Same, but the destination is DEVICE memory on the scene's device (nx*ny*3 floats) and the work is enqueued
- * on `cuda_stream` (a cudaStream_t passed as void*, NULL = the library's own stream); returns after enqueue
- * + internal queue-size readbacks complete (the frame is complete on that stream when the call returns). */
+/* Same, but the destination is DEVICE memory on the scene's device (nx*ny*3 floats) and the frame is ordered on
+ * `cuda_stream` (a cudaStream_t passed as void*): it starts after the work already enqueued there and its last kernel
+ * (the resolve) runs on it.  NULL = the library's own stream; to name the legacy default stream pass cudaStreamLegacy.
+ * The call returns when the frame is complete. */
 int rt_render_device(RtScene* scene, const RtCameraDesc* cam, const RtRenderOpts* opts, float* d_out_rgb, void* cuda_stream);
 
 /* Primary visibility only (ray generation at pixel centres + closest hit), for parity tests:

@@ -276,8 +276,14 @@ class Scene:
         _check(self.lib.rt_render(self.h, C.byref(cam), C.byref(opts), out.ctypes.data))
         return out
 
-    def render_device(self, cam: RtCameraDesc, opts: RtRenderOpts, d_ptr: int, stream: int = 0) -> None:
-        _check(self.lib.rt_render_device(self.h, C.byref(cam), C.byref(opts), C.c_void_p(d_ptr), C.c_void_p(stream)))
+    def render_device(self, cam: RtCameraDesc, opts: RtRenderOpts, d_ptr: int, stream: Optional[int] = None) -> None:
+        """stream: a cudaStream_t handle; None = the library's own stream.  0 is the CUDA legacy default stream (what
+        torch.cuda.current_stream().cuda_stream is unless a side stream is current): it is passed as cudaStreamLegacy so that the
+        frame really is ordered with the caller's work on that stream (barriers, copies) - a NULL handle means "library stream"
+        to rt_render_device."""
+        CUDA_STREAM_LEGACY = 1
+        h = 0 if stream is None else (stream if stream else CUDA_STREAM_LEGACY)
+        _check(self.lib.rt_render_device(self.h, C.byref(cam), C.byref(opts), C.c_void_p(d_ptr), C.c_void_p(h)))
 
     def trace_primary(self, cam: RtCameraDesc) -> np.ndarray:
         out = np.zeros((cam.ny, cam.nx), dtype=HIT_DTYPE)
