@@ -292,6 +292,13 @@ int rt_tonemap(RtScene* scene, const float* in_rgb, int nx, int ny, float key, f
 
 int rt_get_stats(RtScene* scene, RtStats* out);
 
+/* Page-locked host memory for frames (cudaMallocHost / cudaFreeHost) for callers that do not link the CUDA runtime themselves:
+ * rt_render / rt_group_render copy a finished frame straight into such a buffer by DMA; an ordinary malloc'ed frame (what the
+ * reference's Image::_data is, src/Image.cpp:8) is staged through the library's own pinned buffer + a host memcpy (~2.5 ms for a
+ * 1920x1080 frame).  NULL on failure. */
+void* rt_host_alloc_pinned(uint64_t bytes);
+void rt_host_free_pinned(void* p);
+
 /* ---- multi-GPU inside ONE process: the counterpart of the reference's fan-out inside renderScene (8 std::threads over one
  * frame, src/Scene.cpp:340-356).  The scene is replicated on `num_devices` CUDA devices (devices[i], NULL = 0..n-1; devices[0]
  * is the root), one context + one host thread per device.  rt_group_render cuts the frame into interleaved tiles

@@ -119,7 +119,7 @@ HIT_DTYPE = np.dtype([("full", "<i4"), ("object", "<i4"), ("primitive", "<i4"), 
 # every symbol include/rt795.h declares (tests/test_abi.py asserts the library exports all of them)
 CORE_SYMBOLS = ["rt_scene_create", "rt_scene_destroy", "rt_render", "rt_render_device", "rt_trace_primary", "rt_tonemap",
                 "rt_get_stats", "rt_group_create", "rt_group_destroy", "rt_group_render", "rt_group_num_devices", "rt_group_scene",
-                "rt_group_uses_peer_memory", "rt_debug_read_bvh", "rt_last_error", "rt_abi_version", "rt_device_count", "rt_host_load_scene",
+                "rt_group_uses_peer_memory", "rt_host_alloc_pinned", "rt_host_free_pinned", "rt_debug_read_bvh", "rt_last_error", "rt_abi_version", "rt_device_count", "rt_host_load_scene",
                 "rt_host_save_scene_blob", "rt_host_load_scene_blob", "rt_host_load_scene_cached",
                 "rt_host_camera_render_opts", "rt_host_camera_tonemap",
                 "rt_host_free_scene", "rt_host_scene_desc", "rt_host_num_cameras", "rt_host_camera",

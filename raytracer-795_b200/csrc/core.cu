@@ -1302,7 +1302,8 @@ int rt_group_render(RtSceneGroup* g, const RtCameraDesc* cam, const RtRenderOpts
         for (int i = 0; i < n; i++) {
             if (g->peer[i]) continue;
             g->stage.Alloc(npix3);
-            CK(cudaMemcpyPeer(g->stage.p, root->device, g->local[i], g->devices[i], npix3 * sizeof(float)));
+            // stream-ordered on the root's stream: the merge kernel below must not start before the copy has landed
+            CK(cudaMemcpyPeerAsync(g->stage.p, root->device, g->local[i], g->devices[i], npix3 * sizeof(float), root->stream));
             RtRenderOpts o; memset(&o, 0, sizeof o);
             if (opts) o = *opts;
             o.tile_rank = i; o.tile_count = n;
@@ -1390,6 +1391,13 @@ int rt_tonemap(RtScene* sc, const float* in_rgb, int nx, int ny, float key, floa
         CK(cudaGetLastError());
     });
 }
+
+void* rt_host_alloc_pinned(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); SetLastError("rt_host_alloc_pinned: cudaMallocHost failed"); return nullptr; }
+    return p;
+}
+void rt_host_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 
 int rt_get_stats(RtScene* sc, RtStats* out) {
     if (!sc || !out) { SetLastError("rt_get_stats: null argument"); return RT_ERR_INVALID; }

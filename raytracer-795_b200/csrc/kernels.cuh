@@ -100,8 +100,10 @@ RT_D void write_ray(const DRayQueue& q, int slot, uint32_t pixel, const RayOut& 
     q.meta[slot] = make_int4(r.sample, r.meta, r.node, __float_as_int(r.beer_s));
 }
 
+// 6 resident CTAs (80 registers, 68 bytes spilled): C4 shade stage 10.99 -> 10.34 ms; 5 CTAs (96 registers, no spills) 10.99; 4 CTAs 12.70
+// (profiles/bench/r02_ab_occupancy_c4.txt)
 #ifndef RT795_SHADE_MIN_BLOCKS
-#define RT795_SHADE_MIN_BLOCKS 5
+#define RT795_SHADE_MIN_BLOCKS 6
 #endif
 // Shade pass over rays [first, first + min(limit, *in_count - first)) of queue level `in`; continuation rays go to `out`
 // (count in *out_count), shadow rays to `sq` (count in *shadow_count).  The ray count is device-resident; the grid covers `limit`.

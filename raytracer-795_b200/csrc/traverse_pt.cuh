@@ -65,11 +65,11 @@ struct TraceIO {
     int flags;                 // bit 0: dynamic ray fetch, bit 1: postpone leaves (tuning knobs; results do not depend on them)
 };
 
-// Resident CTAs per SM the compiler must leave room for (A/B knobs).  7 x 128 threads = 72 registers per thread: what the
-// occlusion kernel uses anyway, and 80 -> 72 for closest hit, whose stage drops 17.2 -> 16.65 ms on C4; 8 CTAs (64 registers)
-// gives the gain back.
+// Resident CTAs per SM the compiler must leave room for (A/B knobs, profiles/bench/r02_ab_occupancy_c4.txt).  Closest hit: 7 x 128
+// threads = 72 registers (80 -> 72: stage 17.2 -> 16.65 ms on C4 in round 1; 8 CTAs / 64 registers no better).  Occlusion: 8 CTAs
+// (64 registers, 16 bytes spilled) 28.68 -> 28.25 ms; 6 CTAs 28.83.
 #ifndef RT795_MINB_ANY
-#define RT795_MINB_ANY 7
+#define RT795_MINB_ANY 8
 #endif
 #ifndef RT795_MINB_CLOSEST
 #define RT795_MINB_CLOSEST 7
