@@ -129,7 +129,11 @@ struct RtScene {
     TraceKernel k_closest = nullptr, k_closest_count = nullptr, k_any = nullptr, k_any_count = nullptr;
     RaygenTraceKernel k_rg_closest = nullptr, k_rg_closest_count = nullptr;
     int grid_extend = 0, grid_shadow = 0;   // resident CTAs: SM count x occupancy
-    int trav_flags = 2, trav_flags_shadow = 3;   // TraceIO.flags for closest-hit / occlusion launches (measured best on C4; RT795_TRAVERSAL_FLAGS overrides both)
+    // TraceIO.flags for closest-hit / occlusion launches (RT795_FLAGS_CLOSEST / RT795_FLAGS_OCCLUSION / RT795_TRAVERSAL_FLAGS override):
+    // postponed leaves (2) for both, dynamic fetch (1) for occlusion, CTA chunks of 256 / 512 queue entries (bits 16..23).  Chunks, C4 frame
+    // (profiles/bench/r02_ab_chunks_c4.txt): none 52.77 ms, 256/512 51.26, 512/1024 50.92 - but from 1024 up the single-kernel stage times
+    // grow (tail: occlusion 28.8 -> 29.3 ms at 1024, 36.6 at 4096), so the sizes that help the frame without lengthening a stage are used.
+    int trav_flags = (1 << 16) | 2, trav_flags_shadow = (2 << 16) | 3;
     bool full_grid = false;                 // RT795_FULL_GRID=1: one thread per ray instead of resident warps
     // render state
     Pipe pipes[kPipes];

@@ -62,7 +62,9 @@ struct TraceIO {
     int first, limit;          // rays [first, first + min(limit, *count_ptr - first))
     int32_t* cursor;           // global next-ray cursor (zero before the launch)
     float* accum;              // occlusion: pixel accumulator
-    int flags;                 // bit 0: dynamic ray fetch, bit 1: postpone leaves (tuning knobs; results do not depend on them)
+    int flags;                 // bit 0: dynamic ray fetch, bit 1: postpone leaves, bit 2: L2 prefetch of upcoming records, bits 8..15: fetch
+                               // threshold, bits 16..23: CTA chunk size / 256 (0: every warp pulls from the global cursor); tuning knobs -
+                               // results do not depend on them
 };
 
 // Resident CTAs per SM the compiler must leave room for (A/B knobs, profiles/bench/r02_ab_occupancy_c4.txt).  Closest hit: 7 x 128
@@ -129,6 +131,13 @@ RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const 
     int g_prim = -1, g_obj = -1;
     bool exhausted = false;
     const int fetch_threshold = (io.flags >> 8) & 0xff ? (io.flags >> 8) & 0xff : kFetchThreshold;
+    // CTA chunks: the CTA takes `chunk` consecutive queue entries from the global cursor at a time and its warps pull from that chunk
+    // through a shared-memory cursor (one 64-bit word: end << 32 | next), so the four warps of a CTA work on neighbouring rays - rays
+    // of neighbouring pixels walk the same subtrees (L1) - and the global cursor sees one atomic per chunk instead of one per refill.
+    const int chunk = ((io.flags >> 16) & 0xff) * 256;
+    __shared__ unsigned long long s_chunk;
+    __shared__ int s_lock, s_done;
+    if (chunk) { if (threadIdx.x == 0) { s_chunk = 0ull; s_lock = 0; s_done = 0; } __syncthreads(); }
     unsigned cnt_nodes = 0, cnt_prims = 0;
     // COUNT builds only: which lanes of each warp currently hold an unfinished ray (shared bitmask per warp), to split the
     // inactive lanes at a node step into "busy elsewhere" and "ray finished, waiting for a refill"
@@ -204,11 +213,38 @@ RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const 
         }
         unsigned m = __ballot_sync(full, idle);
         if (m && !exhausted) {
-            int nreq = __popc(m), mine = __popc(m & lt), leader = __ffs(m) - 1, base = 0;
-            if ((int)lane == leader) base = atomicAdd(io.cursor, nreq);
-            base = __shfl_sync(full, base, leader);
-            if (base + nreq >= total) exhausted = true;
-            if (idle && base + mine < total) {
+            int nreq = __popc(m), mine = __popc(m & lt), leader = __ffs(m) - 1, base = 0, got = 0;
+            if (chunk == 0) {
+                if ((int)lane == leader) base = atomicAdd(io.cursor, nreq);
+                base = __shfl_sync(full, base, leader);
+                if (base + nreq >= total) exhausted = true;
+                got = max(0, min(nreq, total - base));
+            } else {
+                if ((int)lane == leader) {
+                    unsigned long long w = atomicAdd(&s_chunk, (unsigned long long)nreq);
+                    int nx = (int)(unsigned)w, en = (int)(unsigned)(w >> 32);
+                    if (nx < en) { base = nx; got = min(nreq, en - nx); }
+                    else if (*(volatile int*)&s_done) got = -1;                       // the queue has been handed out completely
+                    else if (atomicCAS(&s_lock, 0, 1) == 0) {
+                        unsigned long long w2 = *(volatile unsigned long long*)&s_chunk;   // under the lock: somebody may have refilled since
+                        if ((int)(unsigned)w2 >= (int)(unsigned)(w2 >> 32)) {
+                            int g = atomicAdd(io.cursor, chunk);
+                            if (g >= total) { *(volatile int*)&s_done = 1; got = -1; }
+                            else {
+                                int e = min(g + chunk, total);
+                                base = g; got = min(nreq, e - g);
+                                atomicExch(&s_chunk, ((unsigned long long)(unsigned)e << 32) | (unsigned)(g + got));
+                            }
+                        }
+                        __threadfence_block();
+                        atomicExch(&s_lock, 0);
+                    }
+                }
+                base = __shfl_sync(full, base, leader);
+                got = __shfl_sync(full, got, leader);
+                if (got < 0) { exhausted = true; got = 0; }
+            }
+            if (idle && mine < got) {
                 rayidx = io.first + base + mine;
                 bool live = true;
                 if (RAYGEN) {
@@ -247,7 +283,7 @@ RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const 
                 }
             }
         }
-        if (__all_sync(full, node == kSentinel && rayidx < 0)) break;
+        if (exhausted && __all_sync(full, node == kSentinel && rayidx < 0)) break;   // (a fetch can come back empty while another warp refills the CTA's chunk)
         // ---------------- traverse
         while (node != kSentinel) {
             bool searching = true;
