@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Step 2 of the full-size parity check (runs where /root/reference was compiled into oracle/_ref): renders the SAME
 full-size scene XMLs with the UNMODIFIED reference (8 threads, its own mt19937 streams) and compares the GPU
-framebuffers brought back in gpurun_out/full_<cfg>.f32.  Writes profiles/r01_fullsize_parity.json.
+framebuffers brought back in gpurun_out/full_<cfg>.f32.  Writes profiles/r02_fullsize_parity.json (RT795_PARITY_OUT overrides the name).
 usage: python profiles/fullsize_parity.py c3 c2 c4"""
 import json
 import os
@@ -18,7 +18,7 @@ import __graft_entry__ as ge  # noqa: E402
 import bench  # noqa: E402
 
 rt = ge.load_package()
-out_path = os.path.join(ROOT, "profiles", "r01_fullsize_parity.json")
+out_path = os.path.join(ROOT, "profiles", os.environ.get("RT795_PARITY_OUT", "r02_fullsize_parity.json"))
 res = json.load(open(out_path)) if os.path.exists(out_path) else {}
 
 

@@ -43,7 +43,7 @@ struct DScene {
     // geometry for traversal
     const uint4* nodes4q;               // BvhNode64Q as 4 x uint4: the same 4-wide tree (same node indices) with 8-bit quantised boxes; NULL unless RT795_QNODES=1
     const float4* nodes4;               // BvhNode128 as 8 x float4 (4-wide collapse of the SAH BVH2); every BLAS first, the TLAS nodes last
-    const int32_t* obj_root4;           // per top-level entry: BLAS root in nodes4 (spheres: unused)
+    const int32_t* obj_root4;           // per top-level entry: BLAS root in nodes4 (spheres: unused); the kernels read it from obj_xf, this copy serves rt_debug_read_bvh
     int32_t tlas_root4;                 // first TLAS node = its root; nodes [tlas_root4, tlas_root4 + tlas_nodes) are the TLAS
     int32_t tlas_nodes;
     const float4* tris_w;               // triangles in leaf order as ray -> (u, v, w) affine maps, 3 rows x float4 (traverse.cuh tri_test_affine)

@@ -22,32 +22,14 @@ struct HitRec {
     int obj;        // top-level entry
 };
 
-#define RT_COUNT_NODE() do { if (COUNT) ++cnt_nodes; } while (0)
-#define RT_COUNT_PRIM() do { if (COUNT) ++cnt_prims; } while (0)
-
 constexpr int kBlasExit = 0x7ffffffe;   // stack marker: leaving an instance, restore the world-space ray
 constexpr int kSentinel = 0x7fffffff;
 constexpr int kNoChildDev = 0x7ffffffd; // == rt795::kNoChild (bvh_build.h)
 
 RT_D float4 ldg4(const float4* p) { return __ldg(p); }
 
-// Möller–Trumbore on the {v0, e1, e2} record; algebraically the reference's Cramer solve (beta = weight of b, gamma of c).
-RT_D bool tri_test(const float4* __restrict__ tri, float3 o, float3 d, float eps, float tmax, float& t, float& u, float& v, int& prim) {
-    float4 a = ldg4(tri), b = ldg4(tri + 1), c = ldg4(tri + 2);
-    float3 v0 = v3(a), e1 = v3(b), e2 = v3(c);
-    float3 p = cross(d, e2);
-    float det = dot(e1, p);
-    float inv = 1.0f / det;
-    float3 tv = o - v0;
-    u = dot(tv, p) * inv;
-    float3 q = cross(tv, e1);
-    v = dot(d, q) * inv;
-    t = dot(e2, q) * inv;
-    prim = __float_as_int(a.w);
-    return (t > 0.f) && (t < tmax) && (u >= -eps) && (v >= -eps) && (u + v <= 1.0f);   // NaN (det == 0) fails every test
-}
-
-// The same test on a precomputed affine map (Woop et al. 2005): rows (r_u, r_v, r_w) take a world point p to the triangle's own
+// Triangle test on a precomputed affine map (Woop et al. 2005) - algebraically the reference's Cramer solve (src/Shape.cpp:297-345: beta = weight of
+// b, gamma of c): rows (r_u, r_v, r_w) take a world point p to the triangle's own
 // coordinates, p = A + u e1 + v e2 + w n.  The hit is where the ray crosses w = 0; (u, v) there are the reference's (beta, gamma).
 // 22 FMA-class operations instead of ~40 (two cross products, four dot products), same predicate.
 RT_D bool tri_test_affine(const float4* __restrict__ rows, float3 o, float3 d, float eps, float tmax, float& t, float& u, float& v) {

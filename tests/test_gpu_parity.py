@@ -616,3 +616,38 @@ def test_route_a_bridge_reference_parser_plus_librt795(rt, scene_dir, tmp_path, 
     img, ref = outs
     assert img.shape == ref.shape and np.isfinite(img).all()
     assert_pointwise(img, ref, np.ones(img.shape[:2], dtype=bool), f"route A {scene}: reference parser + librt795 vs unmodified reference", outlier_budget=1e-3)
+
+
+def test_deep_recursion_two_buffers_and_hashed_rng_nodes(rt, scene_dir):
+    """MaxRecursionDepth 60 between two facing rough (glossy) mirrors: 61 ray-tree levels run through the two ping-pong queue buffers of
+    the sync-free driver (round 1 allocated one buffer per depth: 37 GB at depth 50), and the RNG node ids pass 2^30 after 30 bounces,
+    where kernel and oracle switch to the hashed continuation (csrc/kernels.cuh child_node / oracle ChildNode) - the glossy perturbation
+    draws from those streams, so any disagreement shows up in the image."""
+    d = os.path.join(scene_dir, "deep")
+    os.makedirs(d, exist_ok=True)
+    xml = """<Scene><MaxRecursionDepth>60</MaxRecursionDepth><BackgroundColor>0 0 0</BackgroundColor><ShadowRayEpsilon>1e-3</ShadowRayEpsilon><IntersectionTestEpsilon>1e-6</IntersectionTestEpsilon>
+<Cameras><Camera id="1"><Position>0 0.3 3.9</Position><GazePoint>0.4 0 -4</GazePoint><Up>0 1 0</Up><FovY>50</FovY><NearDistance>1</NearDistance>
+<ImageResolution>48 40</ImageResolution><NumSamples>4</NumSamples><ImageName>deep.ppm</ImageName></Camera></Cameras>
+<Lights><AmbientLight>8 8 8</AmbientLight><PointLight id="1"><Position>0 3.5 0</Position><Intensity>900 900 900</Intensity></PointLight></Lights>
+<Materials>
+<Material id="1" type="mirror"><AmbientReflectance>0.1 0.1 0.1</AmbientReflectance><DiffuseReflectance>0.05 0.05 0.05</DiffuseReflectance><SpecularReflectance>0 0 0</SpecularReflectance><MirrorReflectance>0.97 0.97 0.97</MirrorReflectance><Roughness>0.02</Roughness></Material>
+<Material id="2"><AmbientReflectance>1 1 1</AmbientReflectance><DiffuseReflectance>0.7 0.3 0.2</DiffuseReflectance><SpecularReflectance>0.2 0.2 0.2</SpecularReflectance><PhongExponent>10</PhongExponent></Material>
+</Materials>
+<VertexData>-400 -400 -4  400 -400 -4  400 400 -4  -400 400 -4   -400 -400 4  400 -400 4  400 400 4  -400 400 4   0.8 -0.5 0</VertexData>
+<Objects>
+<Mesh id="1"><Material>1</Material><Faces>1 2 3  1 3 4</Faces></Mesh>
+<Mesh id="2"><Material>1</Material><Faces>6 5 8  6 8 7</Faces></Mesh>
+<Sphere id="3"><Material>2</Material><Center>9</Center><Radius>0.9</Radius></Sphere>
+</Objects></Scene>"""
+    p = os.path.join(d, "deep.xml")
+    with open(p, "w") as f:
+        f.write(xml)
+    hs, sc = _load(rt, p)
+    cam = hs.camera(0)
+    img = sc.render(cam)
+    st = sc.stats()
+    ref = orc.oracle_render(hs.desc, cam)
+    r = rel_err(img, ref).max(axis=-1)
+    assert st.rays_secondary > 20 * cam.nx * cam.ny * cam.num_samples          # the mirrors really bounce dozens of times
+    assert np.quantile(r, 0.97) <= 1e-2 and abs(img.mean() - ref.mean()) <= 2e-3 * ref.mean(), (np.quantile(r, 0.97), img.mean(), ref.mean())
+    sc.close(); hs.close()
