@@ -213,7 +213,8 @@ typedef struct RtRenderOpts {
     /* path tracer only */
     int32_t pt_max_depth;     /* 0 -> scene max_recursion_depth                     */
     int32_t pt_nee;           /* next-event estimation on/off                       */
-    int32_t pt_russian_roulette; /* 0 off, 1 throughput-based                       */
+    int32_t pt_russian_roulette; /* 0 off; survival probability keyed on 1 the path throughput, 2 the cosine between the sampled
+                                    direction and the normal (the reference author's choice, pages/Page7.md:31); both unbiased */
     int32_t pt_importance;    /* 0 uniform hemisphere, 1 cosine-weighted            */
     /* engine knobs (0 -> defaults) */
     int32_t wave_rays;        /* primary rays generated per wave                    */

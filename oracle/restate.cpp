@@ -1000,7 +1000,7 @@ V3 PathTrace(const Ctx& cx, Ray ray, uint32_t pixel, uint32_t sample, int row, i
         if (isnan3(beta)) break;
         count_emission = false;
         if (cx.opts.pt_russian_roulette && node >= 2) {
-            float q = std::max(beta.x, std::max(beta.y, beta.z));
+            float q = cx.opts.pt_russian_roulette == 2 ? cosi : std::max(beta.x, std::max(beta.y, beta.z));   // mode 2: keyed on the cosine (pages/Page7.md:31)
             q = std::min(0.95f, std::max(0.05f, q));
             Rng4 rr = philox(cx.seed, pixel, sample, node, DIM_PT_RR);
             if (rr.u[0] >= q) break;

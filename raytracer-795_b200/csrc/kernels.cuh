@@ -327,7 +327,9 @@ __global__ void __launch_bounds__(kBlock, LOOP ? 4 : RT795_SHADE_MIN_BLOCKS) k_s
                         float3 beta = (W * f) * (cosi / pdf);
                         bool alive = !any_nan(beta);
                         if (alive && rc.pt_rr && node >= 2u) {
-                            float q = fminf(0.95f, fmaxf(0.05f, fmaxf(beta.x, fmaxf(beta.y, beta.z))));
+                            // survival probability: the path throughput (mode 1) or, as the reference's author chose (pages/Page7.md:31), the
+                            // cosine between the sampled direction and the normal (mode 2); survivors are divided by it either way (unbiased)
+                            float q = rc.pt_rr == 2 ? fminf(0.95f, fmaxf(0.05f, cosi)) : fminf(0.95f, fmaxf(0.05f, fmaxf(beta.x, fmaxf(beta.y, beta.z))));
                             float4 rr4 = philox_uniform4(rc.seed, pixel, sample, node, DIM_PT_RR);
                             if (rr4.x >= q) alive = false; else beta = beta / q;
                         }

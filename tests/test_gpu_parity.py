@@ -189,6 +189,11 @@ def test_c5_path_tracer_vs_oracle(rt, scene_dir):
     hs, sc = _load(rt, xml)
     opts = rt.default_opts(integrator=rt.RT_INTEGRATOR_PATH)
     _check_vs_oracle(rt, hs, sc, opts, mean_tol=5e-3, q=0.95, q_tol=2e-2)
+    # Russian roulette keyed on the cosine (pages/Page7.md:31) instead of the throughput: same twin, and the same image in the mean
+    rr2 = rt.default_opts(integrator=rt.RT_INTEGRATOR_PATH, pt_russian_roulette=2)
+    img2, _ = _check_vs_oracle(rt, hs, sc, rr2, mean_tol=5e-3, q=0.95, q_tol=2e-2)
+    img1 = sc.render(hs.camera(0), opts)
+    assert abs(img2.mean() - img1.mean()) <= 0.05 * img1.mean(), (img1.mean(), img2.mean())
     # NEE on vs off converge to the same image (internal consistency; NEE-off has far more variance)
     cam = hs.camera(0)
     a = sc.render(cam, rt.default_opts(integrator=rt.RT_INTEGRATOR_PATH, pt_nee=1, seed=1))
