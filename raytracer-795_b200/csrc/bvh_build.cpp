@@ -12,7 +12,10 @@ namespace rt795 {
 namespace {
 
 constexpr int kBins = 16;
-constexpr float kTraversalCost = 1.0f, kIntersectCost = 1.0f;
+constexpr float kIntersectCost = 1.0f;
+// cost of one inner-node visit relative to one triangle test in the SAH leaf decision.  RT795_SAH_TRAVERSAL_COST / RT795_SAH_MAX_LEAF:
+// tuning overrides for the HOST builder only (A/B of the leaf size; the device builder mirrors the defaults)
+static float TraversalCost() { static float v = [] { const char* e = getenv("RT795_SAH_TRAVERSAL_COST"); float x = e ? (float)atof(e) : kSahTraversalCost; return x > 0.f ? x : kSahTraversalCost; }(); return v; }
 constexpr int kMaxDepth = 36;   // deeper subtrees fall back to median splits (depth <= 36 + log2 n); core.cu checks TLAS+BLAS depth against the traversal stack
 
 struct Tmp {
@@ -77,7 +80,7 @@ struct Builder {
             }
             float area = box.HalfArea();
             float leaf_cost = kIntersectCost * count;
-            float split_cost = best_axis >= 0 && area > 0 ? kTraversalCost + kIntersectCost * best_cost / area : std::numeric_limits<float>::max();
+            float split_cost = best_axis >= 0 && area > 0 ? TraversalCost() + kIntersectCost * best_cost / area : std::numeric_limits<float>::max();
             if (count <= max_leaf && leaf_cost <= split_cost) return -1;
             if (best_axis >= 0) {
                 float lo = cbox.lo[best_axis], scale = kBins / (cbox.hi[best_axis] - lo);
@@ -159,6 +162,7 @@ void BuildSahBvh(const Aabb* prim_bounds, int n, int max_leaf, BuiltBvh* out) {
         out->nodes.push_back(root);
         return;
     }
+    if (const char* e = getenv("RT795_SAH_MAX_LEAF")) { int v = atoi(e); if (v >= 1 && max_leaf > 1) max_leaf = v; }   // TLAS leaves (max_leaf 1) hold exactly one entry
     Builder b(prim_bounds, n, std::min(8, std::max(1, max_leaf)), out->order);
     b.tmp.reserve((size_t)n);
     unsigned hw = std::thread::hardware_concurrency();

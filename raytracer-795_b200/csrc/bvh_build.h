@@ -46,6 +46,10 @@ struct BuiltBvh {
 void BuildSahBvh(const Aabb* prim_bounds, int n, int max_leaf, BuiltBvh* out);
 
 constexpr int32_t kNoChild = 0x7ffffffd;
+// SAH leaf decision: cost of one inner-node visit in units of one triangle test (leaf cost = #triangles).  Measured on C4 with the
+// traversal kernels of round 2 (profiles/bench/r02_ab_sah_c4.txt): 1.0 -> 51.3 ms / 29.4 MB of nodes, 2.0 -> 50.7 ms / 19.0 MB (a node
+// visit costs ~100 issued instructions against ~35 for a triangle test), 4.0 -> 51.2 ms / 9.9 MB.  The device builders use the same value.
+constexpr float kSahTraversalCost = 2.0f;
 inline int32_t EncodeLeaf(int32_t first, int32_t count) { return ~((first << 3) | (count - 1)); }
 
 // 4-wide node (128 bytes = one cache line, 8 x float4): SoA boxes of up to four children

@@ -208,9 +208,9 @@ __global__ void __launch_bounds__(kTB) k_merge_emit(const float4* __restrict__ c
         float3 ulo = min3(f3(lo), f3(lo2)), uhi = max3(f3(hi), f3(hi2));
         float area = half_area(ulo, uhi), al = half_area(f3(lo), f3(hi)), ar = half_area(f3(lo2), f3(hi2));
         int c = (meta[l] & kCntMask) + (meta[r] & kCntMask);
-        // SAH, bottom-up: cost(node) = min(#triangles if <= 4, 1 + sum_child area_child / area * cost(child)) - the host builder's
-        // constants (traversal 1, intersection 1, bvh_build.cpp) and leaf rule
-        float split = area > 0.f ? 1.0f + (al * cst[l] + ar * cst[r]) / area : 3.0e38f;
+        // SAH, bottom-up: cost(node) = min(#triangles if <= 4, C_t + sum_child area_child / area * cost(child)) - the host builder's
+        // constants (traversal kSahTraversalCost, intersection 1, bvh_build.h) and leaf rule
+        float split = area > 0.f ? kSahTraversalCost + (al * cst[l] + ar * cst[r]) / area : 3.0e38f;
         split = fminf(split, 3.0e38f);
         bool leaf = c <= 4 && (float)c <= split;
         cst[id] = leaf ? (float)c : split;
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(128) k_sah_split(SahNodes nd, int lvl_begin, i
         Box3 nb; nb.lo[0] = l.x; nb.lo[1] = l.y; nb.lo[2] = l.z; nb.hi[0] = h.x; nb.hi[1] = h.y; nb.hi[2] = h.z;
         float area = box_half_area(nb);
         float leaf_cost = (float)count;                                  // kIntersectCost * count
-        float split_cost = best_axis >= 0 && area > 0 ? __fadd_rn(1.0f, __fdiv_rn(best_cost, area)) : 3.402823466e38f;
+        float split_cost = best_axis >= 0 && area > 0 ? __fadd_rn(kSahTraversalCost, __fdiv_rn(best_cost, area)) : 3.402823466e38f;
         if (count <= kSahMaxLeaf && leaf_cost <= split_cost) decision = -1;
         else if (best_axis >= 0) decision = best_axis | (best_split << 2);
         else if (count <= kSahMaxLeaf) decision = -1;
@@ -832,7 +832,7 @@ bool BuildBlasOnDevice(const float* d_vertices, const int32_t* d_tri_idx, int fi
                     float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
                     float a = dx * dy + dy * dz + dz * dx;
                     int c = cnt[0] + cnt[1];
-                    float split = a > 0.f ? 1.0f + (area[0] * cs[0] + area[1] * cs[1]) / a : 3.0e38f;
+                    float split = a > 0.f ? kSahTraversalCost + (area[0] * cs[0] + area[1] * cs[1]) / a : 3.0e38f;
                     if (!(split <= 3.0e38f)) split = 3.0e38f;
                     bool leaf = c <= 4 && (float)c <= split;
                     int sl = slot_of(i);
