@@ -124,6 +124,7 @@ struct RtScene {
     int bvh_depth = 0;
     int tlas_base2 = 0;
     // kernel variants (A/B switches, all default to the measured best): RT795_SMEM_TLAS, RT795_FUSED_RAYGEN
+    bool packet_primary = false;           // RT795_PACKET=1: camera rays as warp packets (traverse_packet.cuh)
     bool smem_tlas = false, fused_raygen = true;   // measured on C4 (profiles/bench/r02_ab_driver.txt): staging 54.4 ms vs 53.7 ms without
     int trace_smem = 0;                    // dynamic shared memory of the traversal launches (staged top level), 0 = not staged
     TraceKernel k_closest = nullptr, k_closest_count = nullptr, k_any = nullptr, k_any_count = nullptr;
@@ -671,7 +672,8 @@ struct Driver {
                 TraceIO io{};
                 io.q = q0; io.count_ptr = nullptr; io.first = 0; io.limit = n; io.cursor = &c->cursor_extend[0]; io.flags = sc->trav_flags;
                 int grid = sc->full_grid ? Blocks(n) : std::min(Blocks(n), sc->grid_extend);
-                (count ? sc->k_rg_closest_count : sc->k_rg_closest)<<<std::max(1, grid), kBlock, count ? 0 : sc->trace_smem, st>>>(sc->d, io, c, a);
+                if (sc->packet_primary && !count) k_raygen_trace_packet<<<std::max(1, grid), kBlock, 0, st>>>(sc->d, io, c, a);
+                else (count ? sc->k_rg_closest_count : sc->k_rg_closest)<<<std::max(1, grid), kBlock, count ? 0 : sc->trace_smem, st>>>(sc->d, io, c, a);
                 launches++; n_extend++;
             });
         } else {
@@ -1085,6 +1087,7 @@ int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out) {
             if (const char* q = getenv("RT795_DEBUG_BVH")) sc->keep_debug_bvh = atoi(q) != 0;
             if (const char* q = getenv("RT795_SMEM_TLAS")) sc->smem_tlas = atoi(q) != 0;
             if (const char* q = getenv("RT795_FUSED_RAYGEN")) sc->fused_raygen = atoi(q) != 0;
+            if (const char* q = getenv("RT795_PACKET")) sc->packet_primary = atoi(q) != 0;
             if (const char* q = getenv("RT795_HINTS")) sc->use_hints = atoi(q) != 0;
             if (const char* q = getenv("RT795_DRIVER")) sc->env_chunked = sc->force_chunked = !strcmp(q, "chunked");
             sc->k_closest_count = k_trace_persistent<false, true, 0>; sc->k_any_count = k_trace_persistent<true, true, 0>;

@@ -12,6 +12,7 @@
 #pragma once
 #include "shade.cuh"
 #include "traverse_pt.cuh"
+#include "traverse_packet.cuh"
 
 namespace rt795 {
 

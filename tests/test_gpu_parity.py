@@ -656,3 +656,27 @@ def test_deep_recursion_two_buffers_and_hashed_rng_nodes(rt, scene_dir):
     assert st.rays_secondary > 20 * cam.nx * cam.ny * cam.num_samples          # the mirrors really bounce dozens of times
     assert np.quantile(r, 0.97) <= 1e-2 and abs(img.mean() - ref.mean()) <= 2e-3 * ref.mean(), (np.quantile(r, 0.97), img.mean(), ref.mean())
     sc.close(); hs.close()
+
+
+@pytest.mark.parametrize("config", ["c1", "c4"])
+def test_packet_camera_rays_same_frame(rt, scene_dir, config, monkeypatch):
+    """RT795_PACKET=1 (traverse_packet.cuh: the 32 camera rays of a warp on one traversal stack) is another visiting order of the same
+    tests: same closest hit per ray, hence the same frame up to ties between equal-distance hits (none in these scenes beyond a handful
+    of silhouette samples) - compared against the per-ray kernel, which the tests above pin to the oracle."""
+    if config == "c1":
+        xml = rt.scenes.scene_c1(os.path.join(scene_dir, "c1pk"), res=400)
+    else:
+        xml = rt.scenes.scene_c4(os.path.join(scene_dir, "c4pk"), res=(320, 180), spp=32, n=48)   # 32 spp: one warp = one pixel; instances + motion blur
+    hs = rt.HostScene(xml)
+    cam = hs.camera(0)
+    frames = []
+    for packet in ("0", "1"):
+        monkeypatch.setenv("RT795_PACKET", packet)                       # read when the scene is created
+        sc = rt.Scene(hs.desc, 0)
+        frames.append(sc.render(cam))
+        sc.close()
+    hs.close()
+    a, b = frames
+    r = rel_err(b, a).max(axis=-1)
+    assert (r == 0).mean() >= 0.999, (r == 0).mean()
+    assert r.max() <= 1e-2 and abs(a.mean() - b.mean()) <= 1e-5 * a.mean(), (r.max(), a.mean(), b.mean())
