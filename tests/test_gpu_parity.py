@@ -678,5 +678,8 @@ def test_packet_camera_rays_same_frame(rt, scene_dir, config, monkeypatch):
     hs.close()
     a, b = frames
     r = rel_err(b, a).max(axis=-1)
-    assert (r == 0).mean() >= 0.999, (r == 0).mean()
+    # a pixel's samples are summed with atomicAdd in arrival order, so two renders of one scene differ in the last bits of the float sum
+    same = r <= 2e-6
+    print(f"[packet {config}] pixels equal to 2e-6: {same.mean():.6f}, max rel diff {r.max():.3e}")
+    assert same.mean() >= 0.999, same.mean()
     assert r.max() <= 1e-2 and abs(a.mean() - b.mean()) <= 1e-5 * a.mean(), (r.max(), a.mean(), b.mean())
