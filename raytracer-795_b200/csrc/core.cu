@@ -99,6 +99,7 @@ struct RtScene {
     DScene d{};
     // geometry + shading buffers
     DevBuf<float4> nodes4, tris, spheres;
+    DevBuf<float4> nodes4x;            // RT795_NODES256 builds only
     DevBuf<float4> nodes2_debug;       // binary BVH the 4-wide one is collapsed from: resident only with RT795_DEBUG_BVH=1 (rt_debug_read_bvh)
     DevBuf<uint4> nodes4q;             // 8-bit quantised twin of nodes4: resident only with RT795_QNODES=1 or RT795_DEBUG_BVH=1
     DevBuf<float4> tris_w;
@@ -546,6 +547,17 @@ bool BuildAndUpload(RtScene* sc, const RtSceneDesc* s, bool allow_device) {
         CK(cudaGetLastError());
     }
     d.tris_w = sc->tris_w.p;
+    d.nodes4x = nullptr;
+#ifdef RT795_NODES256
+    {
+        int n4_all = n4_total;
+        sc->nodes4x.Alloc((size_t)n4_all * 16);
+        k_expand_nodes256<<<(n4_all + 127) / 128, 128, 0, st>>>(sc->nodes4.p, n4_all, sc->nodes4x.p);
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        d.nodes4x = sc->nodes4x.p;
+    }
+#endif
     d.nodes4 = sc->nodes4.p; d.obj_root4 = sc->obj_root4.p; d.tlas_root4 = tlas_base4; d.tlas_nodes = (int)t4.nodes.size();
     d.tris = sc->tris.p; d.obj_xf = sc->obj_xf.p; d.spheres = sc->spheres.p; sc->tlas_base2 = tlas_base;
     d.obj_sh = sc->obj_sh.p; d.tri_idx = sc->tri_idx.p; d.vertices = sc->vertices.p; d.normals = sc->normals.p; d.texcoords = sc->texcoords.p;

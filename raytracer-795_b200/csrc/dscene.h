@@ -42,6 +42,7 @@ struct DImage { const void* pixels; int32_t width, height, format, pad; };
 struct DScene {
     // geometry for traversal
     const uint4* nodes4q;               // BvhNode64Q as 4 x uint4: the same 4-wide tree (same node indices) with 8-bit quantised boxes; NULL unless RT795_QNODES=1
+    const float4* nodes4x;              // experiment RT795_NODES256: 256-byte nodes holding every axis pair in both orders (near,far picked by a 32-byte load address); else NULL
     const float4* nodes4;               // BvhNode128 as 8 x float4 (4-wide collapse of the SAH BVH2); every BLAS first, the TLAS nodes last
     const int32_t* obj_root4;           // per top-level entry: BLAS root in nodes4 (spheres: unused); the kernels read it from obj_xf, this copy serves rt_debug_read_bvh
     int32_t tlas_root4;                 // first TLAS node = its root; nodes [tlas_root4, tlas_root4 + tlas_nodes) are the TLAS

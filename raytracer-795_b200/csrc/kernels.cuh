@@ -383,6 +383,19 @@ __global__ void __launch_bounds__(kBlock, LOOP ? 4 : RT795_SHADE_MIN_BLOCKS) k_s
   }
 }
 
+// ---- experiment RT795_NODES256: 128-byte node -> 256-byte node with every axis pair in both orders (see traverse_pt.cuh)
+__global__ void k_expand_nodes256(const float4* __restrict__ in, int n, float4* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4* s = in + (size_t)i * 8;
+    float4* o = out + (size_t)i * 16;
+    for (int a = 0; a < 3; a++) {
+        float4 lo = s[2 * a], hi = s[2 * a + 1];
+        o[4 * a] = lo; o[4 * a + 1] = hi; o[4 * a + 2] = hi; o[4 * a + 3] = lo;
+    }
+    o[12] = s[6]; o[13] = s[7]; o[14] = o[15] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // ---- {v0, e1, e2} records -> affine ray-to-triangle maps (dscene.h tris_w), one thread per triangle, in double for the inverse
 __global__ void k_make_affine_tris(const float4* __restrict__ tris, int n, float4* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

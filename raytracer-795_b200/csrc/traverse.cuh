@@ -27,6 +27,11 @@ constexpr int kSentinel = 0x7fffffff;
 constexpr int kNoChildDev = 0x7ffffffd; // == rt795::kNoChild (bvh_build.h)
 
 RT_D float4 ldg4(const float4* p) { return __ldg(p); }
+// 32 bytes in one instruction (LDG.E.256, sm_100): two adjacent float4s of a 32-byte-aligned pair
+RT_D void ldg8(const float4* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
 
 // Triangle test on a precomputed affine map (Woop et al. 2005) - algebraically the reference's Cramer solve (src/Shape.cpp:297-345: beta = weight of
 // b, gamma of c): rows (r_u, r_v, r_w) take a world point p to the triangle's own
