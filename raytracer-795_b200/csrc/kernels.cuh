@@ -50,10 +50,10 @@ __global__ void __launch_bounds__(kBlock) k_raygen(RaygenArgs a, int count, DRay
     __shared__ int s_res[kBlock / 32 + 1];
     int slot = block_reserve(q_count, active ? 1 : 0, s_res);
     if (active) {
-        q.o_time[slot] = make_float4(o.x, o.y, o.z, time);
-        q.d_tmax[slot] = make_float4(d.x, d.y, d.z, 3.0e38f);
-        q.w_pixel[slot] = make_float4(1.f, 1.f, 1.f, __int_as_float((int)pixel));
-        q.meta[slot] = make_int4((int)sample, meta_pack(a.max_depth, RAY_PRIMARY | RAY_SPECULAR, 0), 1, 0);
+        RT_QST(q.o_time + slot, make_float4(o.x, o.y, o.z, time));
+        RT_QST(q.d_tmax + slot, make_float4(d.x, d.y, d.z, 3.0e38f));
+        RT_QST(q.w_pixel + slot, make_float4(1.f, 1.f, 1.f, __int_as_float((int)pixel)));
+        RT_QST(q.meta + slot, make_int4((int)sample, meta_pack(a.max_depth, RAY_PRIMARY | RAY_SPECULAR, 0), 1, 0));
     }
 }
 
@@ -95,10 +95,10 @@ RT_D uint32_t child_node(uint32_t node, uint32_t branch) {
 struct RayOut { float3 o, d, w; float time; int sample, meta, node; float beer_s; };
 
 RT_D void write_ray(const DRayQueue& q, int slot, uint32_t pixel, const RayOut& r) {
-    q.o_time[slot] = make_float4(r.o.x, r.o.y, r.o.z, r.time);
-    q.d_tmax[slot] = make_float4(r.d.x, r.d.y, r.d.z, 3.0e38f);
-    q.w_pixel[slot] = make_float4(r.w.x, r.w.y, r.w.z, __int_as_float((int)pixel));
-    q.meta[slot] = make_int4(r.sample, r.meta, r.node, __float_as_int(r.beer_s));
+    RT_QST(q.o_time + slot, make_float4(r.o.x, r.o.y, r.o.z, r.time));
+    RT_QST(q.d_tmax + slot, make_float4(r.d.x, r.d.y, r.d.z, 3.0e38f));
+    RT_QST(q.w_pixel + slot, make_float4(r.w.x, r.w.y, r.w.z, __int_as_float((int)pixel)));
+    RT_QST(q.meta + slot, make_int4(r.sample, r.meta, r.node, __float_as_int(r.beer_s)));
 }
 
 // 6 resident CTAs (80 registers, 68 bytes spilled): C4 shade stage 10.99 -> 10.34 ms; 5 CTAs (96 registers, no spills) 10.99; 4 CTAs 12.70
@@ -151,8 +151,8 @@ __global__ void __launch_bounds__(kBlock, LOOP ? 4 : RT795_SHADE_MIN_BLOCKS) k_s
     uint32_t pixel = 0, sample = 0, node = 0;
 
     if (active) {
-        float4 ot = in.o_time[i], dt = in.d_tmax[i], wp = in.w_pixel[i], hr = in.hit[i];
-        int4 me = in.meta[i];
+        float4 ot = RT_QLD(in.o_time + i), dt = RT_QLD(in.d_tmax + i), wp = RT_QLD(in.w_pixel + i), hr = RT_QLD(in.hit + i);
+        int4 me = RT_QLD(in.meta + i);
         float3 ro = v3(ot);
         rd = v3(dt); rtime = ot.w;
         W = v3(wp);
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kBlock, LOOP ? 4 : RT795_SHADE_MIN_BLOCKS) k_s
         uint32_t flags = ((uint32_t)me.y >> 8) & 0xffu;
         int beer_mat = (int)((uint32_t)me.y >> 16);
         HitRec h;
-        h.t = hr.x; h.beta = hr.y; h.gamma = hr.z; h.prim = __float_as_int(hr.w); h.obj = in.hit_obj[i];
+        h.t = hr.x; h.beta = hr.y; h.gamma = hr.z; h.prim = __float_as_int(hr.w); h.obj = RT_QLD(in.hit_obj + i);
 
         if (flags & RAY_DEAD) {
             // level-0 slot outside the image (fused raygen): nothing to shade
@@ -371,9 +371,9 @@ __global__ void __launch_bounds__(kBlock, LOOP ? 4 : RT795_SHADE_MIN_BLOCKS) k_s
                 if (slot >= rc.shadow_cap) atomicExch(io.overflow, 1);
                 else {
                     float3 so = s.P + s.N * sc.shadow_eps;
-                    sq.o_time[slot] = make_float4(so.x, so.y, so.z, rtime);
-                    sq.d_tmax[slot] = make_float4(ls.wi.x, ls.wi.y, ls.wi.z, ls.tmax);
-                    sq.c_pixel[slot] = make_float4(c.x, c.y, c.z, __int_as_float((int)pixel));
+                    RT_QST(sq.o_time + slot, make_float4(so.x, so.y, so.z, rtime));
+                    RT_QST(sq.d_tmax + slot, make_float4(ls.wi.x, ls.wi.y, ls.wi.z, ls.tmax));
+                    RT_QST(sq.c_pixel + slot, make_float4(c.x, c.y, c.z, __int_as_float((int)pixel)));
                 }
             }
         }

@@ -27,6 +27,16 @@ constexpr int kSentinel = 0x7fffffff;
 constexpr int kNoChildDev = 0x7ffffffd; // == rt795::kNoChild (bvh_build.h)
 
 RT_D float4 ldg4(const float4* p) { return __ldg(p); }
+// Ray-queue records are written once and read once (they stream through L2, ~700 MB per wave against the 60 MB scene): they are
+// marked evict-first (ld.global.cs / st.global.cs) so that they displace less of the scene.  C4 50.6 -> 50.3 ms, C2 29.8 -> 29.4
+// (profiles/bench/r02_ab_stream_hints.txt); -DRT795_NO_STREAM_HINTS builds the plain loads / stores.
+#ifndef RT795_NO_STREAM_HINTS
+#define RT_QLD(P) __ldcs(P)
+#define RT_QST(P, V) __stcs((P), (V))
+#else
+#define RT_QLD(P) (*(P))
+#define RT_QST(P, V) (*(P) = (V))
+#endif
 // 32 bytes in one instruction (LDG.E.256, sm_100): two adjacent float4s of a 32-byte-aligned pair
 RT_D void ldg8(const float4* p, float4& a, float4& b) {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"

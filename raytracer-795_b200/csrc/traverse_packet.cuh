@@ -36,10 +36,10 @@ __global__ void __launch_bounds__(128, 7) k_raygen_trace_packet(DScene sc, Trace
         if (live) {
             uint32_t pixel = 0, sample = 0;
             bool in_image = gen_camera_ray(rg, rayidx, wo, wd, time, pixel, sample);
-            io.q.o_time[rayidx] = make_float4(wo.x, wo.y, wo.z, time);
-            io.q.d_tmax[rayidx] = make_float4(wd.x, wd.y, wd.z, 3.0e38f);
-            io.q.w_pixel[rayidx] = make_float4(1.f, 1.f, 1.f, __int_as_float((int)pixel));
-            io.q.meta[rayidx] = make_int4((int)sample, meta_pack(rg.max_depth, in_image ? (RAY_PRIMARY | RAY_SPECULAR) : RAY_DEAD, 0), 1, 0);
+            RT_QST(io.q.o_time + rayidx, make_float4(wo.x, wo.y, wo.z, time));
+            RT_QST(io.q.d_tmax + rayidx, make_float4(wd.x, wd.y, wd.z, 3.0e38f));
+            RT_QST(io.q.w_pixel + rayidx, make_float4(1.f, 1.f, 1.f, __int_as_float((int)pixel)));
+            RT_QST(io.q.meta + rayidx, make_int4((int)sample, meta_pack(rg.max_depth, in_image ? (RAY_PRIMARY | RAY_SPECULAR) : RAY_DEAD, 0), 1, 0));
             live = in_image && !any_nan(wo) && !any_nan(wd);               // src/Helper.cpp:28-30: NaN ray = no hit
         }
         const bool record = base + (int)lane < total;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(128, 7) k_raygen_trace_packet(DScene sc, Trace
         }
 #undef PK_POP
 #undef PK_SET_RAY
-        if (record) { io.q.hit[rayidx] = make_float4(live ? tmax : 0.f, hb, hg, __int_as_float(hprim)); io.q.hit_obj[rayidx] = hobj; }
+        if (record) { RT_QST(io.q.hit + rayidx, make_float4(live ? tmax : 0.f, hb, hg, __int_as_float(hprim))); RT_QST(io.q.hit_obj + rayidx, hobj); }
     }
 }
 

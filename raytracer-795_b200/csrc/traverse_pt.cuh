@@ -203,12 +203,12 @@ RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const 
         if (ANY_HIT) {
             bool add = idle && rayidx >= 0 && hprim < 0;   // unoccluded: the light's contribution reaches the pixel
             float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (add) c = __ldg(io.sq.c_pixel + rayidx);
+            if (add) c = RT_QLD(io.sq.c_pixel + rayidx);
             warp_accum(io.accum, add, (uint32_t)__float_as_int(c.w), v3(c));
             if (idle) rayidx = -1;
         } else if (idle && rayidx >= 0) {
-            if (EXACT) { io.q.hit[rayidx] = make_float4(g_t, g_b, g_g, __int_as_float(g_prim)); io.q.hit_obj[rayidx] = g_obj; }
-            else { io.q.hit[rayidx] = make_float4(tmax, hb, hg, __int_as_float(hprim)); io.q.hit_obj[rayidx] = hobj; }
+            if (EXACT) { RT_QST(io.q.hit + rayidx, make_float4(g_t, g_b, g_g, __int_as_float(g_prim))); RT_QST(io.q.hit_obj + rayidx, g_obj); }
+            else { RT_QST(io.q.hit + rayidx, make_float4(tmax, hb, hg, __int_as_float(hprim))); RT_QST(io.q.hit_obj + rayidx, hobj); }
             rayidx = -1;
         }
         unsigned m = __ballot_sync(full, idle);
@@ -253,12 +253,12 @@ RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const 
                     uint32_t pixel = 0, sample = 0;
                     live = gen_camera_ray(*rg, rayidx, wo, wd, time, pixel, sample);
                     tmax = 3.0e38f;
-                    io.q.o_time[rayidx] = make_float4(wo.x, wo.y, wo.z, time);
-                    io.q.d_tmax[rayidx] = make_float4(wd.x, wd.y, wd.z, 3.0e38f);
-                    io.q.w_pixel[rayidx] = make_float4(1.f, 1.f, 1.f, __int_as_float((int)pixel));
-                    io.q.meta[rayidx] = make_int4((int)sample, meta_pack(rg->max_depth, live ? (RAY_PRIMARY | RAY_SPECULAR) : RAY_DEAD, 0), 1, 0);
+                    RT_QST(io.q.o_time + rayidx, make_float4(wo.x, wo.y, wo.z, time));
+                    RT_QST(io.q.d_tmax + rayidx, make_float4(wd.x, wd.y, wd.z, 3.0e38f));
+                    RT_QST(io.q.w_pixel + rayidx, make_float4(1.f, 1.f, 1.f, __int_as_float((int)pixel)));
+                    RT_QST(io.q.meta + rayidx, make_int4((int)sample, meta_pack(rg->max_depth, live ? (RAY_PRIMARY | RAY_SPECULAR) : RAY_DEAD, 0), 1, 0));
                 } else {
-                    float4 ot = q_o[rayidx], dt = q_d[rayidx];
+                    float4 ot = RT_QLD(q_o + rayidx), dt = RT_QLD(q_d + rayidx);
                     if (io.flags & 4) {
                         // the queue is streamed once from HBM and every lane of the warp waits here for its record (ncu r2d: 6.7 % of
                         // the occlusion kernel's samples sit on the first use of `ot`): pull the records that will be fetched
