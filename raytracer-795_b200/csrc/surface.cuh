@@ -50,13 +50,23 @@ RT_D float perlin_weight(float x) {
 }
 // Perlin::ComputePerlin, src/Perlin.cpp:52-84.  Same corner order and the same per-corner arithmetic
 // (dot(g, d) * ((wx*wy)*wz), accumulated i-major, k-minor); only the shared sub-expressions (per-axis weights, the
-// nested permutation lookups) are evaluated once instead of once per corner.
-RT_D float perlin(float3 p, float scale, int nc) {
-    float3 pt = p * scale;
-    int ii = (int)floorf(pt.x), jj = (int)floorf(pt.y), kk = (int)floorf(pt.z);
-    float dx[2] = {pt.x - (float)ii, pt.x - (float)(ii + 1)}, dy[2] = {pt.y - (float)jj, pt.y - (float)(jj + 1)}, dz[2] = {pt.z - (float)kk, pt.z - (float)(kk + 1)};
-    float wx[2] = {perlin_weight(dx[0]), perlin_weight(dx[1])}, wy[2] = {perlin_weight(dy[0]), perlin_weight(dy[1])}, wz[2] = {perlin_weight(dz[0]), perlin_weight(dz[1])};
+// nested permutation lookups) are evaluated once instead of once per corner.  Split in three so that the bump gradient
+// below can share what its four evaluations have in common:
+//   perlin_codes: the eight corner gradient indices of a lattice cell, 4 bits each (corner c = 4i + 2j + k in bits 4c..4c+3)
+//   perlin_sum:   the weighted corner sum            perlin_convert: the <NoiseConversion>
+RT_D unsigned perlin_codes(int ii, int jj, int kk) {
     int pz[2] = {perlin_shuffled(kk), perlin_shuffled(kk + 1)};
+    unsigned codes = 0u;
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+                codes |= (unsigned)perlin_shuffled(ii + i + perlin_shuffled(jj + j + pz[k])) << (4 * (4 * i + 2 * j + k));
+    return codes;
+}
+RT_D float perlin_sum(unsigned codes, const float* dx, const float* dy, const float* dz, const float* wx, const float* wy, const float* wz) {
     float value = 0.f;
 #pragma unroll
     for (int i = 0; i < 2; i++)
@@ -64,20 +74,47 @@ RT_D float perlin(float3 p, float scale, int nc) {
         for (int j = 0; j < 2; j++)
 #pragma unroll
             for (int k = 0; k < 2; k++) {
-                int idx = perlin_shuffled(ii + i + perlin_shuffled(jj + j + pz[k]));
-                float3 g = perlin_grad(idx);
+                float3 g = perlin_grad((int)((codes >> (4 * (4 * i + 2 * j + k))) & 15u));
                 value += dot(g, v3(dx[i], dy[j], dz[k])) * (wx[i] * wy[j] * wz[k]);
             }
+    return value;
+}
+RT_D float perlin_convert(float value, int nc) {
     if (nc == RT_NC_LINEAR) value = (value + 1.0f) * 0.5f;
     else if (nc == RT_NC_ABSVAL) value = fabsf(value);
     return value;
 }
+// one axis of a sample point: lattice index, the two offsets and their weights
+RT_D void perlin_axis(float x, int& cell, float* d, float* w) {
+    cell = (int)floorf(x);
+    d[0] = x - (float)cell; d[1] = x - (float)(cell + 1);
+    w[0] = perlin_weight(d[0]); w[1] = perlin_weight(d[1]);
+}
+RT_D float perlin(float3 p, float scale, int nc) {
+    float3 pt = p * scale;
+    int ii, jj, kk;
+    float dx[2], dy[2], dz[2], wx[2], wy[2], wz[2];
+    perlin_axis(pt.x, ii, dx, wx); perlin_axis(pt.y, jj, dy, wy); perlin_axis(pt.z, kk, dz, wz);
+    return perlin_convert(perlin_sum(perlin_codes(ii, jj, kk), dx, dy, dz, wx, wy, wz), nc);
+}
+// Bump gradient by forward differences (src/Shape.cpp:486-494: four ComputePerlin calls, eps = 0.001).  The three displaced points
+// differ from p in one coordinate, by much less than a lattice cell: each re-evaluates only that axis (offsets + weights) and re-uses
+// the other two axes and - unless it crossed into the next cell - the cell's eight gradient indices.  Same values as four full
+// evaluations (same expressions per corner), about 40 % of their instructions.
 RT_D float3 perlin_gradient(float3 p, float scale, int nc) {
     const float eps = 0.001f;
-    float v0 = perlin(p, scale, nc);
-    float x = (perlin(v3(p.x + eps, p.y, p.z), scale, nc) - v0) / eps;
-    float y = (perlin(v3(p.x, p.y + eps, p.z), scale, nc) - v0) / eps;
-    float z = (perlin(v3(p.x, p.y, p.z + eps), scale, nc) - v0) / eps;
+    float3 pt = p * scale;
+    int ii, jj, kk, c2;
+    float dx[2], dy[2], dz[2], wx[2], wy[2], wz[2], d2[2], w2[2];
+    perlin_axis(pt.x, ii, dx, wx); perlin_axis(pt.y, jj, dy, wy); perlin_axis(pt.z, kk, dz, wz);
+    const unsigned codes = perlin_codes(ii, jj, kk);
+    float v0 = perlin_convert(perlin_sum(codes, dx, dy, dz, wx, wy, wz), nc);
+    perlin_axis((p.x + eps) * scale, c2, d2, w2);
+    float x = (perlin_convert(perlin_sum(c2 == ii ? codes : perlin_codes(c2, jj, kk), d2, dy, dz, w2, wy, wz), nc) - v0) / eps;
+    perlin_axis((p.y + eps) * scale, c2, d2, w2);
+    float y = (perlin_convert(perlin_sum(c2 == jj ? codes : perlin_codes(ii, c2, kk), dx, d2, dz, wx, w2, wz), nc) - v0) / eps;
+    perlin_axis((p.z + eps) * scale, c2, d2, w2);
+    float z = (perlin_convert(perlin_sum(c2 == kk ? codes : perlin_codes(ii, jj, c2), dx, dy, d2, wx, wy, w2), nc) - v0) / eps;
     return v3(x, y, z);
 }
 
