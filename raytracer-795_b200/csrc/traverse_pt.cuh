@@ -333,19 +333,12 @@ RT_D void trace_body(const DScene& sc, const TraceIO& io, DCounters* ctr, const 
                             const float4* np = s_tlas + (node - sc.tlas_root4) * 8;
                             nx4 = np[sgx]; fx4 = np[1 - sgx]; ny4 = np[2 + sgy]; fy4 = np[3 - sgy]; nz4 = np[4 + sgz]; fz4 = np[5 - sgz]; cr = np[6];
                         } else {
-                            const float4* np = sc.nodes4 + (size_t)node * 8;
 #if defined(RT795_NODES256)
                             // experiment: 256-byte node with (lo,hi) and (hi,lo) of every axis: 3 x LDG.256 picked by address + 1 x LDG.128
                             const float4* xp = sc.nodes4x + (size_t)node * 16;
                             ldg8(xp + 2 * sgx, nx4, fx4); ldg8(xp + 4 + 2 * sgy, ny4, fy4); ldg8(xp + 8 + 2 * sgz, nz4, fz4); cr = ldg4(xp + 12);
-#elif defined(RT795_LDG256)
-                            // experiment: 3 x LDG.256 (lo and hi of an axis in one load) + selects, instead of 6 x LDG.128 picked by address
-                            float4 lx, hx, ly, hy, lz, hz;
-                            ldg8(np, lx, hx); ldg8(np + 2, ly, hy); ldg8(np + 4, lz, hz); cr = ldg4(np + 6);
-#define RT_SEL4(N, F, L, H, S) N = make_float4(S ? H.x : L.x, S ? H.y : L.y, S ? H.z : L.z, S ? H.w : L.w); F = make_float4(S ? L.x : H.x, S ? L.y : H.y, S ? L.z : H.z, S ? L.w : H.w);
-                            RT_SEL4(nx4, fx4, lx, hx, sgx) RT_SEL4(ny4, fy4, ly, hy, sgy) RT_SEL4(nz4, fz4, lz, hz, sgz)
-#undef RT_SEL4
 #else
+                            const float4* np = sc.nodes4 + (size_t)node * 8;
                             nx4 = ldg4(np + sgx); fx4 = ldg4(np + (1 - sgx)); ny4 = ldg4(np + 2 + sgy); fy4 = ldg4(np + (3 - sgy));
                             nz4 = ldg4(np + 4 + sgz); fz4 = ldg4(np + (5 - sgz)); cr = ldg4(np + 6);
 #endif
