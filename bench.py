@@ -199,7 +199,13 @@ def run_reference_arm(args):
     full_kw, sample_kw = WORKLOADS[args.config]
     if args.small:
         sample_kw = SMOKE_WORKLOADS[args.config]
-    xml = make_scene(scenes, args.config, sample_kw, "refsample_small" if args.small else "refsample")
+    tag = "refsample_small" if args.small else "refsample"
+    if not args.small and args.steps + args.warmup > 12 and sample_kw.get("spp", 1) > 1:
+        # a C4 frame at 1920x1080 costs the reference ~7 s per sample per pixel on the box's cores: with the driver's 20 + 5 frames the
+        # per-step sample drops to 1 spp so that the whole run stays within a few minutes (same scene, same resolution, same ray mix)
+        sample_kw = dict(sample_kw, spp=1)
+        tag = "refsample_spp1"
+    xml = make_scene(scenes, args.config, sample_kw, tag)
     secs, qs, kind, cores = run_reference_frames(xml, args.warmup + args.steps)
     secs, qs = secs[args.warmup:], qs[args.warmup:]
     ms = 1e3 * float(np.mean(secs))
